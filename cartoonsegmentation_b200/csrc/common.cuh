@@ -1,0 +1,78 @@
+// Shared host/device helpers for libcsb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/csb200.h"
+
+namespace csb {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+// Per-kernel profiling (csb_profile_begin/end): when on, a CUDA event is recorded on the launching stream after every
+// launch; consecutive events bracket each kernel (kernels of one stream run back to back).
+void profile_mark(const char* what, cudaStream_t st);
+extern std::atomic<int> g_profiling;
+
+// Call after every kernel launch: counts it and converts a launch error into a status.
+inline int launched(const char* what, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CSB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    if (g_profiling.load(std::memory_order_relaxed)) profile_mark(what, st);
+    return CSB_OK;
+}
+
+// memsets issued by the library are not counted as launches but must be visible to the profiler
+inline void memset_done(cudaStream_t st) {
+    if (g_profiling.load(std::memory_order_relaxed)) profile_mark("memset", st);
+}
+
+inline int cuda_ok(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) return fail(CSB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return CSB_OK;
+}
+
+#define CSB_REQUIRE(cond, msg)                                        \
+    do {                                                              \
+        if (!(cond)) return csb::fail(CSB_ERR_INVALID, "%s: %s", __func__, msg); \
+    } while (0)
+
+#define CSB_TRY(expr)                  \
+    do {                               \
+        int _st = (expr);              \
+        if (_st != CSB_OK) return _st; \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Grid for a grid-stride kernel: a whole number of waves (multiple of the SM count), capped by the work.
+inline int wave_grid(long long work_items, int threads, int ctas_per_sm) {
+    long long need = (work_items + threads - 1) / threads;
+    long long wave = (long long) num_sms() * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int) (need < wave ? need : wave);
+}
+
+}  // namespace csb

@@ -1,0 +1,164 @@
+// Ken-Burns frame tail for sm_100a (anime_3dkenburns/kenburns_effect.py:1028-1040, 1069-1070):
+//   k_pack_u8          (render*255).clip(0,255).astype(uint8), CHW -> HWC                                  (:1040)
+//   k_crop_resize      cv2.getRectSubPix (16-bit fixed point) + cv2.resize INTER_LINEAR (11-bit fixed point) (:1069-1070)
+//   k_norm_fill_pack   normalise (models/utils.py:315) + mask depth (:1039) + fill_disocclusion (common.py:149-245) + pack,
+//                      reading the interleaved render accumulator once -- the float render/existing/filled tensors of the
+//                      reference (4 full-resolution fp32 tensors per frame) never touch HBM.
+// The reference does the pack on the host after a D2H of the float frame and the crop/resize in OpenCV on the CPU; the
+// integer arithmetic below reproduces OpenCV's uint8 paths bit for bit (pinned against cv2 in tests/test_oracle_cpu.py).
+#include "kb_fill.cuh"
+
+int csb_render_accumulate(const float* points, const float* data, int B, int N, int C, int H, int W, double focal, double baseline,
+                          const float* shift, const float* shift_dev, int32_t* zkey, float* zee, float* acc, cudaStream_t st);
+
+namespace {
+
+__device__ __forceinline__ uint8_t pack1(float v) {
+    v = __fmul_rn(v, 255.0f);
+    v = fminf(fmaxf(v, 0.0f), 255.0f);      // NaN -> 0 (fmaxf returns the non-NaN operand)
+    return (uint8_t) (int) v;               // truncation, numpy astype
+}
+
+// 15 B/px
+__global__ void __launch_bounds__(256) k_pack_u8(const float* __restrict__ render, long long HW, uint8_t* __restrict__ frame) {
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < HW; i += (long long) gridDim.x * blockDim.x) {
+        frame[i * 3 + 0] = pack1(render[i]);
+        frame[i * 3 + 1] = pack1(render[HW + i]);
+        frame[i * 3 + 2] = pack1(render[2 * HW + i]);
+    }
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+struct CropParams {
+    int ipx, ipy, a11, a12, a21, a22, pw, ph;
+    double sx, sy;
+};
+
+// getRectSubPix_Cn_<uchar,uchar,int,scale_fixpt,cast_8u> (OpenCV samplers.cpp), one crop pixel, 3 channels.
+__device__ __forceinline__ void crop_px(const uint8_t* __restrict__ src, int H, int W, const CropParams& p, int x, int y, int (&o)[3]) {
+    int y0 = clampi(p.ipy + y, 0, H - 1), y1 = clampi(p.ipy + y + 1, 0, H - 1);
+    int x0 = clampi(p.ipx + x, 0, W - 1), x1 = clampi(p.ipx + x + 1, 0, W - 1);
+    const uint8_t *r00 = src + ((size_t) y0 * W + x0) * 3, *r01 = src + ((size_t) y0 * W + x1) * 3;
+    const uint8_t *r10 = src + ((size_t) y1 * W + x0) * 3, *r11 = src + ((size_t) y1 * W + x1) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int t = r00[c] * p.a11 + r01[c] * p.a12 + r10[c] * p.a21 + r11[c] * p.a22;
+        o[c] = (t + (1 << 15)) >> 16;
+    }
+}
+
+// resize.cpp: HResizeLinear<uchar,int,short,2048> + VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>.  6 B/px.
+__global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__ src, int H, int W, CropParams p, uint8_t* __restrict__ dst) {
+    const long long total = (long long) H * W;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        int dx = (int) (i % W), dy = (int) (i / W);
+        float fx = (float) ((dx + 0.5) * p.sx - 0.5);
+        int ix = (int) floorf(fx);
+        fx -= ix;
+        if (ix < 0) { fx = 0; ix = 0; }
+        if (ix >= p.pw - 1) { fx = 0; ix = p.pw - 1; }
+        int ax0 = (int) (short) __float2int_rn((1.f - fx) * 2048.f), ax1 = (int) (short) __float2int_rn(fx * 2048.f);
+        float fy = (float) ((dy + 0.5) * p.sy - 0.5);
+        int iy = (int) floorf(fy);
+        fy -= iy;
+        int y0 = clampi(iy, 0, p.ph - 1), y1 = clampi(iy + 1, 0, p.ph - 1);
+        int b0 = (int) (short) __float2int_rn((1.f - fy) * 2048.f), b1 = (int) (short) __float2int_rn(fy * 2048.f);
+        int x1 = ix + 1 < p.pw ? ix + 1 : ix;
+        int c00[3], c01[3], c10[3], c11[3];
+        crop_px(src, H, W, p, ix, y0, c00);
+        crop_px(src, H, W, p, x1, y0, c01);
+        crop_px(src, H, W, p, ix, y1, c10);
+        crop_px(src, H, W, p, x1, y1, c11);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int s0 = c00[c] * ax0 + c01[c] * ax1, s1 = c10[c] * ax0 + c11[c] * ax1;
+            int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+            dst[i * 3 + c] = (uint8_t) clampi(v, 0, 255);
+        }
+    }
+}
+
+// Fused normalise + depth mask + disocclusion fill + u8 pack for C = 4 (BGR + depth), CP = 8.
+// acc pixel = {b*w, g*w, r*w, depth*w, w, 0, 0, 0} (32 B, one sector).  18 B/px when depth_out is null.
+__global__ void __launch_bounds__(256) k_norm_fill_pack(const float* __restrict__ acc, int H, int W, uint8_t* __restrict__ frame,
+                                                        float* __restrict__ depth_out) {
+    const long long HW = (long long) H * W;
+    // masked depth of the composed reference path: render[3] * (existing > 0)   (kenburns_effect.py:1039)
+    auto depthv = [&](int yy, int xx) {
+        const float* A = acc + ((size_t) yy * W + xx) * 8;
+        float w = __ldg(A + 4);
+        float r = __fdiv_rn(__ldg(A + 3), __fadd_rn(w, 0.0000001f));
+        return __fmul_rn(r, w > 0.0f ? 1.0f : 0.0f);
+    };
+    auto valid = [&](int yy, int xx) { return depthv(yy, xx) > 0.0f; };
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < HW; i += (long long) gridDim.x * blockDim.x) {
+        const int x = (int) (i % W), y = (int) (i / W);
+        long long src = i;
+        if (!valid(y, x)) {
+            long long f = csbfill::find_fill(x, y, H, W, valid, depthv);
+            if (f >= 0) src = f;
+        }
+        const float4 q = __ldg(reinterpret_cast<const float4*>(acc + (size_t) src * 8));
+        const float w = __ldg(acc + (size_t) src * 8 + 4);
+        const float d = __fadd_rn(w, 0.0000001f);
+        frame[i * 3 + 0] = pack1(__fdiv_rn(q.x, d));
+        frame[i * 3 + 1] = pack1(__fdiv_rn(q.y, d));
+        frame[i * 3 + 2] = pack1(__fdiv_rn(q.z, d));
+        if (depth_out) depth_out[i] = __fdiv_rn(q.w, d);
+    }
+}
+
+int make_crop(int H, int W, int pw, int ph, double cx, double cy, CropParams& p) {
+    if (pw <= 0 || ph <= 0) return CSB_ERR_INVALID;
+    float fcx = (float) cx, fcy = (float) cy;
+    fcx -= (pw - 1) * 0.5f;
+    fcy -= (ph - 1) * 0.5f;
+    p.ipx = (int) floor(fcx);
+    p.ipy = (int) floor(fcy);
+    float a = fcx - p.ipx, b = fcy - p.ipy;
+    p.a11 = (int) lrint((double) ((1.f - a) * (1.f - b)) * 65536.0);
+    p.a12 = (int) lrint((double) (a * (1.f - b)) * 65536.0);
+    p.a21 = (int) lrint((double) ((1.f - a) * b) * 65536.0);
+    p.a22 = (int) lrint((double) (a * b) * 65536.0);
+    p.pw = pw;
+    p.ph = ph;
+    p.sx = 1.0 / ((double) W / pw);
+    p.sy = 1.0 / ((double) H / ph);
+    return CSB_OK;
+}
+
+}  // namespace
+
+extern "C" int csb_frame_pack_u8(const float* render, int H, int W, uint8_t* frame, void* stream) {
+    CSB_REQUIRE(render && frame, "null pointer");
+    CSB_REQUIRE(H > 0 && W > 0, "bad shape");
+    k_pack_u8<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(render, (long long) H * W, frame);
+    return csb::launched("k_pack_u8", (cudaStream_t) stream);
+}
+
+extern "C" int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, int ph, double cx, double cy, uint8_t* out, void* stream) {
+    CSB_REQUIRE(frame && out && frame != out, "null or aliased pointer");
+    CSB_REQUIRE(H > 0 && W > 0, "bad shape");
+    CropParams p;
+    CSB_REQUIRE(make_crop(H, W, pw, ph, cx, cy, p) == CSB_OK, "bad crop size");
+    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(frame, H, W, p, out);
+    return csb::launched("k_crop_resize", (cudaStream_t) stream);
+}
+
+extern "C" int csb_kenburns_frame(const float* points, const float* data, int N, int H, int W, double focal, double baseline,
+                                  const float* shift, const float* shift_dev, int pw, int ph, double cx, double cy, int32_t* zkey,
+                                  float* zee, float* acc,
+                                  uint8_t* packed, uint8_t* out, float* depth_out, void* stream) {
+    CSB_REQUIRE(points && data && zkey && zee && acc && packed && out, "null pointer");
+    CSB_REQUIRE(N >= 0 && H > 0 && W > 0, "bad shape");
+    CSB_REQUIRE(((uintptr_t) acc & 15) == 0, "acc must be 16-byte aligned");
+    CropParams p;
+    CSB_REQUIRE(make_crop(H, W, pw, ph, cx, cy, p) == CSB_OK, "bad crop size");
+    cudaStream_t st = (cudaStream_t) stream;
+    CSB_TRY(csb_render_accumulate(points, data, 1, N, 4, H, W, focal, baseline, shift, shift_dev, zkey, zee, acc, st));
+    k_norm_fill_pack<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(acc, H, W, packed, depth_out);
+    CSB_TRY(csb::launched("k_norm_fill_pack", st));
+    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, out);
+    return csb::launched("k_crop_resize", st);
+}

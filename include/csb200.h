@@ -1,0 +1,125 @@
+/*
+ * csb200.h -- C ABI of libcsb200.so, the B200 (sm_100a) replacement for the reference's
+ * kernel-JIT operator boundary.
+ *
+ * What it replaces (paths relative to the reference repo):
+ *   utils/cupy_utils.py:7-13   launch_kernel(name, src)(grid=, block=, args=[int32 n, tensor.data_ptr(), ...])
+ *                              -- a cupy.RawKernel launch on raw device pointers of contiguous torch tensors.
+ *   The five call sites of that boundary are listed next to each entry point below.
+ *
+ * Conventions
+ *   - every entry point returns an int status (CSB_OK == 0) and enqueues all of its work on `stream`
+ *     (a cudaStream_t passed as void*; the Python side passes torch.cuda.current_stream().cuda_stream).
+ *     No entry point synchronises, allocates or frees device memory, or reads results back to the host:
+ *     the caller owns every buffer including scratch, so a whole frame is CUDA-graph capturable.
+ *   - all tensors are contiguous fp32 unless stated, layouts as in the reference
+ *     (points [B,3,N] channel-planar, images [B,C,H,W]).
+ *   - errors: non-zero status, message via csb_last_error() (thread-local).  Kernels never assert/trap
+ *     (the reference kernels use device-side assert, anime_3dkenburns/models/utils.py:73-74).
+ */
+#ifndef CSB200_H
+#define CSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSB_API __attribute__((visibility("default")))
+
+#define CSB_OK 0
+#define CSB_ERR_INVALID 1   /* bad shape / null pointer / misaligned buffer */
+#define CSB_ERR_CUDA 2      /* a CUDA runtime call failed; see csb_last_error() */
+#define CSB_ERR_ARCH 3      /* device is not sm_100 */
+
+CSB_API int csb_version(void);
+CSB_API const char* csb_last_error(void);
+/* Number of kernel launches this library has enqueued since load (process-wide, monotonic). */
+CSB_API uint64_t csb_launch_count(void);
+/* Per-kernel device timing for bench.py's roofline: between begin and end every launch is followed by a CUDA event on
+ * its stream; end() synchronises and writes {"kernel": {"ms": total, "count": launches}, ...} into json. */
+CSB_API int csb_profile_begin(void* stream);
+CSB_API int csb_profile_end(char* json, size_t cap);
+
+/* ---------------------------------------------------------------------------------------------
+ * render_pointcloud -- anime_3dkenburns/models/utils.py:56-315 (kernel_pointrender_updateZee :63-149,
+ * kernel_pointrender_updateDegrid :152-212, kernel_pointrender_updateOutput :215-313, host tail :315),
+ * with process_shift's tensor part (anime_3dkenburns/common.py:76-81) optionally folded in.
+ *
+ *   points  [B,3,N]   data [B,C,N]                      (inputs, read-only)
+ *   shift   3 host floats (sx,sy,sz) or NULL: when given, every point is first transformed exactly as
+ *           common.py:78-81 does:  x = x*(z/(z+1e-7)) + sx, y likewise, z = z + sz
+ *   shift_dev  the same 3 floats in DEVICE memory (takes precedence), e.g. written by csb_shift_from_scalars,
+ *           so a pipeline never has to read the depth range back to the host
+ *   zkey    [B,H,W] int32 scratch       zee [B,H,W] fp32 scratch (post-degrid z-buffer; also an output for tests)
+ *   acc     [B,H,W,CP] fp32 scratch, CP = csb_render_acc_channels(C) (channel-interleaved accumulator)
+ *   render  [B,C,H,W]  existing [B,1,H,W]               (outputs; either may be NULL to skip)
+ * ------------------------------------------------------------------------------------------- */
+CSB_API int csb_render_acc_channels(int C);
+CSB_API int csb_pointcloud_render(const float* points, const float* data, int B, int N, int C, int H, int W,
+                          double focal, double baseline, const float* shift, const float* shift_dev,
+                          int32_t* zkey, float* zee, float* acc, float* render, float* existing, void* stream);
+/* The three stages on their own (tests pin each against the reference kernel of the same name). */
+CSB_API int csb_pointcloud_zpass(const float* points, int B, int N, int H, int W, double focal, double baseline,
+                         const float* shift, int32_t* zkey, void* stream);
+CSB_API int csb_pointcloud_degrid(const int32_t* zkey, int B, int H, int W, float* zee, void* stream);
+
+/* Autozoom score -- anime_3dkenburns/common.py:116-131: for each of S candidate shifts, render the raw point
+ * cloud and count pixels with tenExisting > 0.  Only coverage is needed, so no colour is splatted.
+ *   shifts [S,3] host floats;  zkey [S,H,W] int32 scratch;  zee [S,H,W] fp32 scratch; cover [S,H,W] uint8 scratch;
+ *   counts [S] int32 device output (stays on device; the caller reads it once). */
+CSB_API int csb_autozoom_coverage(const float* points, int N, int H, int W, double focal, double baseline,
+                          const float* shifts, int S, int32_t* zkey, float* zee, uint8_t* cover, int32_t* counts,
+                          void* stream);
+
+/* fill_disocclusion -- anime_3dkenburns/common.py:145-247 (kernel_discfill_updateOutput :149-245).
+ *   input [B,C,H,W], depth [B,1,H,W] -> output [B,C,H,W] (output may not alias input). */
+CSB_API int csb_disocclusion_fill(const float* input, const float* depth, int B, int C, int H, int W, float* output, void* stream);
+
+/* process_shift scalar part -- anime_3dkenburns/common.py:60-72, evaluated on the device in double precision from the
+ * `scalars` written by csb_disparity_to_cloud (closest point = argmin of the depth crop): fltShiftU/V as in the reference,
+ * fltDepthFrom = depthmin, fltDepthTo = depthmin * depth_ratio.  shift_dev: 3 device floats. */
+CSB_API int csb_shift_from_scalars(const float* scalars, int W, int H, double focal, double shiftU, double shiftV, double depth_ratio,
+                           float* shift_dev, void* stream);
+
+/* process_shift tensor part -- anime_3dkenburns/common.py:76-81.  shift = 3 host floats. */
+CSB_API int csb_points_shift(const float* points, int B, int N, const float* shift, float* out, void* stream);
+
+/* depth_to_points -- anime_3dkenburns/models/utils.py:43-50.  depth [B,1,H,W] -> points [B,3,H,W]. */
+CSB_API int csb_depth_to_points(const float* depth, int B, int H, int W, double focal, float* points, void* stream);
+
+/* spatial_filter -- anime_3dkenburns/models/utils.py:9-40.  kind: 0 'laplacian', 3 'median-3', 5 'median-5'. */
+CSB_API int csb_spatial_filter(const float* input, int B, int C, int H, int W, int kind, float* output, void* stream);
+
+/* generate_kenburns_config math -- anime_3dkenburns/kenburns_effect.py:928-937, fused:
+ *   raw disparity [H,W] -> disparity, depth, valid [H,W]; points, unaltered [3,H,W];
+ *   scalars (device, 8 floats): dispmin, dispmax, depthmin, depthmax, argmin x,y, argmax x,y of depth[128:-128,128:-128]
+ *   (cv2.minMaxLoc tie rule: first occurrence in row-major order).  scratch: 64 uint64 (device).
+ *   Optional (both or neither): image_hwc [H,W,3] u8 BGR -> data4 [4,H*W] = {B,G,R}*float32(1/255) planar ++ depth, the
+ *   render payload the frame loop builds at kenburns_effect.py:921,1036. */
+CSB_API int csb_disparity_to_cloud(const float* raw, int H, int W, double focal, double baseline, float* disparity, float* depth,
+                           float* valid, float* points, float* unaltered, float* scalars, uint64_t* scratch,
+                           const uint8_t* image_hwc, float* data4, void* stream);
+
+/* Frame tail -- anime_3dkenburns/kenburns_effect.py:1040 ((x*255).clip(0,255).astype(uint8), CHW -> HWC)
+ * and :1069-1070 (cv2.getRectSubPix centre crop + cv2.resize INTER_LINEAR back to W x H, both on uint8 with
+ * OpenCV's fixed-point arithmetic).  render [>=3,H,W] fp32 (first three planes used).
+ *   csb_frame_pack_u8:      render -> frame [H,W,3] u8
+ *   csb_frame_crop_resize:  frame [H,W,3] u8 -> out [H,W,3] u8 (crop pw x ph around (cx,cy), resize to W x H) */
+CSB_API int csb_frame_pack_u8(const float* render, int H, int W, uint8_t* frame, void* stream);
+CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, int ph, double cx, double cy, uint8_t* out, void* stream);
+
+/* Fused Ken-Burns frame: shift + render (C=4: BGR + depth) + normalise + disocclusion fill + u8 pack, then
+ * crop+resize -- the body of the reference's frame loop, kenburns_effect.py:1028-1040,1069-1070, as 5 launches.
+ *   points [1,3,N], data [1,4,N]; scratch as csb_pointcloud_render (C=4); packed [H,W,3] u8 scratch;
+ *   out [H,W,3] u8;  depth_out [H,W] fp32 or NULL (filled depth plane, needed only by the bokeh stage). */
+CSB_API int csb_kenburns_frame(const float* points, const float* data, int N, int H, int W, double focal, double baseline,
+                       const float* shift, const float* shift_dev, int pw, int ph, double cx, double cy,
+                       int32_t* zkey, float* zee, float* acc, uint8_t* packed, uint8_t* out, float* depth_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSB200_H */

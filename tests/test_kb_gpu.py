@@ -1,0 +1,203 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars: z-buffer, degrid, disocclusion fill, autozoom counts, uint8 frame tail: bit exact.  Splat/normalise: the
+reference itself is order-dependent (fp32 atomicAdd), tolerance 1e-5 relative on the accumulators and 1e-4 absolute
+on the render (north star: 1e-3).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kb_oracle as orc
+from tests.kb_scene import BASELINE, FOCAL, make_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    from cartoonsegmentation_b200.anime_3dkenburns import common, kenburns_effect
+    from cartoonsegmentation_b200.anime_3dkenburns.models import utils
+    return utils, common, kenburns_effect
+
+
+def shifted(s, u=9.0, v=-5.0, zoom=0.92):
+    c = s['common']
+    return {'tenPoints': s['points'], 'fltShiftU': u, 'fltShiftV': v, 'fltDepthFrom': c['objDepthrange'][0], 'fltDepthTo': c['objDepthrange'][0] * zoom}
+
+
+@pytest.mark.parametrize("H,W,C,extra", [(64, 96, 4, 0), (64, 96, 3, 0), (128, 160, 4, 3000), (96, 64, 7, 0), (256, 256, 4, 5000)])
+def test_render_pointcloud_vs_oracle(ops, H, W, C, extra):
+    utils, common, _ = ops
+    s = make_scene(H, W, seed=H + C, extra_points=extra)
+    pts_o, _ = orc.process_shift(shifted(s), s['common'])
+    data = s['data'][:, :C] if C <= 4 else np.concatenate([s['data'], s['data'][:, :C - 4] * 0.5], 1)
+    r_o, e_o, z0_o, z1_o = orc.render_pointcloud(pts_o, data, W, H, FOCAL, BASELINE, return_zee=True)
+    pts_g, _ = common.process_shift({**shifted(s), 'tenPoints': cu(s['points'])}, s['common'])
+    assert np.array_equal(pts_g.cpu().numpy(), pts_o)                                    # process_shift: bit exact
+    z0_g, zkey = utils.render_zpass(pts_g, W, H, FOCAL, BASELINE)
+    assert np.array_equal(z0_g.cpu().numpy(), z0_o)                                      # z-pass: bit exact
+    assert np.array_equal(utils.render_degrid(zkey).cpu().numpy(), z1_o)                 # degrid: bit exact
+    r_g, e_g = utils.render_pointcloud(pts_g, cu(data), W, H, FOCAL, BASELINE)
+    np.testing.assert_allclose(e_g.cpu().numpy(), e_o, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r_g.cpu().numpy(), r_o, rtol=1e-4, atol=1e-4)
+    assert int((e_g > 0).sum()) == int((e_o > 0).sum())
+    # shift folded into the render == separate process_shift
+    sh = orc.shift_scalars(shifted(s), s['common'])
+    r_f, e_f = utils.render_pointcloud(cu(s['points']), cu(data), W, H, FOCAL, BASELINE, tenShift=np.array(sh, np.float32))
+    np.testing.assert_allclose(r_f.cpu().numpy(), r_o, rtol=1e-4, atol=1e-4)
+    assert torch.equal(e_f > 0, e_g > 0)
+
+
+def test_render_edge_cases(ops):
+    utils, _, _ = ops
+    H, W = 32, 48
+    # all points invalid (z = 0) -> nothing rendered; zee stays 1e6
+    pts = torch.zeros(1, 3, 100, device='cuda'); data = torch.rand(1, 4, 100, device='cuda')
+    r, e = utils.render_pointcloud(pts, data, W, H, FOCAL, BASELINE)
+    assert float(e.abs().max()) == 0.0 and float(r.abs().max()) == 0.0
+    z, _ = utils.render_zpass(pts, W, H, FOCAL, BASELINE)
+    assert float(z.min()) == 1000000.0
+    # empty cloud
+    r, e = utils.render_pointcloud(torch.zeros(1, 3, 0, device='cuda'), torch.zeros(1, 4, 0, device='cuda'), W, H, FOCAL, BASELINE)
+    assert float(e.abs().max()) == 0.0
+    # far out-of-frame, negative z, NaN, exactly-on-pixel points
+    p = np.array([[1e6, -1e6, 3.0, float('nan'), 0.0], [0.0, 5.0, 2.0, 1.0, 0.0], [600.0, 600.0, -5.0, 700.0, 512.0]], np.float32)[None]
+    d = np.arange(20, dtype=np.float32).reshape(1, 4, 5)
+    r_o, e_o = orc.render_pointcloud(p, d, W, H, FOCAL, BASELINE)
+    r, e = utils.render_pointcloud(cu(p), cu(d), W, H, FOCAL, BASELINE)
+    np.testing.assert_allclose(e.cpu().numpy(), e_o, atol=1e-6)
+    np.testing.assert_allclose(r.cpu().numpy(), r_o, atol=1e-4)
+    # batch of 2
+    s = make_scene(64, 96)
+    p2 = np.concatenate([s['points'], s['points'] * np.float32(1.01)], 0); d2 = np.concatenate([s['data'], s['data'][:, ::-1]], 0)
+    r_o, e_o = orc.render_pointcloud(p2, d2, 96, 64, FOCAL, BASELINE)
+    r, e = utils.render_pointcloud(cu(p2), cu(d2), 96, 64, FOCAL, BASELINE)
+    np.testing.assert_allclose(r.cpu().numpy(), r_o, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(e.cpu().numpy(), e_o, rtol=1e-5, atol=1e-6)
+    with pytest.raises(Exception):
+        utils.render_pointcloud(torch.zeros(1, 3, 4), torch.zeros(1, 4, 4), W, H, FOCAL, BASELINE)     # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("H,W", [(64, 96), (256, 256), (150, 130)])
+def test_fill_disocclusion_vs_oracle(ops, H, W):
+    utils, common, _ = ops
+    s = make_scene(H, W, seed=3)
+    pts_o, _ = orc.process_shift(shifted(s, 14.0, 8.0, 0.85), s['common'])
+    r_o, e_o = orc.render_pointcloud(pts_o, s['data'], W, H, FOCAL, BASELINE)
+    depth = r_o[:, 3:4] * (e_o > 0.0)
+    f_o = orc.fill_disocclusion(r_o, depth)
+    f_g = common.fill_disocclusion(cu(r_o), cu(depth))
+    assert (depth <= 0).sum() > 0
+    assert np.array_equal(f_g.cpu().numpy(), f_o)                                        # bit exact (powf tie-breaks included)
+    # no holes -> identity ; all holes -> unchanged
+    assert torch.equal(common.fill_disocclusion(cu(r_o), torch.ones(1, 1, H, W, device='cuda')), cu(r_o))
+    assert torch.equal(common.fill_disocclusion(cu(r_o), torch.zeros(1, 1, H, W, device='cuda')), cu(r_o))
+
+
+def test_points_ops_vs_oracle(ops):
+    utils, _, kb = ops
+    d = np.random.default_rng(0).uniform(1, 2000, (2, 1, 37, 53)).astype(np.float32)
+    assert np.array_equal(utils.depth_to_points(cu(d), FOCAL).cpu().numpy(), orc.depth_to_points(d, FOCAL))
+    assert np.array_equal(utils.depth_to_points(cu(d), 300.0).cpu().numpy(), orc.depth_to_points(d, 300.0))
+    x = np.random.default_rng(1).uniform(0, 1, (1, 3, 41, 29)).astype(np.float32)
+    for t in ('laplacian', 'median-3', 'median-5'):
+        assert np.array_equal(utils.spatial_filter(cu(x), t).cpu().numpy(), orc.spatial_filter(x, t)), t
+    assert utils.spatial_filter(cu(x), 'bogus') is None
+    for (H, W) in [(300, 290), (64, 96)]:
+        s = make_scene(H, W, seed=5)
+        g = kb.disparity_to_cloud(cu(s['raw']), FOCAL, BASELINE)
+        o = s['cloud']
+        for k in ('disparity', 'depth', 'valid', 'points', 'unaltered'):
+            assert np.array_equal(g[k].cpu().numpy().reshape(o[k].shape), o[k]), k
+        assert g['dispmin'] == o['dispmin'] and g['dispmax'] == o['dispmax']
+        if H > 256:
+            assert g['depthrange'] == o['depthrange']
+
+
+def test_autozoom_vs_oracle(ops):
+    _, common, _ = ops
+    H, W = 64, 96
+    s = make_scene(H, W, seed=11)
+    c = dict(s['common'])
+    objFrom = {'fltCenterU': W / 2.0, 'fltCenterV': H / 2.0, 'intCropWidth': int(np.floor(0.97 * W)), 'intCropHeight': int(np.floor(0.97 * H))}
+    settings = {'fltShift': 10.0, 'fltZoom': 1.25, 'objFrom': objFrom}
+    cands, cropw = common.autozoom_candidates(settings, c)
+    assert len(cands) > 50
+    dfrom, dto = c['objDepthrange'][0], c['objDepthrange'][0] * (cropw / objFrom['intCropWidth'])
+    shifts, expect = [], []
+    for (u, v) in cands:
+        st = {'tenPoints': s['points'], 'fltShiftU': u, 'fltShiftV': v, 'fltDepthFrom': dfrom, 'fltDepthTo': dto}
+        shifts.append(np.array(orc.shift_scalars(st, c), np.float32))
+        p, _ = orc.process_shift(st, c)
+        _, e = orc.render_pointcloud(p, s['data'][:, :3], W, H, FOCAL, BASELINE)
+        expect.append(orc.count_positive(e))
+    counts = common.autozoom_coverage(cu(s['points']), shifts, W, H, FOCAL, BASELINE).cpu().numpy()
+    assert counts.tolist() == expect                                                     # integer exact for every candidate
+    c['tenRawPoints'] = cu(s['points'])
+    res = common.process_autozoom(settings, c)
+    best = int(np.argmax(expect))                                                        # first maximum
+    assert res['fltCenterU'] == objFrom['fltCenterU'] + cands[best][0] and res['fltCenterV'] == objFrom['fltCenterV'] + cands[best][1]
+    assert res['intCropWidth'] == int(round(objFrom['intCropWidth'] / 1.25))
+
+
+@pytest.mark.parametrize("H,W,pw,ph", [(64, 96, 93, 62), (256, 256, 248, 248), (150, 130, 127, 145)])
+def test_frame_tail_vs_oracle(ops, H, W, pw, ph):
+    _, _, kb = ops
+    rng = np.random.default_rng(H)
+    r = rng.uniform(-0.1, 1.1, (1, 4, H, W)).astype(np.float32)
+    f_g = kb.frame_pack_u8(cu(r))
+    f_o = orc.frame_pack_u8(r[0])
+    assert np.array_equal(f_g.cpu().numpy(), f_o)
+    o = orc.resize_linear(orc.get_rect_sub_pix(f_o, (pw, ph), (W / 2.0, H / 2.0)), (W, H))
+    g = kb.frame_crop_resize(f_g, pw, ph, W / 2.0, H / 2.0)
+    assert np.array_equal(g.cpu().numpy(), o)                                            # OpenCV fixed point: bit exact
+
+
+@pytest.mark.parametrize("H,W,extra", [(64, 96, 0), (256, 256, 4000)])
+def test_fused_frame_vs_composed_oracle(ops, H, W, extra):
+    """csb_kenburns_frame (5 launches) == process_shift -> render -> fill -> pack -> crop -> resize of the reference loop."""
+    _, _, kb = ops
+    s = make_scene(H, W, seed=21, extra_points=extra)
+    st = shifted(s, 11.0, 6.0, 0.9)
+    p, _ = orc.process_shift(st, s['common'])
+    r, e = orc.render_pointcloud(p, s['data'], W, H, FOCAL, BASELINE)
+    filled = orc.fill_disocclusion(r, r[:, 3:4] * (e > 0.0))
+    pw, ph = int(np.floor(0.97 * W)), int(np.floor(0.97 * H))
+    expect = orc.resize_linear(orc.get_rect_sub_pix(orc.frame_pack_u8(filled[0]), (pw, ph), (W / 2.0, H / 2.0)), (W, H))
+    sh = np.array(orc.shift_scalars(st, s['common']), np.float32)
+    out, depth = kb.kenburns_frame(cu(s['points']), cu(s['data']), W, H, FOCAL, BASELINE, sh, pw, ph, W / 2.0, H / 2.0, want_depth=True)
+    diff = np.abs(out.cpu().numpy().astype(int) - expect.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 2e-3          # fp32 splat order -> at most 1 LSB on a few pixels
+    np.testing.assert_allclose(depth.cpu().numpy(), filled[0, 3], rtol=1e-4, atol=1e-2)
+
+
+def test_full_size_properties(ops):
+    """1024x1024 (BASELINE size), too slow for a full oracle sweep -> size-independent properties."""
+    utils, common, kb = ops
+    H = W = 1024
+    s = make_scene(H, W, seed=1)
+    pts, data = cu(s['points']), cu(s['data'])
+    r, e = utils.render_pointcloud(pts, data, W, H, FOCAL, BASELINE)
+    valid = cu(s['cloud']['valid'][0, 0] > 0)
+    img = data.view(1, 4, H, W)
+    assert float((r[0, :3][:, valid] - img[0, :3][:, valid]).abs().max()) < 2e-5          # identity render reproduces the image
+    assert int((e > 0).sum()) == int(valid.sum())
+    # linearity in the data: render(a*d1 + d2) == a*render(d1) + render(d2) (same geometry, same z-buffer)
+    sh = np.array([3.0, -2.0, -20.0], np.float32)
+    d2 = torch.rand_like(data)
+    ra, ea = utils.render_pointcloud(pts, data, W, H, FOCAL, BASELINE, tenShift=sh)
+    rb, eb = utils.render_pointcloud(pts, d2, W, H, FOCAL, BASELINE, tenShift=sh)
+    rc, ec = utils.render_pointcloud(pts, 0.5 * data + d2, W, H, FOCAL, BASELINE, tenShift=sh)
+    m = (ea > 0)[0, 0]
+    assert float(((0.5 * ra + rb) - rc)[0][:, m].abs().max()) < 1e-3 * float(rc.abs().max())
+    assert torch.equal(ea > 0, ec > 0)
+    counts = common.autozoom_coverage(pts, [sh], W, H, FOCAL, BASELINE)
+    assert int(counts[0]) == int((ea > 0).sum())                                          # coverage kernel == full render, exact
+    f = common.fill_disocclusion(ra, ra[:, 3:4] * (ea > 0).float())
+    assert torch.equal(f[0][:, m], ra[0][:, m])
+    assert torch.equal(common.fill_disocclusion(f, torch.ones_like(ea)), f)               # idempotent once holes are gone

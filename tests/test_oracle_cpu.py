@@ -1,0 +1,117 @@
+"""CPU suite: the oracle against the reference's own dependencies (OpenCV for the uint8 tail), internal properties
+of the restated kernels, and the committed golden fixtures (tests/golden, produced on the B200 by running the
+UNMODIFIED reference kernels -- see tests/golden/make_kb_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import kb_oracle as orc
+from tests.kb_scene import BASELINE, FOCAL, make_scene
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_u8_tail_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for (H, W, ph, pw) in [(1024, 1024, 993, 993), (256, 320, 249, 310), (100, 100, 97, 97), (101, 77, 60, 81), (64, 64, 63, 62)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        a = cv2.getRectSubPix(image=img, patchSize=(pw, ph), center=(W / 2.0, H / 2.0))
+        assert np.array_equal(a, orc.get_rect_sub_pix(img, (pw, ph), (W / 2.0, H / 2.0)))
+        c = cv2.resize(src=a, dsize=(W, H), fx=0.0, fy=0.0, interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(c, orc.resize_linear(a, (W, H)))
+
+
+def test_frame_pack_matches_numpy():
+    rng = np.random.default_rng(1)
+    r = rng.uniform(-0.2, 1.2, (4, 33, 47)).astype(np.float32)
+    ref = (r[0:3].transpose(1, 2, 0) * 255.0).clip(0.0, 255.0).astype(np.uint8)      # kenburns_effect.py:1040
+    assert np.array_equal(ref, orc.frame_pack_u8(r))
+
+
+def test_depth_to_points_matches_torch_restatement():
+    torch = pytest.importorskip("torch")
+    d = torch.rand(2, 1, 37, 53) * 1000 + 1
+
+    def ref(tenDepth, fltFocal):   # the reference body, anime_3dkenburns/models/utils.py:43-50, on CPU tensors
+        W, H = tenDepth.shape[3], tenDepth.shape[2]
+        hor = torch.linspace((-0.5 * W) + 0.5, (0.5 * W) - 0.5, W).view(1, 1, 1, -1).repeat(tenDepth.shape[0], 1, H, 1) * (1.0 / fltFocal)
+        ver = torch.linspace((-0.5 * H) + 0.5, (0.5 * H) - 0.5, H).view(1, 1, -1, 1).repeat(tenDepth.shape[0], 1, 1, W) * (1.0 / fltFocal)
+        return torch.cat([tenDepth * hor, tenDepth * ver, tenDepth], 1)
+    for f in (512.0, 300.0):
+        assert np.array_equal(ref(d, f).numpy(), orc.depth_to_points(d.numpy(), f))
+
+
+def test_spatial_filter_matches_torch_restatement():
+    torch = pytest.importorskip("torch")
+    x = torch.rand(1, 2, 23, 31)
+    for k, name in ((3, 'median-3'), (5, 'median-5')):
+        t = torch.nn.functional.pad(x, [k // 2] * 4, mode='reflect').unfold(2, k, 1).unfold(3, k, 1)
+        t = t.contiguous().view(1, 2, 23, 31, k * k).median(-1, False)[0]
+        assert np.array_equal(t.numpy(), orc.spatial_filter(x.numpy(), name))
+    w = torch.zeros(2, 2, 3, 3)
+    for i in range(2):
+        w[i, i, 0, 1] = -1.0; w[i, i, 0, 2] = -1.0; w[i, i, 1, 1] = 4.0; w[i, i, 1, 0] = -1.0; w[i, i, 2, 0] = -1.0
+    t = torch.nn.functional.conv2d(torch.nn.functional.pad(x, [1, 1, 1, 1], mode='replicate'), w)
+    np.testing.assert_allclose(t.numpy(), orc.spatial_filter(x.numpy(), 'laplacian'), rtol=0, atol=2e-6)
+    assert orc.spatial_filter(x.numpy(), 'nope') is None
+
+
+def test_render_identity_reproduces_image():
+    """Unshifted cloud: every valid point lands exactly on its own pixel, so render == image there."""
+    s = make_scene(64, 96)
+    render, existing = orc.render_pointcloud(s['points'], s['data'], 96, 64, FOCAL, BASELINE)
+    valid = s['cloud']['valid'][0, 0] > 0
+    img = s['data'].reshape(1, 4, 64, 96)
+    assert valid.mean() > 0.5
+    np.testing.assert_allclose(render[0, :3][:, valid], img[0, :3][:, valid], atol=2e-5)
+    assert np.all(existing[0, 0][valid] > 0.99)
+
+
+def test_fill_disocclusion_properties():
+    s = make_scene(64, 96)
+    common = s['common']
+    pts, _ = orc.process_shift({'tenPoints': s['points'], 'fltShiftU': 12.0, 'fltShiftV': -7.0, 'fltDepthFrom': common['objDepthrange'][0],
+                                'fltDepthTo': common['objDepthrange'][0] * 0.9}, common)
+    render, existing = orc.render_pointcloud(pts, s['data'], 96, 64, FOCAL, BASELINE)
+    depth = render[:, 3:4] * (existing > 0.0)
+    holes = depth[0, 0] <= 0
+    assert 0 < holes.sum() < holes.size
+    out = orc.fill_disocclusion(render, depth)
+    assert np.array_equal(out[0][:, ~holes], render[0][:, ~holes])          # valid pixels untouched
+    assert np.array_equal(orc.fill_disocclusion(out, out[:, 3:4] * np.float32(1) + (holes * 0)[None, None] + 1.0), out)  # no holes -> identity
+    filled = out[0, 3][holes]
+    assert (filled > 0).mean() > 0.5                                         # most holes receive a valid source
+
+
+def test_autozoom_count_matches_render():
+    s = make_scene(64, 96)
+    _, existing = orc.render_pointcloud(s['points'], s['data'][:, :3], 96, 64, FOCAL, BASELINE)
+    assert orc.count_positive(existing) == int((existing > 0).sum())
+
+
+def test_disparity_to_cloud_minmaxloc_matches_opencv():
+    cv2 = pytest.importorskip("cv2")
+    s = make_scene(300, 290)
+    depth = s['cloud']['depth'][0, 0]
+    mn, mx, lmn, lmx = cv2.minMaxLoc(src=depth[128:-128, 128:-128], mask=None)
+    dr = s['cloud']['depthrange']
+    assert (np.float32(mn), np.float32(mx), tuple(lmn), tuple(lmx)) == (np.float32(dr[0]), np.float32(dr[1]), dr[2], dr[3])
+
+
+@pytest.mark.parametrize("name", sorted(f for f in (os.listdir(GOLD) if os.path.isdir(GOLD) else []) if f.startswith("kb_ref_") and f.endswith(".npz")))
+def test_oracle_matches_reference_kernel_golden(name):
+    """Golden vectors = outputs of the UNMODIFIED reference kernels run on a B200 (tests/golden/make_kb_golden.py)."""
+    g = np.load(os.path.join(GOLD, name))
+    H, W = int(g['H']), int(g['W'])
+    pts, data = g['points'], g['data']
+    render, existing, z0, z1 = orc.render_pointcloud(pts, data, W, H, FOCAL, BASELINE, return_zee=True)
+    assert np.array_equal(z0, g['zee_pre'])                                  # atomicMin is order independent: bit exact
+    # in-place degrid race of the reference: allow a few differing pixels
+    assert (z1 != g['zee_post']).mean() < 1e-3
+    np.testing.assert_allclose(existing, g['existing'], atol=1e-4)
+    bad = np.abs(render - g['render']) > 1e-3
+    assert bad.mean() < 1e-3
+    filled = orc.fill_disocclusion(g['render'], g['render'][:, 3:4] * (g['existing'] > 0.0))
+    assert np.array_equal(filled, g['filled'])
