@@ -1,0 +1,285 @@
+"""RTMDet-Ins detector forward on the B200 engine: ConvNeXt-B backbone, CSPNeXtPAFPN neck,
+RTMDetInsSepBNHead + MaskFeatModule -- the network `AnimeInsSeg.model` holds in the reference
+(built from the checkpoint's mmdet config, animeinsseg/__init__.py:196-209; architecture restated in SURVEY.md Appendix A.2-A.6).
+
+Everything runs NHWC fp16 with fp32 accumulation:
+  * every conv / linear is one `csb_conv2d_nhwc` launch (tcgen05 implicit GEMM) with BatchNorm, layer-scale and the `* stride`
+    of the regression branch folded into the packed weights, and bias + SiLU/GELU/ReLU + residual fused into its epilogue;
+  * sibling convs that read the same tensor are fused along Cout (CSPLayer main+short, the three head towers' first conv);
+  * concats never copy: producers write straight into channel slices of the concat buffer (out_coff), consumers read slices (in_coff);
+  * depthwise 7x7 + LayerNorm, depthwise 5x5 + BN + SiLU, LayerNorm2d, nearest / bilinear resampling are the HBM-bound kernels of
+    csrc/nn_elem.cu.
+
+Parameters come in as a state_dict keyed by mmdet's parameter names (`backbone.*`, `neck.*`, `bbox_head.*`), so a real checkpoint
+drops in; `synthetic_state_dict` generates the seeded variance-preserving weights BASELINE.json asks for.
+"""
+import math
+
+import torch
+
+from .. import engine as E
+
+MEAN_BGR, STD_BGR = (103.53, 116.28, 123.675), (57.375, 57.12, 58.395)      # rtmdet base cfg, SURVEY Appendix A.1
+DEPTHS, DIMS = (3, 3, 27, 3), (128, 256, 512, 1024)
+STRIDES = (8, 16, 32)
+NUM_GEN_PARAMS = 169
+
+
+# ------------------------------------------------------------------------------------------------ parameter inventory
+def _convmodule(specs, name, cin, cout, k, groups=1):
+    specs.append((f"{name}.conv.weight", (cout, cin // groups, k, k), 'conv_act'))
+    for p, kind in (('weight', 'bn_w'), ('bias', 'bn_b'), ('running_mean', 'bn_m'), ('running_var', 'bn_v')):
+        specs.append((f"{name}.bn.{p}", (cout,), kind))
+
+
+def _csplayer(specs, name, cin, cout, n):
+    mid = cout // 2
+    _convmodule(specs, f"{name}.main_conv", cin, mid, 1)
+    _convmodule(specs, f"{name}.short_conv", cin, mid, 1)
+    _convmodule(specs, f"{name}.final_conv", 2 * mid, cout, 1)
+    for b in range(n):
+        _convmodule(specs, f"{name}.blocks.{b}.conv1", mid, mid, 3)
+        _convmodule(specs, f"{name}.blocks.{b}.conv2.depthwise_conv", mid, mid, 5, groups=mid)
+        _convmodule(specs, f"{name}.blocks.{b}.conv2.pointwise_conv", mid, mid, 1)
+
+
+def param_specs():
+    """[(name, shape, kind)] of the ConvNeXt-B RTMDet-Ins detector, mmdet parameter names."""
+    s = []
+    s += [("backbone.downsample_layers.0.0.weight", (DIMS[0], 3, 4, 4), 'conv_lin'), ("backbone.downsample_layers.0.0.bias", (DIMS[0],), 'bias'),
+          ("backbone.downsample_layers.0.1.weight", (DIMS[0],), 'ln_w'), ("backbone.downsample_layers.0.1.bias", (DIMS[0],), 'ln_b')]
+    for i in range(1, 4):
+        s += [(f"backbone.downsample_layers.{i}.0.weight", (DIMS[i - 1],), 'ln_w'), (f"backbone.downsample_layers.{i}.0.bias", (DIMS[i - 1],), 'ln_b'),
+              (f"backbone.downsample_layers.{i}.1.weight", (DIMS[i], DIMS[i - 1], 2, 2), 'conv_lin'), (f"backbone.downsample_layers.{i}.1.bias", (DIMS[i],), 'bias')]
+    for i in range(4):
+        d = DIMS[i]
+        for b in range(DEPTHS[i]):
+            p = f"backbone.stages.{i}.{b}"
+            s += [(f"{p}.depthwise_conv.weight", (d, 1, 7, 7), 'conv_lin'), (f"{p}.depthwise_conv.bias", (d,), 'bias'),
+                  (f"{p}.norm.weight", (d,), 'ln_w'), (f"{p}.norm.bias", (d,), 'ln_b'),
+                  (f"{p}.pointwise_conv1.weight", (4 * d, d), 'conv_act'), (f"{p}.pointwise_conv1.bias", (4 * d,), 'bias'),
+                  (f"{p}.pointwise_conv2.weight", (d, 4 * d), 'conv_res'), (f"{p}.pointwise_conv2.bias", (d,), 'bias'),
+                  (f"{p}.gamma", (d,), 'gamma')]
+    for i in (1, 2, 3):
+        s += [(f"backbone.norm{i}.weight", (DIMS[i],), 'ln_w'), (f"backbone.norm{i}.bias", (DIMS[i],), 'ln_b')]
+    c = DIMS[1:]
+    _convmodule(s, "neck.reduce_layers.0", c[2], c[1], 1)
+    _convmodule(s, "neck.reduce_layers.1", c[1], c[0], 1)
+    _csplayer(s, "neck.top_down_blocks.0", 2 * c[1], c[1], 3)
+    _csplayer(s, "neck.top_down_blocks.1", 2 * c[0], c[0], 3)
+    _convmodule(s, "neck.downsamples.0", c[0], c[0], 3)
+    _convmodule(s, "neck.downsamples.1", c[1], c[1], 3)
+    _csplayer(s, "neck.bottom_up_blocks.0", 2 * c[0], c[1], 3)
+    _csplayer(s, "neck.bottom_up_blocks.1", 2 * c[1], c[2], 3)
+    for i in range(3):
+        _convmodule(s, f"neck.out_convs.{i}", c[i], 256, 3)
+    for tower in ("cls_convs", "reg_convs", "kernel_convs"):
+        for lvl in range(3):
+            for i in range(2):
+                _convmodule(s, f"bbox_head.{tower}.{lvl}.{i}", 256, 256, 3)
+    for lvl in range(3):
+        s += [(f"bbox_head.rtm_cls.{lvl}.weight", (1, 256, 1, 1), 'conv_lin'), (f"bbox_head.rtm_cls.{lvl}.bias", (1,), 'cls_bias'),
+              (f"bbox_head.rtm_reg.{lvl}.weight", (4, 256, 1, 1), 'conv_lin'), (f"bbox_head.rtm_reg.{lvl}.bias", (4,), 'reg_bias'),
+              (f"bbox_head.rtm_kernel.{lvl}.weight", (NUM_GEN_PARAMS, 256, 1, 1), 'conv_lin'), (f"bbox_head.rtm_kernel.{lvl}.bias", (NUM_GEN_PARAMS,), 'bias')]
+    s += [("bbox_head.mask_head.fusion_conv.weight", (256, 768, 1, 1), 'conv_lin'), ("bbox_head.mask_head.fusion_conv.bias", (256,), 'bias')]
+    for i in range(4):
+        _convmodule(s, f"bbox_head.mask_head.stacked_convs.{i}", 256, 256, 3)
+    s += [("bbox_head.mask_head.projection.weight", (8, 256, 1, 1), 'conv_lin'), ("bbox_head.mask_head.projection.bias", (8,), 'bias')]
+    return s
+
+
+def synthetic_state_dict(seed=0, cls_bias=-2.0):
+    """Seeded variance-preserving weights: conv std sqrt(2/fan_in) before SiLU/GELU/ReLU, 1/sqrt(fan_in) before linear
+    outputs, biases U(-0.1,0.1), BN gamma U(0.8,1.2) beta U(-0.1,0.1) mean N(0,0.1) var U(0.8,1.2), LN gamma U(0.8,1.2), layer-scale 1.0.
+    (The reference's 'random init' is PyTorch's default because init_weights() is never called, animeinsseg/__init__.py:204-209; that
+    init collapses activations -- documented deviation.)  share_conv: tower conv weights are generated once and shared across levels."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def u(shape, lo, hi):
+        return torch.rand(shape, generator=g) * (hi - lo) + lo
+    for name, shape, kind in param_specs():
+        if kind in ('conv_act', 'conv_lin', 'conv_res'):
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            std = math.sqrt(2.0 / fan_in) if kind == 'conv_act' else (0.5 / math.sqrt(fan_in) if kind == 'conv_res' else 1.0 / math.sqrt(fan_in))
+            sd[name] = torch.randn(shape, generator=g) * std
+        elif kind in ('bias', 'bn_b', 'ln_b'):
+            sd[name] = u(shape, -0.1, 0.1)
+        elif kind in ('bn_w', 'ln_w', 'bn_v'):
+            sd[name] = u(shape, 0.8, 1.2)
+        elif kind == 'bn_m':
+            sd[name] = torch.randn(shape, generator=g) * 0.1
+        elif kind == 'gamma':
+            sd[name] = torch.ones(shape)
+        elif kind == 'cls_bias':
+            sd[name] = torch.full(shape, float(cls_bias))
+        elif kind == 'reg_bias':
+            sd[name] = u(shape, 1.0, 3.0)           # ltrb distances of a few strides -> boxes of useful size
+        else:
+            raise ValueError(kind)
+    for tower in ("cls_convs", "reg_convs", "kernel_convs"):        # share_conv=True
+        for lvl in (1, 2):
+            for i in range(2):
+                sd[f"bbox_head.{tower}.{lvl}.{i}.conv.weight"] = sd[f"bbox_head.{tower}.0.{i}.conv.weight"]
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------ weight folding / packing
+def _fold_bn(sd, name, eps):
+    w = sd[f"{name}.conv.weight"].float()
+    g, b, m, v = (sd[f"{name}.bn.{k}"].float() for k in ("weight", "bias", "running_mean", "running_var"))
+    s = g / torch.sqrt(v + eps)
+    return w * s.view(-1, 1, 1, 1), b - m * s
+
+
+class _Conv:
+    """One packed conv: weight [Cout,R,S,Cin] fp16 + fp32 bias, with its launch attributes."""
+
+    def __init__(self, w, b, dev, stride=1, pad=0, act=None, cin_pad=None):
+        self.w = E.pack_conv_weight(w.to(dev), torch.float16, cin_pad)
+        self.b = None if b is None else b.float().contiguous().to(dev)
+        self.stride, self.pad, self.act = stride, pad, act
+
+    def __call__(self, x, **kw):
+        return E.conv2d_nhwc(x, self.w, self.b, stride=self.stride, pad=self.pad, act=self.act, **kw)
+
+
+class _CSP:
+    def __init__(self, sd, name, dev, eps):
+        wm, bm = _fold_bn(sd, f"{name}.main_conv", eps)
+        ws, bs = _fold_bn(sd, f"{name}.short_conv", eps)
+        self.mid = wm.shape[0]
+        self.ms = _Conv(torch.cat([wm, ws], 0), torch.cat([bm, bs], 0), dev, act='silu')          # main + short fused along Cout
+        self.final = _Conv(*_fold_bn(sd, f"{name}.final_conv", eps), dev, act='silu')
+        self.blocks = []
+        b = 0
+        while f"{name}.blocks.{b}.conv1.conv.weight" in sd:
+            c1 = _Conv(*_fold_bn(sd, f"{name}.blocks.{b}.conv1", eps), dev, pad=1, act='silu')
+            wd, bd = _fold_bn(sd, f"{name}.blocks.{b}.conv2.depthwise_conv", eps)
+            dw = (wd[:, 0].permute(1, 2, 0).contiguous().to(dev), bd.contiguous().to(dev))            # [K,K,C] fp32
+            pw = _Conv(*_fold_bn(sd, f"{name}.blocks.{b}.conv2.pointwise_conv", eps), dev, act='silu')
+            self.blocks.append((c1, dw, pw))
+            b += 1
+
+    def __call__(self, x, out=None, out_coff=0):
+        y = self.ms(x)                                        # [.., 2*mid] = [main | short]
+        for c1, dw, pw in self.blocks:                        # CSPNeXtBlock (add_identity=False in the neck)
+            a = E.conv2d_nhwc(y, c1.w, c1.b, pad=1, act='silu', in_coff=0)
+            d = E.dwconv_nhwc(a, dw[0], dw[1], act='silu')
+            E.conv2d_nhwc(d, pw.w, pw.b, act='silu', out=y, out_coff=0)      # back into the main half
+        return E.conv2d_nhwc(y, self.final.w, self.final.b, act='silu', out=out, out_coff=out_coff)
+
+
+class RTMDetIns:
+    """B200 forward of the detector.  `forward(img_u8)` -> (cls, reg, ker: per-level NHWC fp32; mask_feat [N,h,w,8] fp32)."""
+
+    def __init__(self, state_dict, device='cuda', bn_eps=1e-5):
+        sd, dev = state_dict, torch.device(device)
+        self.dev = dev
+        f32 = lambda t: t.float().contiguous().to(dev)
+        # ---- backbone (Appendix A.4)
+        self.stem = _Conv(sd["backbone.downsample_layers.0.0.weight"], sd["backbone.downsample_layers.0.0.bias"], dev, stride=4, cin_pad=16)
+        self.stem_ln = (f32(sd["backbone.downsample_layers.0.1.weight"]), f32(sd["backbone.downsample_layers.0.1.bias"]))
+        self.down = [None]
+        for i in range(1, 4):
+            self.down.append(((f32(sd[f"backbone.downsample_layers.{i}.0.weight"]), f32(sd[f"backbone.downsample_layers.{i}.0.bias"])),
+                              _Conv(sd[f"backbone.downsample_layers.{i}.1.weight"], sd[f"backbone.downsample_layers.{i}.1.bias"], dev, stride=2)))
+        self.blocks = []
+        for i in range(4):
+            st = []
+            for b in range(DEPTHS[i]):
+                p = f"backbone.stages.{i}.{b}"
+                gamma = sd[f"{p}.gamma"].float()
+                dw = f32(sd[f"{p}.depthwise_conv.weight"][:, 0].permute(1, 2, 0))                  # [7,7,C]
+                st.append(dict(dw=dw, dwb=f32(sd[f"{p}.depthwise_conv.bias"]), ln=(f32(sd[f"{p}.norm.weight"]), f32(sd[f"{p}.norm.bias"])),
+                               fc1=_Conv(sd[f"{p}.pointwise_conv1.weight"][:, :, None, None], sd[f"{p}.pointwise_conv1.bias"], dev, act='gelu'),
+                               # layer scale folded: gamma * (W2 h + b2)
+                               fc2=_Conv(sd[f"{p}.pointwise_conv2.weight"][:, :, None, None] * gamma.view(-1, 1, 1, 1), sd[f"{p}.pointwise_conv2.bias"] * gamma, dev)))
+            self.blocks.append(st)
+        self.out_ln = {i: (f32(sd[f"backbone.norm{i}.weight"]), f32(sd[f"backbone.norm{i}.bias"])) for i in (1, 2, 3)}
+        # ---- neck (Appendix A.5)
+        cm = lambda n, **kw: _Conv(*_fold_bn(sd, n, bn_eps), dev, act='silu', **kw)
+        self.reduce = [cm("neck.reduce_layers.0"), cm("neck.reduce_layers.1")]
+        self.top_down = [_CSP(sd, "neck.top_down_blocks.0", dev, bn_eps), _CSP(sd, "neck.top_down_blocks.1", dev, bn_eps)]
+        self.downs = [cm("neck.downsamples.0", stride=2, pad=1), cm("neck.downsamples.1", stride=2, pad=1)]
+        self.bottom_up = [_CSP(sd, "neck.bottom_up_blocks.0", dev, bn_eps), _CSP(sd, "neck.bottom_up_blocks.1", dev, bn_eps)]
+        self.out_convs = [cm(f"neck.out_convs.{i}", pad=1) for i in range(3)]
+        # ---- head (Appendix A.6): first convs of the three towers fused along Cout per level (BN is per level)
+        self.tower0, self.tower1, self.preds = [], [], []
+        for lvl, stride in enumerate(STRIDES):
+            ws, bs = zip(*[_fold_bn(sd, f"bbox_head.{t}.{lvl}.0", bn_eps) for t in ("cls_convs", "reg_convs", "kernel_convs")])
+            self.tower0.append(_Conv(torch.cat(ws, 0), torch.cat(bs, 0), dev, pad=1, act='silu'))
+            self.tower1.append([cm(f"bbox_head.{t}.{lvl}.1", pad=1) for t in ("cls_convs", "reg_convs", "kernel_convs")])
+            self.preds.append((_Conv(sd[f"bbox_head.rtm_cls.{lvl}.weight"], sd[f"bbox_head.rtm_cls.{lvl}.bias"], dev),
+                               # relu(x) * stride == relu(stride * x): fold the stride into weight and bias
+                               _Conv(sd[f"bbox_head.rtm_reg.{lvl}.weight"] * stride, sd[f"bbox_head.rtm_reg.{lvl}.bias"] * stride, dev, act='relu'),
+                               _Conv(sd[f"bbox_head.rtm_kernel.{lvl}.weight"], sd[f"bbox_head.rtm_kernel.{lvl}.bias"], dev)))
+        self.fusion = _Conv(sd["bbox_head.mask_head.fusion_conv.weight"], sd["bbox_head.mask_head.fusion_conv.bias"], dev)
+        self.mask_convs = [cm(f"bbox_head.mask_head.stacked_convs.{i}", pad=1) for i in range(4)]
+        self.projection = _Conv(sd["bbox_head.mask_head.projection.weight"], sd["bbox_head.mask_head.projection.bias"], dev)
+
+    # -------------------------------------------------------------------------------------------- forward
+    def backbone(self, x16, cat_slices):
+        """x16: [N,H,W,16] fp16 normalised image.  cat_slices: {stage: (buffer, channel offset)} where norm{stage} output is written."""
+        t = self.stem(x16)
+        t = E.layernorm_nhwc(t, *self.stem_ln)
+        for i in range(4):
+            if i > 0:
+                ln, conv = self.down[i]
+                t = conv(E.layernorm_nhwc(t, *ln))
+            for blk in self.blocks[i]:
+                u = E.dwconv_nhwc(t, blk['dw'], blk['dwb'], ln=blk['ln'], eps=1e-6)
+                h = blk['fc1'](u)
+                E.conv2d_nhwc(h, blk['fc2'].w, blk['fc2'].b, residual=t, res_mode=2, out=t)       # in place: t = t + gamma*(W2 h + b2)
+            if i in cat_slices:
+                buf, off = cat_slices[i]
+                E.layernorm_nhwc(t, *self.out_ln[i], out=buf, yoff=off)
+        return t
+
+    def forward(self, img_u8):
+        if img_u8.dim() == 3:
+            img_u8 = img_u8[None]
+        N, H, W, _ = img_u8.shape
+        assert H % 32 == 0 and W % 32 == 0, "detector input must be padded to a multiple of 32 (Pad to det_size)"
+        dev, f16 = img_u8.device, torch.float16
+        h3, w3, h4, w4, h5, w5 = H // 8, W // 8, H // 16, W // 16, H // 32, W // 32
+        x16 = E.image_prep_nhwc(img_u8, MEAN_BGR, STD_BGR, swap_rb=False, CP=16)
+        cat3 = torch.empty((N, h3, w3, 512), device=dev, dtype=f16)      # [up(p4) | c3]
+        cat4 = torch.empty((N, h4, w4, 1024), device=dev, dtype=f16)     # [up(p5) | c4]
+        c5 = torch.empty((N, h5, w5, 1024), device=dev, dtype=f16)
+        catB4 = torch.empty((N, h4, w4, 512), device=dev, dtype=f16)     # [down(o3) | p4]
+        catB5 = torch.empty((N, h5, w5, 1024), device=dev, dtype=f16)    # [down(o4) | p5]
+        catM = torch.empty((N, h3, w3, 768), device=dev, dtype=f16)      # [P3 | up(P4) | up(P5)]
+        self.backbone(x16, {1: (cat3, 256), 2: (cat4, 512), 3: (c5, 0)})
+        # ---- neck
+        self.reduce[0](c5, out=catB5, out_coff=512)                                           # p5
+        E.resample_nhwc(catB5, h4, w4, 'nearest', out=cat4, xoff=512, yoff=0, C=512)
+        t4 = self.top_down[0](cat4)
+        self.reduce[1](t4, out=catB4, out_coff=256)                                           # p4
+        E.resample_nhwc(catB4, h3, w3, 'nearest', out=cat3, xoff=256, yoff=0, C=256)
+        o3 = self.top_down[1](cat3)
+        self.downs[0](o3, out=catB4, out_coff=0)
+        o4 = self.bottom_up[0](catB4)
+        self.downs[1](o4, out=catB5, out_coff=0)
+        o5 = self.bottom_up[1](catB5)
+        self.out_convs[0](o3, out=catM, out_coff=0)                                           # P3 lives in the mask-feat concat buffer
+        P4 = self.out_convs[1](o4)
+        P5 = self.out_convs[2](o5)
+        E.resample_nhwc(P4, h3, w3, 'bilinear', out=catM, yoff=256)
+        E.resample_nhwc(P5, h3, w3, 'bilinear', out=catM, yoff=512)
+        # ---- head
+        cls, reg, ker = [], [], []
+        for lvl, feat in enumerate((catM, P4, P5)):
+            T = E.conv2d_nhwc(feat, self.tower0[lvl].w, self.tower0[lvl].b, pad=1, act='silu', in_coff=0)      # [.., 768] = [cls | reg | kernel]
+            outs = []
+            for j, (t1, pred) in enumerate(zip(self.tower1[lvl], self.preds[lvl])):
+                f = E.conv2d_nhwc(T, t1.w, t1.b, pad=1, act='silu', in_coff=256 * j)
+                outs.append(E.conv2d_nhwc(f, pred.w, pred.b, act=pred.act, out_f32=True))
+            cls.append(outs[0]); reg.append(outs[1]); ker.append(outs[2])
+        m = self.fusion(catM)
+        for c in self.mask_convs:
+            m = c(m)
+        mask_feat = E.conv2d_nhwc(m, self.projection.w, self.projection.b, out_f32=True)
+        return cls, reg, ker, mask_feat

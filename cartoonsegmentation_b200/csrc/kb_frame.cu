@@ -1,8 +1,9 @@
 // Ken-Burns frame tail for sm_100a (anime_3dkenburns/kenburns_effect.py:1028-1040, 1069-1070):
 //   k_pack_u8          (render*255).clip(0,255).astype(uint8), CHW -> HWC                                  (:1040)
 //   k_crop_resize      cv2.getRectSubPix (16-bit fixed point) + cv2.resize INTER_LINEAR (11-bit fixed point) (:1069-1070)
-//   k_norm_fill_pack   normalise (models/utils.py:315) + mask depth (:1039) + fill_disocclusion (common.py:149-245) + pack,
-//                      reading the interleaved render accumulator once -- the float render/existing/filled tensors of the
+//   k_norm_pack_mark + k_fill_holes
+//                      normalise (models/utils.py:315) + mask depth (:1039) + fill_disocclusion (common.py:149-245) + pack,
+//                      reading the interleaved render accumulator -- the float render/existing/filled tensors of the
 //                      reference (4 full-resolution fp32 tensors per frame) never touch HBM.
 // The reference does the pack on the host after a D2H of the float frame and the crop/resize in OpenCV on the CPU; the
 // integer arithmetic below reproduces OpenCV's uint8 paths bit for bit (pinned against cv2 in tests/test_oracle_cpu.py).
@@ -79,33 +80,106 @@ __global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__
     }
 }
 
-// Fused normalise + depth mask + disocclusion fill + u8 pack for C = 4 (BGR + depth), CP = 8.
-// acc pixel = {b*w, g*w, r*w, depth*w, w, 0, 0, 0} (32 B, one sector).  18 B/px when depth_out is null.
-__global__ void __launch_bounds__(256) k_norm_fill_pack(const float* __restrict__ acc, int H, int W, uint8_t* __restrict__ frame,
-                                                        float* __restrict__ depth_out) {
-    const long long HW = (long long) H * W;
-    // masked depth of the composed reference path: render[3] * (existing > 0)   (kenburns_effect.py:1039)
-    auto depthv = [&](int yy, int xx) {
-        const float* A = acc + ((size_t) yy * W + xx) * 8;
-        float w = __ldg(A + 4);
-        float r = __fdiv_rn(__ldg(A + 3), __fadd_rn(w, 0.0000001f));
-        return __fmul_rn(r, w > 0.0f ? 1.0f : 0.0f);
-    };
-    auto valid = [&](int yy, int xx) { return depthv(yy, xx) > 0.0f; };
+// Fused normalise + depth mask + disocclusion fill + u8 pack for C = 4 (BGR + depth), CP = 8, in two launches.
+// acc pixel = {b*w, g*w, r*w, depth*w, w, 0, 0, 0} (32 B, one sector).
+//
+// A pixel is a hole of the composed reference path iff  render[3] * (existing > 0) <= 0  (kenburns_effect.py:1039, common.py:163), i.e.
+// iff !(w > 0 && acc3 / (w + 1e-7) > 0).  For finite data that is exactly !(w > 0 && acc3 > 0): the quotient of a normal positive
+// acc3 (the float reductions flush subnormals) by w + 1e-7 <= ~5 cannot underflow to zero.
+//
+//   k_norm_pack_mark  every pixel: valid -> normalise + pack (+ depth); hole -> appended to a device-side hole list.  Also writes a byte
+//                     validity mask (1 B/px) so that the ray march below touches 32 pixels per sector instead of 1.  21 B/px.
+//   k_fill_holes      16 lanes per hole pixel, one ray direction per lane (the reference walks the 16 directions serially in ONE thread,
+//                     common.py:181-235): all lanes busy, no divergence against valid pixels; the serial "first strictly shortest
+//                     direction wins" rule becomes a shuffle arg-min on (distance, direction index).
+__device__ __forceinline__ bool acc_valid(const float* __restrict__ acc, long long pix) {
+    const float* A = acc + (size_t) pix * 8;
+    return __ldg(A + 4) > 0.0f && __ldg(A + 3) > 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_norm_pack_mark(const float* __restrict__ acc, long long HW, uint8_t* __restrict__ frame, float* __restrict__ depth_out,
+                                                        uint8_t* __restrict__ mask, int* __restrict__ holes, int* __restrict__ nholes) {
     for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < HW; i += (long long) gridDim.x * blockDim.x) {
-        const int x = (int) (i % W), y = (int) (i / W);
-        long long src = i;
-        if (!valid(y, x)) {
-            long long f = csbfill::find_fill(x, y, H, W, valid, depthv);
-            if (f >= 0) src = f;
-        }
-        const float4 q = __ldg(reinterpret_cast<const float4*>(acc + (size_t) src * 8));
-        const float w = __ldg(acc + (size_t) src * 8 + 4);
+        const float4 q = __ldg(reinterpret_cast<const float4*>(acc + (size_t) i * 8));
+        const float w = __ldg(acc + (size_t) i * 8 + 4);
+        const bool ok = w > 0.0f && q.w > 0.0f;
+        mask[i] = ok ? 1 : 0;
+        if (!ok) holes[atomicAdd(nholes, 1)] = (int) i;        // aggregated per warp by the compiler (REDUX + one atomic)
+        // holes that find no fill source keep their own normalised value (common.py:146 clone), so write it for every pixel
         const float d = __fadd_rn(w, 0.0000001f);
         frame[i * 3 + 0] = pack1(__fdiv_rn(q.x, d));
         frame[i * 3 + 1] = pack1(__fdiv_rn(q.y, d));
         frame[i * 3 + 2] = pack1(__fdiv_rn(q.z, d));
         if (depth_out) depth_out[i] = __fdiv_rn(q.w, d);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_holes(const float* __restrict__ acc, const uint8_t* __restrict__ mask, const int* __restrict__ holes,
+                                                    const int* __restrict__ nholes, int H, int W, uint8_t* __restrict__ frame, float* __restrict__ depth_out) {
+    const int n = *nholes;
+    const int d = threadIdx.x & 15;                                 // ray direction of this lane
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16);          // the 16 lanes cooperating on one hole
+    float dx, dy;
+    {
+        const float tx[16] = {-1, 0, 1, 1, -1, 1, 2, 2, -2, -1, 1, 2, 3, 3, 3, 3}, ty[16] = {1, 1, 1, 0, 2, 2, 1, -1, 3, 3, 3, 3, 2, 1, -1, -2};
+        const float nrm = sqrtf((tx[d] * tx[d]) + (ty[d] * ty[d]));  // common.py:174-179
+        dx = __fdiv_rn(tx[d], nrm);
+        dy = __fdiv_rn(ty[d], nrm);
+    }
+    auto depthv = [&](int yy, int xx) {                               // masked depth, kenburns_effect.py:1039
+        const float* A = acc + ((size_t) yy * W + xx) * 8;
+        const float w = __ldg(A + 4);
+        return __fmul_rn(__fdiv_rn(__ldg(A + 3), __fadd_rn(w, 0.0000001f)), w > 0.0f ? 1.0f : 0.0f);
+    };
+    const int groups = (gridDim.x * blockDim.x) >> 4;
+    for (int hidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; hidx < n; hidx += groups) {
+        const int pix = holes[hidx];
+        const int x = pix % W, y = pix / W;
+        float ffx = (float) x, ffy = (float) y, tfx = (float) x, tfy = (float) y;
+        int ifx = 0, ify = 0, itx = 0, ity = 0;
+        bool found = true;
+        do {                                                          // common.py:188-196
+            ffx = __fsub_rn(ffx, dx); ifx = (int) roundf(ffx);
+            ffy = __fsub_rn(ffy, dy); ify = (int) roundf(ffy);
+            if ((ifx < 0) | (ifx >= W)) break;
+            if ((ify < 0) | (ify >= H)) break;
+            if (__ldg(mask + (size_t) ify * W + ifx)) break;
+        } while (true);
+        if ((ifx < 0) | (ifx >= W) | (ify < 0) | (ify >= H)) found = false;
+        if (found) {
+            do {                                                      // common.py:199-207
+                tfx = __fadd_rn(tfx, dx); itx = (int) roundf(tfx);
+                tfy = __fadd_rn(tfy, dy); ity = (int) roundf(tfy);
+                if ((itx < 0) | (itx >= W)) break;
+                if ((ity < 0) | (ity >= H)) break;
+                if (__ldg(mask + (size_t) ity * W + itx)) break;
+            } while (true);
+            if ((itx < 0) | (itx >= W) | (ity < 0) | (ity >= H)) found = false;
+        }
+        float dist = 1000000.0f;                                      // fltShortest init :165; a direction only wins with dist < 1e6
+        int fill = -1;
+        if (found) {
+            dist = sqrtf(__fadd_rn(powf((float) (itx - ifx), 2), powf((float) (ity - ify), 2)));     // :210
+            fill = ify * W + ifx;
+            if (depthv(ify, ifx) < depthv(ity, itx)) fill = ity * W + itx;                           // :216-219
+            if (!(1000000.0f > dist)) fill = -1;
+        }
+        // serial rule: a later direction replaces the best only if strictly shorter -> min over (dist, direction index)
+        int best = d;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(gmask, dist, o);
+            const int ob = __shfl_xor_sync(gmask, best, o), of = __shfl_xor_sync(gmask, fill, o);
+            if (od < dist || (od == dist && ob < best)) { dist = od; best = ob; fill = of; }
+        }
+        if (d == 0 && fill >= 0) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(acc + (size_t) fill * 8));
+            const float dd = __fadd_rn(__ldg(acc + (size_t) fill * 8 + 4), 0.0000001f);
+            frame[(size_t) pix * 3 + 0] = pack1(__fdiv_rn(q.x, dd));
+            frame[(size_t) pix * 3 + 1] = pack1(__fdiv_rn(q.y, dd));
+            frame[(size_t) pix * 3 + 2] = pack1(__fdiv_rn(q.z, dd));
+            if (depth_out) depth_out[pix] = __fdiv_rn(q.w, dd);
+        }
     }
 }
 
@@ -150,15 +224,22 @@ extern "C" int csb_kenburns_frame(const float* points, const float* data, int N,
                                   const float* shift, const float* shift_dev, int pw, int ph, double cx, double cy, int32_t* zkey,
                                   float* zee, float* acc,
                                   uint8_t* packed, uint8_t* out, float* depth_out, void* stream) {
-    CSB_REQUIRE(points && data && zkey && zee && acc && packed && out, "null pointer");
-    CSB_REQUIRE(N >= 0 && H > 0 && W > 0, "bad shape");
+    CSB_REQUIRE(((points && data) || N == 0) && zkey && zee && acc && packed && out, "null pointer");
+    CSB_REQUIRE(N >= 0 && H > 0 && W > 0 && (long long) H * W >= 8, "bad shape");
     CSB_REQUIRE(((uintptr_t) acc & 15) == 0, "acc must be 16-byte aligned");
     CropParams p;
     CSB_REQUIRE(make_crop(H, W, pw, ph, cx, cy, p) == CSB_OK, "bad crop size");
     cudaStream_t st = (cudaStream_t) stream;
     CSB_TRY(csb_render_accumulate(points, data, 1, N, 4, H, W, focal, baseline, shift, shift_dev, zkey, zee, acc, st));
-    k_norm_fill_pack<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(acc, H, W, packed, depth_out);
-    CSB_TRY(csb::launched("k_norm_fill_pack", st));
+    // scratch reuse: the z-buffers are dead after the splat -> zkey holds the hole list, zee the byte mask + the hole counter
+    uint8_t* mask = reinterpret_cast<uint8_t*>(zee);
+    int* nholes = reinterpret_cast<int*>(zee) + (size_t) H * W / 2 + 1;
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(nholes, 0, sizeof(int), st), "memset nholes"));
+    csb::memset_done(st);
+    k_norm_pack_mark<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(acc, (long long) H * W, packed, depth_out, mask, zkey, nholes);
+    CSB_TRY(csb::launched("k_norm_pack_mark", st));
+    k_fill_holes<<<csb::num_sms() * 8, 256, 0, st>>>(acc, mask, zkey, nholes, H, W, packed, depth_out);
+    CSB_TRY(csb::launched("k_fill_holes", st));
     k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, out);
     return csb::launched("k_crop_resize", st);
 }

@@ -317,7 +317,7 @@ extern "C" int csb_render_acc_channels(int C) { return ((C + 1) + 3) / 4 * 4; }
 
 static int zpass_impl(const float* points, int B, int N, int H, int W, double focal, double baseline, const float* shift,
                       const float* shift_dev, int32_t* zkey, cudaStream_t stream) {
-    CSB_REQUIRE(points && zkey, "null pointer");
+    CSB_REQUIRE((points || N == 0) && zkey, "null pointer");
     CSB_REQUIRE(B > 0 && N >= 0 && H > 0 && W > 0, "bad shape");
     cudaStream_t st = (cudaStream_t) stream;
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(zkey, 0x7f, sizeof(int32_t) * (size_t) B * H * W, st), "memset zkey"));
@@ -356,7 +356,7 @@ int csb_render_accumulate(const float* points, const float* data, int B, int N, 
 extern "C" int csb_pointcloud_render(const float* points, const float* data, int B, int N, int C, int H, int W, double focal,
                                      double baseline, const float* shift, const float* shift_dev, int32_t* zkey, float* zee, float* acc,
                                      float* render, float* existing, void* stream) {
-    CSB_REQUIRE(points && data && zkey && zee && acc, "null pointer");
+    CSB_REQUIRE(((points && data) || N == 0) && zkey && zee && acc, "null pointer");
     CSB_REQUIRE(B > 0 && N >= 0 && C > 0 && H > 0 && W > 0, "bad shape");
     CSB_REQUIRE(((uintptr_t) acc & 15) == 0, "acc must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t) stream;

@@ -1,0 +1,404 @@
+// Implicit-GEMM convolution / GEMM on the 5th-generation tensor cores (tcgen05) for sm_100a.
+//
+//   y[n,oh,ow,co] = act( sum_{r,s,ci} x[n, oh*stride + r*dil - pad, ow*stride + s*dil - pad, ci] * w[co,r,s,ci] + bias[co] (+ residual) )
+//
+// This is the dense-contraction engine behind every conv / linear layer of the hot path (SURVEY.md §8a rows A2-A4, A10,
+// B6, C5; Appendix B lists the shapes).  The reference runs them through cuDNN fp32 NCHW.
+//
+// Design (one CTA per SM, persistent over output tiles, warp-specialised):
+//   * activations NHWC fp16/bf16; an output tile is bh x bw = 128 pixels of one image (or 128 consecutive pixels for 1x1).
+//   * warp 0 (one lane): TMA producer.  For every filter tap (r,s) and every 64-channel chunk it issues ONE 4-D tiled
+//     cp.async.bulk.tensor load of the *shifted* activation box {64 ch, bw, bh, 1} -- out-of-bounds coordinates are
+//     zero-filled by the TMA unit, which is the convolution's zero padding; stride-2 convs use the tensor map's
+//     elementStrides -- plus one 2-D load of the weight tile {64 k, BLOCK_N rows} of the K-major packed filter.
+//     Both land in 128B-swizzled shared memory, i.e. directly in the canonical K-major UMMA operand layout.
+//   * warp 1 (one lane): issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N<=256, K=16) with fp32 accumulators
+//     in TMEM; tcgen05.commit releases the smem stage to the producer and, after the last k-block, hands the
+//     accumulator to the epilogue.  Two accumulator stages (2 x 256 TMEM columns) overlap epilogue and MMA.
+//   * warps 4-7: epilogue.  tcgen05.ld (32 lanes x 32 columns per warp) -> bias, residual, activation in fp32 ->
+//     fp16/bf16 (or fp32) NHWC store, optionally into a channel slice of a wider tensor (concat fusion).
+//   * mbarrier pipeline: full/empty per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator stage.
+//
+// Roofline: tensor pipe.  FLOPs = 2 * N*Hout*Wout * Cout * R*S*Cin.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kAccStages = 2;
+constexpr int kMaxStages = 8;
+
+struct ConvKernelParams {
+    // geometry (output space)
+    int N, H, W;                 // batch, output height/width (flat mode: N=1, H=1, W=pixels)
+    int Cin, Cout;
+    int R, S, stride, pad, dil;
+    int bh, bw, tiles_h, tiles_w, tiles_m, tiles_n, block_n;
+    int bk, kchunks, stages;     // bk: channels per k-block (64/32/16) -> swizzle 128/64/32 B
+    int in_coff;
+    // epilogue
+    const float* bias;
+    const void* residual;
+    int res_ld, res_coff, res_mode;   // 0 none, 1 add before activation, 2 add after activation
+    int act;
+    const float* act_param;      // per-channel PReLU slope
+    void* out;
+    float* out_f32;
+    int out_ld, out_coff;
+    int is_bf16;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a broken pipeline traps (the launch reports an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand descriptor (cute::UMMA::SmemDescriptor): start address, LBO (ignored for swizzled K-major, set 1), SBO = 8 rows,
+// version 1 (Blackwell), layout type 2/4/6 = SWIZZLE_128B/64B/32B.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    return (uint64_t) ((saddr & 0x3ffff) >> 4) | (1ull << 16) | ((uint64_t) ((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act, float slope) {
+    switch (act) {
+        case CSB_ACT_RELU: return fmaxf(x, 0.0f);
+        case CSB_ACT_SILU: return x / (1.0f + __expf(-x));
+        case CSB_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+        case CSB_ACT_PRELU: return x > 0.0f ? x : x * slope;
+        case CSB_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-x));
+        case CSB_ACT_SOFTPLUS: return x > 20.0f ? x : log1pf(__expf(x));
+        case CSB_ACT_HARDSIGMOID: return fminf(fmaxf(x * (1.0f / 6.0f) + 0.5f, 0.0f), 1.0f);
+        default: return x;
+    }
+}
+
+template <class T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <class T>
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[32], size_t pix, int n0, bool row_ok) {
+    // pix: linear output pixel index; n0: first output channel of this 32-column chunk
+    if (!row_ok) return;
+    const T* res = p.res_mode ? reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0 : nullptr;
+    const bool vec_ok = (n0 + 32 <= p.Cout) && ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0));
+    float y[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int c = n0 + j;
+        float v = __uint_as_float(acc[j]);
+        if (c < p.Cout) {
+            if (p.bias) v += __ldg(p.bias + c);
+            if (p.res_mode == 1) v += to_f<T>(res[j]);
+            v = apply_act(v, p.act, p.act_param ? __ldg(p.act_param + c) : 0.25f);
+            if (p.res_mode == 2) v += to_f<T>(res[j]);
+        }
+        y[j] = v;
+    }
+    if (p.out_f32) {
+        float* o = p.out_f32 + pix * p.out_ld + p.out_coff + n0;
+        for (int j = 0; j < 32 && n0 + j < p.Cout; ++j) o[j] = y[j];
+        return;
+    }
+    T* o = reinterpret_cast<T*>(p.out) + pix * p.out_ld + p.out_coff + n0;
+    if (vec_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            alignas(16) T h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = from_f<T>(y[g * 8 + j]);
+            *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(h);
+        }
+    } else {
+        for (int j = 0; j < 32 && n0 + j < p.Cout; ++j) o[j] = from_f<T>(y[j]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                         const ConvKernelParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t row_bytes = (uint32_t) p.bk * 2u;
+    const uint32_t a_bytes = kBlockM * row_bytes, b_bytes = (uint32_t) p.block_n * row_bytes;
+    const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + (uint32_t) p.stages * stage_bytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kAccStages + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 2 * kAccStages);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = p.tiles_m * p.tiles_n;
+    const int kblocks = p.R * p.S * p.kchunks;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+                const int oh0 = th * p.bh, ow0 = tw * p.bw, n0 = nt * p.block_n;
+                for (int r = 0; r < p.R; ++r)
+                    for (int s = 0; s < p.S; ++s)
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            const uint32_t a_dst = smem_base + (uint32_t) stage * stage_bytes, b_dst = a_dst + a_bytes;
+                            mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
+                            tma_load_4d(a_dst, &tmA, full_bar(stage), p.in_coff + kc * p.bk, ow0 * p.stride + s * p.dil - p.pad,
+                                        oh0 * p.stride + r * p.dil - p.pad, img);
+                            tma_load_2d(b_dst, &tmB, full_bar(stage), ((r * p.S + s) * p.kchunks + kc) * p.bk, n0);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B fp16 or bf16, both K-major, N>>3 @17, M>>4 @24
+        const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.block_n >> 3) << 17) | ((uint32_t) (kBlockM >> 4) << 24);
+        int stage = 0, as = 0;
+        uint32_t phase = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(as), aphase ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t) as * 256u;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_base + (uint32_t) stage * stage_bytes, b_addr = a_addr + a_bytes;
+                    const uint64_t adesc = make_desc(a_addr, row_bytes), bdesc = make_desc(b_addr, row_bytes);
+                    for (int k = 0; k < p.bk / kUmmaK; ++k)   // advance 16 elements = 32 B = 2 descriptor units inside the swizzle atom
+                        umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(empty_bar(stage));
+                    if (kb == kblocks - 1) umma_commit(tfull_bar(as));
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+        }
+    } else if (warp >= 4) {
+        // ===================================================== epilogue (TMEM -> registers -> global)
+        const int q = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+            const int m = q * 32 + lane;
+            const int oh = th * p.bh + m / p.bw, ow = tw * p.bw + m % p.bw;
+            const bool row_ok = oh < p.H && ow < p.W;
+            const size_t pix = ((size_t) img * p.H + oh) * p.W + ow;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) as * 256u;
+            const int nchunks = (min(p.block_n, p.Cout - nt * p.block_n) + 31) / 32;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + (uint32_t) ch * 32u, acc);
+                if (ch == nchunks - 1) {           // accumulator fully read: hand the TMEM stage back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                }
+                if (p.is_bf16) epilogue_chunk<__nv_bfloat16>(p, acc, pix, nt * p.block_n + ch * 32, row_ok);
+                else epilogue_chunk<__half>(p, acc, pix, nt * p.block_n + ch * 32, row_ok);
+            }
+            if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn) f;
+    });
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_of(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); }
+
+}  // namespace
+
+extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void* w, const float* bias, const float* act_param,
+                               const void* residual, void* y, float* y_f32, void* stream) {
+    CSB_REQUIRE(d && x && w && (y || y_f32), "null pointer");
+    CSB_REQUIRE(d->N > 0 && d->Hin > 0 && d->Win > 0 && d->Cin > 0 && d->Cout > 0 && d->R > 0 && d->S > 0, "bad shape");
+    CSB_REQUIRE(d->stride == 1 || d->stride == 2 || d->stride == 4, "stride must be 1, 2 or 4");
+    CSB_REQUIRE(d->Cin % 16 == 0, "Cin must be a multiple of 16 (pad the channel dimension)");
+    CSB_REQUIRE(d->in_ld % 8 == 0 && d->in_coff % 8 == 0 && d->in_ld >= d->in_coff + d->Cin, "input channel stride/offset must be multiples of 8");
+    CSB_REQUIRE(((uintptr_t) x & 15) == 0 && ((uintptr_t) w & 15) == 0, "x and w must be 16-byte aligned");
+    CSB_REQUIRE(d->res_mode == 0 || residual, "residual pointer missing");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return csb::fail(CSB_ERR_CUDA, "%s: %s", "csb_conv2d_nhwc", "cuTensorMapEncodeTiled unavailable");
+    const int Hout = (d->Hin + 2 * d->pad - d->dil * (d->R - 1) - 1) / d->stride + 1;
+    const int Wout = (d->Win + 2 * d->pad - d->dil * (d->S - 1) - 1) / d->stride + 1;
+    CSB_REQUIRE(Hout > 0 && Wout > 0, "empty output");
+
+    ConvKernelParams p{};
+    p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
+    p.bk = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
+    p.kchunks = d->Cin / p.bk;
+    p.in_coff = d->in_coff;
+    const bool flat = d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0;
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t box[4], estr[4];
+    const cuuint64_t esz = 2;
+    if (flat) {   // 1x1: the NHWC tensor is a [pixels, C] matrix -> tiles of 128 consecutive pixels, no spatial waste
+        p.N = 1; p.H = 1; p.W = d->N * Hout * Wout; p.bh = 1; p.bw = kBlockM;
+        gdim[0] = (cuuint64_t) d->in_ld; gdim[1] = (cuuint64_t) p.W; gdim[2] = 1; gdim[3] = 1;
+        gstr[0] = (cuuint64_t) d->in_ld * esz; gstr[1] = gstr[0] * gdim[1]; gstr[2] = gstr[1];
+    } else {
+        p.N = d->N; p.H = Hout; p.W = Wout;
+        long long best = -1;
+        for (int bw = 8; bw <= 128; bw *= 2) {   // tile shape minimising padded area; ties -> squarer tile
+            const int bh = kBlockM / bw;
+            if (bw * d->stride > 256 || bh * d->stride > 256) continue;
+            long long area = (long long) ((Wout + bw - 1) / bw) * bw * ((Hout + bh - 1) / bh) * bh;
+            long long score = area * 1024 + (bw > bh ? bw / bh : bh / bw);
+            if (best < 0 || score < best) { best = score; p.bw = bw; p.bh = bh; }
+        }
+        gdim[0] = (cuuint64_t) d->in_ld; gdim[1] = (cuuint64_t) d->Win; gdim[2] = (cuuint64_t) d->Hin; gdim[3] = (cuuint64_t) d->N;
+        gstr[0] = (cuuint64_t) d->in_ld * esz; gstr[1] = gstr[0] * d->Win; gstr[2] = gstr[1] * d->Hin;
+    }
+    p.tiles_h = (p.H + p.bh - 1) / p.bh; p.tiles_w = (p.W + p.bw - 1) / p.bw; p.tiles_m = p.N * p.tiles_h * p.tiles_w;
+    p.block_n = d->Cout >= 256 ? 256 : ((d->Cout + 15) / 16) * 16;
+    p.tiles_n = (d->Cout + p.block_n - 1) / p.block_n;
+    box[0] = (cuuint32_t) p.bk; box[1] = (cuuint32_t) (p.bw * d->stride); box[2] = (cuuint32_t) (p.bh * d->stride); box[3] = 1;
+    estr[0] = 1; estr[1] = (cuuint32_t) d->stride; estr[2] = (cuuint32_t) d->stride; estr[3] = 1;
+    const CUtensorMapDataType dt = d->dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUtensorMap tmA, tmB;
+    CUresult r = enc(&tmA, dt, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(p.bk),
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_conv2d_nhwc", "cuTensorMapEncodeTiled(A) failed");
+    const cuuint64_t ktot = (cuuint64_t) d->R * d->S * d->Cin;
+    cuuint64_t wdim[2] = {ktot, (cuuint64_t) d->Cout}, wstr[1] = {ktot * esz};
+    cuuint32_t wbox[2] = {(cuuint32_t) p.bk, (cuuint32_t) p.block_n}, westr[2] = {1, 1};
+    r = enc(&tmB, dt, 2, const_cast<void*>(w), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(p.bk),
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_conv2d_nhwc", "cuTensorMapEncodeTiled(B) failed");
+
+    const uint32_t row_bytes = p.bk * 2, stage_bytes = ((kBlockM + p.block_n) * row_bytes + 1023u) & ~1023u;
+    const int kblocks = p.R * p.S * p.kchunks;
+    int stages = (int) ((200u * 1024u) / stage_bytes);
+    stages = stages > kMaxStages ? kMaxStages : stages;
+    stages = stages > kblocks * 2 ? (kblocks * 2 < 2 ? 2 : kblocks * 2) : stages;
+    p.stages = stages < 2 ? 2 : stages;
+    const size_t smem = (size_t) p.stages * stage_bytes + 1024 /*align*/ + 8 * (2 * kMaxStages + 2 * kAccStages) + 16;
+    p.bias = bias; p.act = d->act; p.act_param = act_param;
+    p.residual = residual; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.res_mode = d->res_mode;
+    p.out = y; p.out_f32 = y_f32; p.out_ld = d->out_ld; p.out_coff = d->out_coff; p.is_bf16 = d->dtype == 1;
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] { cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    const int total = p.tiles_m * p.tiles_n;
+    const int grid = total < csb::num_sms() ? total : csb::num_sms();
+    k_conv_tc<<<grid, kThreads, smem, (cudaStream_t) stream>>>(tmA, tmB, p);
+    return csb::launched("k_conv_tc", (cudaStream_t) stream);
+}

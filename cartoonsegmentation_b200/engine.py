@@ -1,0 +1,100 @@
+"""Host side of the tcgen05 conv/GEMM engine (csrc/tc_conv.cu, include/csb200.h csb_conv2d_nhwc).
+
+Activations are NHWC fp16 (or bf16) CUDA tensors; weights are packed once to [Cout][R][S][Cin] (K-major rows) with
+BatchNorm folded in.  Every call enqueues one persistent tcgen05 kernel on torch's current stream.  No CPU fallback.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib, ptr, stream
+
+ACT = {None: 0, 'none': 0, 'relu': 1, 'silu': 2, 'gelu': 3, 'prelu': 4, 'sigmoid': 5, 'softplus': 6, 'hardsigmoid': 7}
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("N", "Hin", "Win", "Cin", "in_ld", "in_coff", "Cout", "R", "S", "stride", "pad", "dil",
+                                       "out_ld", "out_coff", "act", "res_mode", "res_ld", "res_coff", "dtype")]
+
+
+def pack_conv_weight(w, dtype=torch.float16, cin_pad=None):
+    """torch conv weight [Cout, Cin, R, S] -> [Cout, R, S, Cin(_pad)] K-major, contiguous, on the same device."""
+    Cout, Cin, R, S = w.shape
+    wp = w.permute(0, 2, 3, 1)
+    if cin_pad is not None and cin_pad != Cin:
+        wp = torch.nn.functional.pad(wp, (0, cin_pad - Cin))
+    return wp.contiguous().to(dtype)
+
+
+def out_hw(Hin, Win, R, S, stride, pad, dil):
+    return (Hin + 2 * pad - dil * (R - 1) - 1) // stride + 1, (Win + 2 * pad - dil * (S - 1) - 1) // stride + 1
+
+
+def conv2d_nhwc(x, w, bias=None, stride=1, pad=0, dil=1, act=None, act_param=None, residual=None, res_mode=0, out=None, out_coff=0,
+                in_coff=0, cin=None, res_coff=0, out_f32=False):
+    """x: [N,H,W,Cx] NHWC fp16/bf16 (channels in_coff..in_coff+cin used); w: packed [Cout,R,S,Cin]; -> y [N,Ho,Wo,Cout] (or `out`
+    written at channel offset out_coff).  residual: NHWC tensor added before (res_mode=1) / after (res_mode=2) the activation."""
+    N, H, W, Cx = x.shape
+    Cout, R, S, Cin = w.shape
+    cin = Cin if cin is None else cin
+    assert cin == Cin and x.dtype == w.dtype and x.dtype in (torch.float16, torch.bfloat16)
+    Ho, Wo = out_hw(H, W, R, S, stride, pad, dil)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
+    assert out.shape[:3] == (N, Ho, Wo)
+    if residual is not None and res_mode == 0:
+        res_mode = 1
+    d = ConvDesc(N, H, W, Cin, Cx, in_coff, Cout, R, S, stride, pad, dil, out.shape[3], out_coff, ACT[act], res_mode,
+                 residual.shape[3] if residual is not None else 0, res_coff, 1 if x.dtype == torch.bfloat16 else 0)
+    is_f32 = out.dtype == torch.float32
+    check(lib().csb_conv2d_nhwc(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(act_param), ptr(residual), None if is_f32 else ptr(out),
+                                ptr(out) if is_f32 else None, stream()), "csb_conv2d_nhwc")
+    return out
+
+
+def dwconv_nhwc(x, w, bias=None, ln=None, eps=1e-6, act=None, out=None, xoff=0, yoff=0, channels=None):
+    """Depthwise KxK (stride 1, pad K/2) + bias [+ LayerNorm over C (ln=(gamma, beta))] [+ act].  x NHWC fp16, w [K,K,C] fp32."""
+    N, H, W, ldx = x.shape
+    K = w.shape[0]
+    Cc = w.shape[2] if channels is None else channels
+    if out is None:
+        out = torch.empty((N, H, W, Cc), device=x.device, dtype=x.dtype)
+    check(lib().csb_dwconv_nhwc(ptr(x), ldx, xoff, ptr(w), ptr(bias), ptr(ln[0]) if ln else None, ptr(ln[1]) if ln else None, _cf(eps), ACT[act], N, H, W, Cc, K, ptr(out), out.shape[3], yoff, stream()), "csb_dwconv_nhwc")
+    return out
+
+
+def _cf(v):
+    return C.c_float(float(v))
+
+
+def layernorm_nhwc(x, gamma, beta, eps=1e-6, out=None, xoff=0, yoff=0, C=None):
+    ldx = x.shape[-1]
+    C_ = gamma.numel() if C is None else C
+    npix = x.numel() // ldx
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (C_,), device=x.device, dtype=x.dtype)
+    check(lib().csb_layernorm_nhwc(ptr(x), ldx, xoff, ptr(gamma), ptr(beta), _cf(eps), C.c_longlong(npix), C_, ptr(out), out.shape[-1], yoff, stream()),
+          "csb_layernorm_nhwc")
+    return out
+
+
+def resample_nhwc(x, Ho, Wo, mode, out=None, xoff=0, yoff=0, C=None):
+    """mode: 'nearest' | 'bilinear' (align_corners=False) | 'bilinear_ac' (align_corners=True)"""
+    N, Hi, Wi, ldx = x.shape
+    C_ = ldx if C is None else C
+    if out is None:
+        out = torch.empty((N, Ho, Wo, C_), device=x.device, dtype=x.dtype)
+    m = {'nearest': 0, 'bilinear': 1, 'bilinear_ac': 2}[mode]
+    check(lib().csb_resample_nhwc(ptr(x), ldx, xoff, N, Hi, Wi, C_, Ho, Wo, m, ptr(out), out.shape[3], yoff, stream()), "csb_resample_nhwc")
+    return out
+
+
+def image_prep_nhwc(img_u8, mean, std, swap_rb=False, CP=16):
+    """uint8 [N,H,W,3] (or [H,W,3]) -> fp16 NHWC [N,H,W,CP], (x-mean)/std, zero padded channels."""
+    if img_u8.dim() == 3:
+        img_u8 = img_u8[None]
+    N, H, W, _ = img_u8.shape
+    out = torch.empty((N, H, W, CP), device=img_u8.device, dtype=torch.float16)
+    m = (C.c_float * 3)(*[float(v) for v in mean]); s = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib().csb_image_prep_nhwc(ptr(img_u8), C.c_longlong(N * H * W), m, s, int(swap_rb), CP, ptr(out), stream()), "csb_image_prep_nhwc")
+    return out

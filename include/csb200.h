@@ -112,12 +112,82 @@ CSB_API int csb_frame_pack_u8(const float* render, int H, int W, uint8_t* frame,
 CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, int ph, double cx, double cy, uint8_t* out, void* stream);
 
 /* Fused Ken-Burns frame: shift + render (C=4: BGR + depth) + normalise + disocclusion fill + u8 pack, then
- * crop+resize -- the body of the reference's frame loop, kenburns_effect.py:1028-1040,1069-1070, as 5 launches.
+ * crop+resize -- the body of the reference's frame loop, kenburns_effect.py:1028-1040,1069-1070, as 6 launches.
  *   points [1,3,N], data [1,4,N]; scratch as csb_pointcloud_render (C=4); packed [H,W,3] u8 scratch;
  *   out [H,W,3] u8;  depth_out [H,W] fp32 or NULL (filled depth plane, needed only by the bokeh stage). */
 CSB_API int csb_kenburns_frame(const float* points, const float* data, int N, int H, int W, double focal, double baseline,
                        const float* shift, const float* shift_dev, int pw, int ph, double cx, double cy,
                        int32_t* zkey, float* zee, float* acc, uint8_t* packed, uint8_t* out, float* depth_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contractions on the tcgen05 tensor cores (csrc/tc_conv.cu).  In the reference every conv / linear layer of
+ * the detector, ISNet, LeReS and Inpaint nets is a torch.nn.Conv2d / Linear dispatched to cuDNN/cuBLAS fp32 NCHW
+ * (e.g. animeinsseg/models/animeseg_refine/isnet.py:95-108, depth_modules/leres/leres/network_auxi.py:100-124,
+ * anime_3dkenburns/models/pointcloud_inpainting.py:85-90 and the mmdet modules restated in SURVEY.md Appendix A).
+ *
+ * csb_conv2d_nhwc:  y = act(conv(x, w) + bias [+ residual]) with fp32 accumulation.
+ *   x        NHWC fp16/bf16 [N,Hin,Win,in_ld], channels in_coff .. in_coff+Cin are convolved (Cin % 16 == 0)
+ *   w        [Cout][R][S][Cin] fp16/bf16 (K-major rows; BatchNorm / layer-scale already folded in)
+ *   bias     [Cout] fp32 or NULL;  act_param: per-channel PReLU slope [Cout] or NULL
+ *   residual NHWC like y (res_ld/res_coff), added before (res_mode 1) or after (res_mode 2) the activation
+ *   y        NHWC fp16/bf16 [N,Hout,Wout,out_ld] written at channel offset out_coff (concat fusion), or
+ *   y_f32    the same in fp32 (exactly one of y / y_f32 is used when both are given: y_f32 wins)
+ * ------------------------------------------------------------------------------------------- */
+#define CSB_ACT_NONE 0
+#define CSB_ACT_RELU 1
+#define CSB_ACT_SILU 2
+#define CSB_ACT_GELU 3        /* exact erf GELU */
+#define CSB_ACT_PRELU 4
+#define CSB_ACT_SIGMOID 5
+#define CSB_ACT_SOFTPLUS 6
+#define CSB_ACT_HARDSIGMOID 7
+
+typedef struct csb_conv_desc {
+    int N, Hin, Win, Cin;
+    int in_ld, in_coff;
+    int Cout, R, S, stride, pad, dil;
+    int out_ld, out_coff;
+    int act;
+    int res_mode, res_ld, res_coff;
+    int dtype;                /* 0 fp16, 1 bf16 */
+} csb_conv_desc;
+
+CSB_API int csb_conv2d_nhwc(const csb_conv_desc* desc, const void* x, const void* w, const float* bias, const float* act_param,
+                    const void* residual, void* y, float* y_f32, void* stream);
+
+/* HBM-bound NHWC fp16 layers between the tensor-core convs (csrc/nn_elem.cu).  Channel-slice addressing: ld = channels of the
+ * buffer, off = first channel, so concats (CSPNeXtPAFPN, MaskFeatModule, CSPLayer -- SURVEY.md Appendix A.3-A.6) need no copy.
+ *   csb_dwconv_nhwc     depthwise KxK (K = 3/5/7, stride 1, zero pad K/2) + bias, then LayerNorm over C (ln_gamma/ln_beta != NULL:
+ *                       the ConvNeXt block head, Appendix A.4) and/or an activation (CSPNeXtBlock depthwise 5x5 + folded BN + SiLU).
+ *                       w is [K][K][C] fp32.
+ *   csb_layernorm_nhwc  LayerNorm2d over the channels of each pixel (ConvNeXt stem / downsample / output norms).
+ *   csb_resample_nhwc   mode 0 nearest, 1 bilinear align_corners=False, 2 bilinear align_corners=True, into a channel slice.
+ *   csb_image_prep_nhwc uint8 HWC -> fp16 NHWC with CP channels (zero padded), (x - mean)/std, optional R/B swap
+ *                       (mmdet DetDataPreprocessor; animeinsseg/__init__.py:63-76). */
+CSB_API int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w, const float* bias, const float* ln_gamma, const float* ln_beta,
+                    float eps, int act, int N, int H, int W, int C, int K, void* y, int ldy, int yoff, void* stream);
+CSB_API int csb_layernorm_nhwc(const void* x, int ldx, int xoff, const float* gamma, const float* beta, float eps, long long npix, int C,
+                       void* y, int ldy, int yoff, void* stream);
+CSB_API int csb_resample_nhwc(const void* x, int ldx, int xoff, int N, int Hi, int Wi, int C, int Ho, int Wo, int mode, void* y, int ldy, int yoff,
+                      void* stream);
+CSB_API int csb_image_prep_nhwc(const uint8_t* img, long long npix, const float* mean3, const float* std3, int swap_rb, int CP, void* y, void* stream);
+
+/* RTMDet-Ins post-processing (csrc/det_post.cu) -- SURVEY.md §8a rows A5-A8; mmdet predict_by_feat / mmcv batched_nms restated in
+ * SURVEY.md Appendix A.7, mask head animeinsseg/models/rtmdet_inshead_custom.py:253-303, mask tail animeinsseg/__init__.py:361-370.
+ * Single class.  Per level l (L <= 4): cls[l] [N,h,w,1], reg[l] [N,h,w,4] (ltrb distances in pixels), ker[l] [N,h,w,169], all fp32 NHWC.
+ *   csb_rtmdet_select: score = sigmoid(cls) > score_thr, top nms_pre per level (stable descending), distance2bbox + clamp to the image,
+ *     min_bbox_size filter (< 0 disables), greedy NMS (IoU > iou_thr suppressed), first max_per_img kept.
+ *     scratch: cand [N, L*nms_pre, 10] fp32, cand_count [N*L] int32.
+ *     out: boxes [N,max_per_img,4] xyxy, scores [N,max_per_img], priors [N,max_per_img,4] (x,y,stride,stride),
+ *          kernels [N,max_per_img,169], num [N] int32 (device; rows >= num[n] are zero).
+ *   csb_rtmdet_masks: logits [N,max_per_img,h,w] (scratch/output) = dynamic-conv mask head on mask_feat [N,h,w,8] fp32; then
+ *     F.interpolate(scale_factor=stride0) -> F.interpolate(size=(resized_h,resized_w)) -> crop [:out_h,:out_w] -> sigmoid > mask_thr
+ *     -> masks [N,max_per_img,out_h,out_w] uint8 0/1 (torch.bool compatible). */
+CSB_API int csb_rtmdet_select(const float* const* cls, const float* const* reg, const float* const* ker, const int* hs, const int* ws, const int* strides,
+                      int L, int N, float score_thr, int nms_pre, float iou_thr, int max_per_img, float min_bbox_size, int img_h, int img_w,
+                      float* cand, int* cand_count, float* boxes, float* scores, float* priors, float* kernels, int* num, void* stream);
+CSB_API int csb_rtmdet_masks(const float* mask_feat, const float* kernels, const float* priors, const int* num, int N, int max_per_img, int h, int w,
+                     int stride0, int out_h, int out_w, int resized_h, int resized_w, float mask_thr, float* logits, uint8_t* masks, void* stream);
 
 #ifdef __cplusplus
 }

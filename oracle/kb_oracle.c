@@ -28,6 +28,15 @@
 
 #define ORC_API __attribute__((visibility("default")))
 
+/* CUDA float -> int conversion (cvt.rzi.s32.f32): NaN -> 0, saturating -- the reference kernels run on the GPU, so `(int) floor(NaN)`
+ * is 0 there, not C's undefined behaviour. */
+static inline int f2i(float v) {
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return (-2147483647 - 1);
+    return (int) v;
+}
+
 typedef struct { int ok; float ox, oy, err; int x0, y0; float wnw, wne, wsw, wse; } proj_t;
 
 /* models/utils.py:76-135 (identical in :229-266) */
@@ -45,7 +54,7 @@ static proj_t project(float x, float y, float z, int H, int W, double focal, dou
     p.ox = (float) (((double) ix + (0.5 * W)) - 0.5);               /* :96 */
     p.oy = (float) (((double) iy + (0.5 * H)) - 0.5);               /* :97 */
     p.err = (float) (1000000.0 - ((focal * baseline) / ((double) z + 0.0000001)));  /* :99 */
-    p.x0 = (int) floorf(p.ox); p.y0 = (int) floorf(p.oy);           /* :101-102 */
+    p.x0 = f2i(floorf(p.ox)); p.y0 = f2i(floorf(p.oy));           /* :101-102 */
     int sex = p.x0 + 1, sey = p.y0 + 1;
     p.wnw = ((float) sex - p.ox) * ((float) sey - p.oy);            /* :110-113 */
     p.wne = (p.ox - (float) p.x0) * ((float) sey - p.oy);
@@ -175,8 +184,8 @@ ORC_API void orc_fill_disocclusion(const float* in, const float* depth, int B, i
             float ffx = (float) x, ffy = (float) y, tfx = (float) x, tfy = (float) y;
             int ifx = 0, ify = 0, itx = 0, ity = 0;
             do {                                                    /* :188-196 */
-                ffx -= dirx[d]; ifx = (int) roundf(ffx);
-                ffy -= diry[d]; ify = (int) roundf(ffy);
+                ffx -= dirx[d]; ifx = f2i(roundf(ffx));
+                ffy -= diry[d]; ify = f2i(roundf(ffy));
                 if (ifx < 0 || ifx >= W) break;
                 if (ify < 0 || ify >= H) break;
                 if (Dp[(long) ify * W + ifx] > 0.0f) break;
@@ -184,8 +193,8 @@ ORC_API void orc_fill_disocclusion(const float* in, const float* depth, int B, i
             if (ifx < 0 || ifx >= W) continue;
             if (ify < 0 || ify >= H) continue;
             do {                                                    /* :199-207 */
-                tfx += dirx[d]; itx = (int) roundf(tfx);
-                tfy += diry[d]; ity = (int) roundf(tfy);
+                tfx += dirx[d]; itx = f2i(roundf(tfx));
+                tfy += diry[d]; ity = f2i(roundf(tfy));
                 if (itx < 0 || itx >= W) break;
                 if (ity < 0 || ity >= H) break;
                 if (Dp[(long) ity * W + itx] > 0.0f) break;

@@ -1,0 +1,98 @@
+"""GPU numerics of the tcgen05 implicit-GEMM conv engine against a plain PyTorch fp32 reference of the same op
+(inputs/weights rounded to fp16 first, so the only differences are fp32 accumulation order and the fp16 output rounding).
+Tolerance: |err| <= 2e-3 * max|ref| + 1e-3 (fp16 output has 2^-11 relative rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    from cartoonsegmentation_b200 import engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return engine
+
+
+def ref_conv(x_nhwc, w_oihw, bias, stride, pad, dil, act, residual=None, res_mode=0, slope=None):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w_oihw.half().float(), bias, stride=stride, padding=pad, dilation=dil)
+    if residual is not None and res_mode == 1:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    if act == 'relu': y = F.relu(y)
+    elif act == 'silu': y = F.silu(y)
+    elif act == 'gelu': y = F.gelu(y)
+    elif act == 'prelu': y = F.prelu(y, slope)
+    elif act == 'sigmoid': y = torch.sigmoid(y)
+    if residual is not None and res_mode == 2:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, dil, act
+    (1, 16, 16, 64, 64, 1, 1, 0, 1, None),          # smallest GEMM: one tile, one k-block
+    (2, 24, 40, 128, 256, 1, 1, 0, 1, 'silu'),      # 1x1, flat mode, N tile 256
+    (1, 32, 32, 64, 128, 3, 1, 1, 1, 'relu'),       # 3x3 s1: TMA zero padding on all borders
+    (2, 20, 28, 128, 96, 3, 1, 1, 1, 'silu'),       # ragged spatial tiles, Cout not a multiple of 32
+    (1, 33, 47, 64, 64, 3, 2, 1, 1, 'relu'),        # stride 2 through elementStrides, odd sizes
+    (1, 32, 32, 256, 512, 3, 1, 1, 1, None),        # two N tiles, 36 k-blocks
+    (1, 24, 24, 64, 64, 3, 1, 2, 2, 'relu'),        # dilation 2 (ISNet RSU)
+    (1, 16, 16, 512, 2048, 1, 1, 0, 1, 'gelu'),     # ConvNeXt MLP up-projection
+    (1, 40, 40, 32, 32, 3, 1, 1, 1, 'prelu'),       # 32-channel layers (Inpaint net): 64 B swizzle
+    (1, 40, 40, 16, 48, 3, 1, 1, 1, None),          # 16-channel k-block: 32 B swizzle
+    (1, 64, 64, 256, 169, 1, 1, 0, 1, None),        # rtm_kernel head: 169 outputs, scalar store path
+    (1, 128, 128, 256, 256, 3, 1, 1, 1, 'silu'),    # the hottest detector shape (Appendix B)
+    (3, 8, 8, 64, 16, 7, 1, 3, 1, None),            # 7x7, tiny maps, batch 3
+    (1, 64, 64, 64, 64, 4, 4, 0, 1, None),          # 4x4 stride 4 (patchify)
+    (1, 32, 32, 128, 256, 2, 2, 0, 1, None),        # 2x2 stride 2 (ConvNeXt downsample)
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad,dil,act", CASES)
+def test_conv_vs_torch(eng, N, H, W, Cin, Cout, k, stride, pad, dil, act):
+    g = torch.Generator(device='cuda').manual_seed(H * 1000 + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, device='cuda', generator=g).half()
+    w = (torch.randn(Cout, Cin, k, k, device='cuda', generator=g) / (Cin * k * k) ** 0.5)
+    b = torch.randn(Cout, device='cuda', generator=g) * 0.1
+    slope = torch.rand(Cout, device='cuda', generator=g) * 0.5 if act == 'prelu' else None
+    y = eng.conv2d_nhwc(x, eng.pack_conv_weight(w), b, stride=stride, pad=pad, dil=dil, act=act, act_param=slope)
+    r = ref_conv(x, w, b, stride, pad, dil, act, slope=slope)
+    torch.cuda.synchronize()
+    err = (y.float() - r).abs().max().item()
+    tol = 2e-3 * r.abs().max().item() + 1e-3
+    assert y.shape == r.shape
+    assert err <= tol, f"max err {err} > {tol}"
+
+
+def test_conv_residual_slices_and_f32(eng):
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn(2, 24, 24, 192, device='cuda', generator=g).half()
+    w = torch.randn(64, 128, 3, 3, device='cuda', generator=g) / (128 * 9) ** 0.5
+    b = torch.randn(64, device='cuda', generator=g) * 0.1
+    res = torch.randn(2, 24, 24, 64, device='cuda', generator=g).half()
+    wp = eng.pack_conv_weight(w)
+    # input = channel slice [64:192) of x, output written into channels [32:96) of a 128-channel tensor (concat fusion)
+    out = torch.zeros(2, 24, 24, 128, device='cuda', dtype=torch.float16)
+    eng.conv2d_nhwc(x, wp, b, pad=1, act='silu', residual=res, res_mode=2, out=out, out_coff=32, in_coff=64)
+    r = ref_conv(x[..., 64:], w, b, 1, 1, 1, 'silu', residual=res, res_mode=2)
+    assert (out[..., 32:96].float() - r).abs().max().item() <= 2e-3 * r.abs().max().item() + 1e-3
+    assert out[..., :32].abs().max().item() == 0 and out[..., 96:].abs().max().item() == 0
+    # residual before activation (ResNeXt bottleneck), fp32 output
+    y = eng.conv2d_nhwc(x, wp, b, pad=1, act='relu', residual=res, res_mode=1, in_coff=64, out_f32=True)
+    r = ref_conv(x[..., 64:], w, b, 1, 1, 1, 'relu', residual=res, res_mode=1)
+    assert y.dtype == torch.float32 and (y - r).abs().max().item() <= 5e-4 * r.abs().max().item() + 1e-4
+    # bf16
+    xb, wb = x.bfloat16(), eng.pack_conv_weight(w, torch.bfloat16)
+    yb = eng.conv2d_nhwc(xb, wb, b, pad=1, in_coff=64, out_f32=True)
+    rb = F.conv2d(xb[..., 64:].float().permute(0, 3, 1, 2), w.bfloat16().float(), b, padding=1).permute(0, 2, 3, 1)
+    assert (yb - rb).abs().max().item() <= 5e-4 * rb.abs().max().item() + 1e-4
+
+
+def test_conv_rejects_bad_arguments(eng):
+    x = torch.zeros(1, 8, 8, 24, device='cuda', dtype=torch.float16)
+    w = torch.zeros(16, 3, 3, 24, device='cuda', dtype=torch.float16)
+    with pytest.raises(Exception):
+        eng.conv2d_nhwc(x, w, None, pad=1)           # Cin = 24 is not a multiple of 16
