@@ -90,3 +90,302 @@ def kenburns_frame(tenPoints, tenData, intWidth, intHeight, fltFocal, fltBaselin
                                    ptr(scratch.zkey), ptr(scratch.zee), ptr(scratch.acc), ptr(scratch.packed), ptr(out), ptr(depth), stream()),
           "csb_kenburns_frame")
     return out, depth
+
+
+# ================================================================================================================
+# Call surface of the reference: KenBurnsConfig (reference :207-366), build_kenburns_cfg (:369-374), KenBurnsPipeline (:392-1081)
+# ================================================================================================================
+import math
+from copy import copy as _shallow_copy
+from dataclasses import dataclass, field, fields
+from typing import Any, Optional, Union
+
+from ..animeinsseg import AnimeInsSeg, AnimeInstances
+from .common import process_autozoom, shift_scalars
+
+_ALIASES = {'fltFocal': 'focal', 'fltBaseline': 'baseline', 'intWidth': 'int_width', 'intHeight': 'int_height', 'fltDispmin': 'disparity_min',
+            'fltDispmax': 'disparity_max', 'objDepthrange': 'depth_range', 'tenRawImage': 'tensor_raw_image', 'tenRawDisparity': 'raw_disparity',
+            'tenRawDepth': 'raw_depth', 'tenRawPoints': 'raw_point', 'tenRawUnaltered': 'raw_unaltered', 'tenInpaImage': 'inpainted_img',
+            'tenInpaDisparity': 'inpainted_disparity', 'tenInpaDepth': 'inpainted_depth', 'tenInpaPoints': 'inpainted_points'}
+
+
+@dataclass
+class KenBurnsConfig:
+    """Same fields and dict-style aliases (the upstream `objCommon` names) as the reference dataclass, kenburns_effect.py:207-366."""
+    detector: str = 'animeinsseg'
+    det_ckpt: str = 'models/AnimeInstanceSegmentation/rtmdetl_e60.ckpt'
+    det_size: int = 640
+    scale_depth: bool = False
+    depth_field: bool = False
+    mask_refine_kwargs: dict = field(default_factory=dict)
+    marigold_kwargs: dict = field(default_factory=dict)
+    pred_score_thr: float = 0.3
+    depth_est: str = 'zoe'
+    depth_est_device: str = ''
+    depth_refinement: str = 'default'
+    depthest_use_medium: bool = False
+    inpaint_type: str = 'default'
+    num_frame: int = 75
+    playback: bool = True
+    auto_zoom: bool = True
+    focal: float = 1024 / 2.0
+    baseline: float = 40.0
+    dof_speed: float = 50.
+    depth_factor: int = 1
+    lightness_factor: int = 13
+    max_size: int = 720
+    int_height: int = 1024
+    int_width: int = 1024
+    default_depth_refine: bool = False
+    refine_crf: bool = True
+    depth_est_size: int = 640
+    sd_img2img_url: str = 'http://127.0.0.1:7860/sdapi/v1/img2img'
+    ldm_inpaint_options: dict = field(default_factory=dict)
+    ldm_inpaint_size: int = 0
+    instances: AnimeInstances = None
+    # non-init state (class attributes in the reference)
+    disparity_min = 0
+    disparity_max = 0
+    depth_range = None
+    tensor_raw_image = None
+    original_img_nparray = None
+    raw_disparity = None
+    raw_depth = None
+    raw_point = None
+    raw_unaltered = None
+    inpainted_img = None
+    inpainted_disparity = None
+    inpainted_depth = None
+    inpainted_points = None
+    bg_prompt = None
+    save_path = r''
+    stage_depth_coarse = None
+    stage_depth_adjusted = None
+    stage_depth_final = None
+
+    def __post_init__(self):
+        # the reference keeps these as shared class-level lists that grow forever (:284-285, SURVEY Appendix C.15); per-config here
+        self.stage_inpainted_imgs = []
+        self.stage_inpainted_masks = []
+
+    def __getitem__(self, item: str):
+        return getattr(self, _ALIASES.get(item, item))
+
+    def __setitem__(self, item, value):
+        setattr(self, _ALIASES.get(item, item), value)
+
+    def copy(self):
+        """Reference: deepcopy (:365).  Tensors are immutable inputs of the pipeline, so a shallow field copy is equivalent and
+        avoids cloning hundreds of MB of device memory."""
+        c = _shallow_copy(self)
+        c.stage_inpainted_imgs, c.stage_inpainted_masks = list(self.stage_inpainted_imgs), list(self.stage_inpainted_masks)
+        return c
+
+
+def build_kenburns_cfg(tgt_cfg: Union[str, dict]):
+    if isinstance(tgt_cfg, str):
+        import yaml                                   # the reference uses OmegaConf.load (:370); plain YAML is what the shipped configs are
+        with open(tgt_cfg) as f:
+            tgt_cfg = dict(yaml.safe_load(f))
+    fieldSet = {f.name for f in fields(KenBurnsConfig) if f.init}
+    return KenBurnsConfig(**{k: v for k, v in tgt_cfg.items() if k in fieldSet})
+
+
+def scaledown_maxsize(img: np.ndarray, max_size: int, divisior: int = None):
+    """utils/io_utils.py:254-274: only ever shrinks; Python banker's round(); cv2 INTER_LINEAR (host side, as in the reference)."""
+    import cv2
+    im_h, im_w = img.shape[:2]
+    ori_h, ori_w = im_h, im_w
+    resize_ratio = max_size / max(im_h, im_w)
+    if max_size < max(im_h, im_w):
+        im_h, im_w = int(round(im_h * resize_ratio)), int(round(im_w * resize_ratio))
+    if divisior is not None:
+        im_w, im_h = int(round(im_w / divisior) * divisior), int(round(im_h / divisior) * divisior)
+    if im_w != ori_w or im_h != ori_h:
+        img = cv2.resize(img, (im_w, im_h), interpolation=cv2.INTER_LINEAR)
+    return img
+
+
+def depth_adjustment_animesseg(instances: AnimeInstances, tenDisparity, tenImage, use_medium=False):
+    """reference :39-91 -- per instance: flatten the disparity under the mask to the maximum found in the bottom 3% of its rows.
+    Host-orchestrated torch glue exactly as the reference (K sequential passes, .item() syncs); a segmented-reduction kernel is the
+    planned replacement."""
+    assert tenDisparity.shape[0] == 1
+    tenMasks = [] if instances is None or instances.is_empty else [instances.masks[i].float() for i in range(instances.masks.shape[0])]
+    resized = tenDisparity.shape[2] != tenImage.shape[2] or tenDisparity.shape[3] != tenImage.shape[3]
+    tenAdjusted = torch.nn.functional.interpolate(tenDisparity, size=(tenImage.shape[2], tenImage.shape[3]), mode='bilinear', align_corners=False) \
+        if resized else tenDisparity
+    for tenAdjust in tenMasks:
+        tenPlane = tenAdjusted * tenAdjust
+        if tenPlane.sum().item() == 0:
+            continue
+        if not use_medium:
+            rows = (tenPlane.sum([3], True) > 0.0).flatten().nonzero()
+            intTop, intBottom = rows[0].item(), rows[-1].item()
+            tenAdjusted = ((1.0 - tenAdjust) * tenAdjusted) + (tenAdjust * tenPlane[:, :, int(round(intTop + (0.97 * (intBottom - intTop)))):, :].max())
+        else:
+            tenAdjusted[tenPlane > 0] = tenAdjusted[tenPlane > 0].median()
+    if resized:
+        return torch.nn.functional.interpolate(tenAdjusted, size=(tenDisparity.shape[2], tenDisparity.shape[3]), mode='bilinear', align_corners=False)
+    return tenAdjusted
+
+
+class KenBurnsPipeline:
+    """reference :392.  Same public methods; every tensor op on the hot path goes through the C ABI (include/csb200.h)."""
+
+    def __init__(self, cfg: Union[KenBurnsConfig, str, dict] = None, device: str = None) -> None:
+        if cfg is None:
+            cfg = KenBurnsConfig()
+        elif isinstance(cfg, (str, dict)):
+            cfg = build_kenburns_cfg(cfg)
+        elif not isinstance(cfg, KenBurnsConfig):
+            raise NotImplementedError
+        self.cfg = cfg
+        self.device = torch.device('cuda' if device is None else device)
+        self.animeinsseg = None
+        self.depth_model = None          # callable: (img_bgr_u8 ndarray, img_tensor [1,3,H,W]) -> disparity [1,1,H,W] on the device
+        self.kenburns_inpaintnet = None
+        self.depth_refinenet = None
+        self.inpaint_type = 'default'
+        self._frame_scratch = None
+        self.set_detector(cfg.detector)
+        self.set_depth_estimation(cfg.depth_est)
+        self.set_inpainting(cfg.inpaint_type)
+
+    # ---- component selection (reference :427-560)
+    def set_detector(self, detector: str, det_ckpt=None):
+        if detector != 'animeinsseg':
+            raise NotImplementedError(f"detector '{detector}' is outside the hot path (SURVEY.md §2 row 7: sam / maskrcnn are out of scope)")
+        if self.animeinsseg is None:
+            import os
+            ck = det_ckpt if det_ckpt is not None else (self.cfg.det_ckpt if isinstance(self.cfg.det_ckpt, str) and os.path.exists(self.cfg.det_ckpt) else None)
+            self.animeinsseg = AnimeInsSeg(ck, default_det_size=self.cfg.det_size, device=self.device, refine_kwargs={'refine_method': 'none'})
+
+    def set_depth_estimation(self, depth_est: str):
+        self.cfg.depth_est = depth_est
+        if depth_est not in ('zoe', 'leres', 'marigold', 'default', 'external'):
+            raise NotImplementedError(depth_est)
+
+    def set_inpainting(self, inpainting: str):
+        self.inpaint_type = inpainting
+
+    def set_depth_refinement(self, depth_refinement: str):
+        raise NotImplementedError("Refine disparity net (SURVEY.md §8f rank 2) is not built yet")
+
+    def set_config(self, cfg: KenBurnsConfig):
+        self.cfg = cfg
+
+    def update_config_param(self, cfg_key: str, cfg_value: Any):
+        self.cfg[cfg_key] = cfg_value
+
+    # ---- segmentation (reference :862-872)
+    def run_instance_segmentation(self, img: np.ndarray, scale_down_to_maxsize=True):
+        if scale_down_to_maxsize:
+            img = scaledown_maxsize(img, self.cfg.max_size)
+        kw = self.cfg.mask_refine_kwargs if self.cfg.mask_refine_kwargs else {'refine_method': 'none'}       # `{}` selects 'none' in the reference (Appendix C.8)
+        instances = self.animeinsseg.infer(img, self.cfg.pred_score_thr, kw, output_type='tensor')
+        return instances, img
+
+    # ---- depth (reference :583-635)
+    def infer_disparity(self, img: np.ndarray, instances: AnimeInstances, img_tensor=None, kcfg: KenBurnsConfig = None, verbose=False):
+        kcfg = self.cfg if kcfg is None else kcfg
+        if img_tensor is None:
+            img_tensor = torch.from_numpy(np.ascontiguousarray(img.transpose(2, 0, 1)[None].astype(np.float32) * (1.0 / 255.0))).to(self.device)
+        if self.depth_model is None:
+            raise NotImplementedError(f"depth estimator '{self.cfg.depth_est}' (SURVEY.md §8a rows B1-B6) is not built yet; set pipeline.depth_model "
+                                      "to a callable or pass disparity= to generate_kenburns_config")
+        disparity = self.depth_model(img, img_tensor)
+        disparity = depth_adjustment_animesseg(instances, disparity, img_tensor, use_medium=self.cfg.depthest_use_medium)      # :604
+        return disparity
+
+    # ---- reference :898-951
+    def generate_kenburns_config(self, img: np.ndarray, instances: Optional[AnimeInstances] = None, verbose: bool = False, savep=None, disparity=None):
+        """`disparity` (extension): a precomputed raw disparity [1,1,H,W]; skips the depth estimator (still instance-adjusted)."""
+        if isinstance(img, str):
+            import cv2
+            img = cv2.imread(img)
+        with torch.no_grad():
+            if instances is None:
+                instances, _ = self.run_instance_segmentation(img, scale_down_to_maxsize=False)
+            img = scaledown_maxsize(img, self.cfg.max_size)
+            instances.resize(img.shape[0], img.shape[1])
+            self.cfg.int_height, self.cfg.int_width = img.shape[:2]
+            img_u8 = torch.from_numpy(np.ascontiguousarray(img)).to(self.device)
+            cfg: KenBurnsConfig = self.cfg.copy()
+            if disparity is None:
+                disparity = self.infer_disparity(img, instances, None, kcfg=cfg)
+            else:
+                img_tensor = (img_u8.permute(2, 0, 1)[None].float() * (1.0 / 255.0))
+                disparity = depth_adjustment_animesseg(instances, disparity.to(self.device).float(), img_tensor, use_medium=self.cfg.depthest_use_medium)
+            c = disparity_to_cloud(disparity, cfg.focal, cfg.baseline, image_u8=img_u8)                  # :928-937 fused, one D2H of 8 floats
+            cfg['fltDispmin'], cfg['fltDispmax'], cfg['objDepthrange'] = c['dispmin'], c['dispmax'], c['depthrange']
+            H, W = img.shape[:2]
+            cfg['tenRawImage'] = c['data'][:, :3].view(1, 3, H, W)
+            cfg['tenRawDisparity'], cfg['tenRawDepth'] = c['disparity'], c['depth']
+            cfg['tenRawPoints'], cfg['tenRawUnaltered'] = c['points'].view(1, 3, -1), c['unaltered'].view(1, 3, -1)
+            cfg.inpainted_img = cfg['tenRawImage'].view(1, 3, -1)
+            cfg['tenInpaDisparity'] = cfg['tenRawDisparity'].view(1, 1, -1)
+            cfg['tenInpaDepth'] = cfg['tenRawDepth'].view(1, 1, -1)
+            cfg['tenInpaPoints'] = cfg['tenRawPoints'].view(1, 3, -1)
+            cfg._render_data = c['data']                       # [1,4,N] = image ++ depth, the frame loop's payload (:1036)
+            cfg.instances = instances
+            cfg.original_img_nparray = img
+            return cfg
+
+    # ---- reference :953-977
+    def autozoom(self, cfg: KenBurnsConfig, verbose: bool = False, inpaint: bool = True):
+        with torch.no_grad():
+            objFrom = {'fltCenterU': cfg.int_width / 2.0, 'fltCenterV': cfg.int_height / 2.0,
+                       'intCropWidth': int(math.floor(0.97 * cfg.int_width)), 'intCropHeight': int(math.floor(0.97 * cfg.int_height))}
+            objTo = process_autozoom({'fltShift': 100.0, 'fltZoom': 1.25, 'objFrom': objFrom}, cfg)
+            npy_frame_list, _ = self.process_kenburns({'fltSteps': np.linspace(0.0, 1.0, cfg.num_frame).tolist(), 'objFrom': objFrom, 'objTo': objTo,
+                                                       'boolInpaint': True}, cfg, inpaint, verbose)
+            return npy_frame_list
+
+    def inpaint(self, tenShift, tenPoints, objCommon, verbose=False):
+        raise NotImplementedError("point-cloud Inpaint net (SURVEY.md §8a rows C5-C6) is not built yet; call process_kenburns(..., inpaint=False)")
+
+    # ---- reference :979-1081
+    def process_kenburns(self, objSettings, objCommon: KenBurnsConfig, inpaint: bool = True, verbose: bool = False):
+        with torch.no_grad():
+            W, H = objCommon['intWidth'], objCommon['intHeight']
+            oF, oT = objSettings['objFrom'], objSettings['objTo']
+
+            def camera(fltStep):
+                fltFrom = 1.0 - fltStep
+                fltTo = 1.0 - fltFrom
+                fltShiftU = ((fltFrom * oF['fltCenterU']) + (fltTo * oT['fltCenterU'])) - (W / 2.0)
+                fltShiftV = ((fltFrom * oF['fltCenterV']) + (fltTo * oT['fltCenterV'])) - (H / 2.0)
+                fltCropWidth = (fltFrom * oF['intCropWidth']) + (fltTo * oT['intCropWidth'])
+                fltDepthFrom = objCommon['objDepthrange'][0]
+                fltDepthTo = objCommon['objDepthrange'][0] * (fltCropWidth / max(oF['intCropWidth'], oT['intCropWidth']))
+                return {'fltShiftU': fltShiftU, 'fltShiftV': fltShiftV, 'fltDepthFrom': fltDepthFrom, 'fltDepthTo': fltDepthTo}
+            if inpaint:
+                objCommon.inpainted_img = objCommon['tenRawImage'].view(1, 3, -1)
+                objCommon['tenInpaDisparity'] = objCommon['tenRawDisparity'].view(1, 1, -1)
+                objCommon['tenInpaDepth'] = objCommon['tenRawDepth'].view(1, 1, -1)
+                objCommon['tenInpaPoints'] = objCommon['tenRawPoints'].view(1, 3, -1)
+                for fltStep in [0.0, 1.0]:
+                    sh = np.array(shift_scalars(camera(fltStep), objCommon), np.float32)
+                    self.inpaint(1.1 * sh, None, objCommon, verbose)
+            if objCommon.depth_field:
+                raise NotImplementedError("depth-of-field bokeh (SURVEY.md §8f rank 1) is not built yet")
+            pts = objCommon['tenInpaPoints']
+            N = pts.shape[2]
+            data = getattr(objCommon, '_render_data', None)
+            if data is None or data.shape[2] != N:
+                data = torch.cat([objCommon.inpainted_img, objCommon['tenInpaDepth']], 1).view(1, 4, -1).contiguous()       # :1036
+            pw, ph = max(oF['intCropWidth'], oT['intCropWidth']), max(oF['intCropHeight'], oT['intCropHeight'])
+            steps = objSettings['fltSteps']
+            if self._frame_scratch is None or self._frame_scratch.key[2:4] != (H, W):
+                self._frame_scratch = FrameScratch(H, W, pts.device)
+            out_dev = torch.empty((len(steps), H, W, 3), device=pts.device, dtype=torch.uint8)
+            out_host = torch.empty((len(steps), H, W, 3), dtype=torch.uint8).pin_memory()
+            for i, fltStep in enumerate(steps):                                    # the reference frame loop, :1015-1072
+                sh = np.array(shift_scalars(camera(fltStep), objCommon), np.float32)
+                kenburns_frame(pts, data, W, H, objCommon['fltFocal'], objCommon['fltBaseline'], sh, pw, ph, W / 2.0, H / 2.0,
+                               scratch=self._frame_scratch, out=out_dev[i])
+                out_host[i].copy_(out_dev[i], non_blocking=True)                   # D2H overlaps the next frame's render
+            torch.cuda.current_stream().synchronize()
+            frames = [out_host[i].numpy() for i in range(len(steps))]
+            return [frames, objCommon]

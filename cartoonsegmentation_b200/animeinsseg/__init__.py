@@ -1,0 +1,165 @@
+"""B200 implementation of the reference's `animeinsseg` package surface for the hot path: `AnimeInsSeg.infer` -> `AnimeInstances`
+(reference animeinsseg/__init__.py:185-227, 395-504, 704-708).
+
+The mmdet model object of the reference (`self.model`, built from the checkpoint-embedded config, :196-209) is replaced by
+`rtmdet.RTMDetIns` (tcgen05 conv engine) + the post-processing kernels of csrc/det_post.cu; `self.model.bbox_head.test_cfg` stays a
+mutable dict with the reference's keys (`max_per_img`, `mask_thr_binary`, `score_thr`, `nms_pre`, `nms`, `min_bbox_size`), so
+`set_max_instance` / `set_mask_threshold` behave as in the reference.
+"""
+import ctypes as C
+import math
+from types import SimpleNamespace
+from typing import List, Union
+
+import numpy as np
+import torch
+
+from .._lib import check, lib, ptr, stream
+from .anime_instances import AnimeInstances
+from .rtmdet import RTMDetIns, STRIDES, synthetic_state_dict
+
+__all__ = ["AnimeInsSeg", "AnimeInstances"]
+
+
+def rtmdet_postprocess(cls, reg, ker, mask_feat, img_hw, test_cfg, ori_hw=None, scale_factor=(1.0, 1.0)):
+    """A5-A8 on the device: (cls, reg, ker per level NHWC fp32, mask_feat [N,h,w,8]) ->
+    dict(boxes [N,K,4] xyxy in the ORIGINAL image frame, scores [N,K], num [N] int32 (device), masks [N,K,H,W] bool, logits)."""
+    N = cls[0].shape[0]
+    L = len(cls)
+    dev = cls[0].device
+    K, nms_pre = int(test_cfg['max_per_img']), int(test_cfg['nms_pre'])
+    hs = (C.c_int * L)(*[c.shape[1] for c in cls]); ws = (C.c_int * L)(*[c.shape[2] for c in cls]); st = (C.c_int * L)(*STRIDES[:L])
+    arr = lambda ts: (C.c_void_p * L)(*[t.data_ptr() for t in ts])
+    cand = torch.empty((N, L * nms_pre, 10), device=dev); cand_count = torch.empty((N * L,), device=dev, dtype=torch.int32)
+    boxes = torch.empty((N, K, 4), device=dev); scores = torch.empty((N, K), device=dev); priors = torch.empty((N, K, 4), device=dev)
+    kernels = torch.empty((N, K, 169), device=dev); num = torch.empty((N,), device=dev, dtype=torch.int32)
+    cls = [t.contiguous() for t in cls]; reg = [t.contiguous() for t in reg]; ker = [t.contiguous() for t in ker]
+    check(lib().csb_rtmdet_select(arr(cls), arr(reg), arr(ker), hs, ws, st, L, N, C.c_float(test_cfg['score_thr']), nms_pre,
+                                  C.c_float(test_cfg['nms']['iou_threshold']), K, C.c_float(test_cfg['min_bbox_size']), int(img_hw[0]), int(img_hw[1]),
+                                  ptr(cand), ptr(cand_count), ptr(boxes), ptr(scores), ptr(priors), ptr(kernels), ptr(num), stream()), "csb_rtmdet_select")
+    h, w = mask_feat.shape[1:3]
+    ori_hw = img_hw if ori_hw is None else ori_hw
+    # mask tail (reference :361-370): x8, then resize to ceil(size * 1/scale_factor), crop to the original image
+    rh, rw = math.ceil(h * STRIDES[0] * (1.0 / scale_factor[0])), math.ceil(w * STRIDES[0] * (1.0 / scale_factor[1]))
+    logits = torch.empty((N, K, h, w), device=dev); masks = torch.empty((N, K, ori_hw[0], ori_hw[1]), device=dev, dtype=torch.uint8)
+    check(lib().csb_rtmdet_masks(ptr(mask_feat.contiguous()), ptr(kernels), ptr(priors), ptr(num), N, K, h, w, STRIDES[0], int(ori_hw[0]), int(ori_hw[1]),
+                                 rh, rw, C.c_float(test_cfg['mask_thr_binary']), ptr(logits), ptr(masks), stream()), "csb_rtmdet_masks")
+    if scale_factor != (1.0, 1.0):        # rescale boxes to the original frame (mmdet: bboxes /= scale_factor (w,h,w,h))
+        boxes = boxes / boxes.new_tensor([scale_factor[0], scale_factor[1], scale_factor[0], scale_factor[1]])
+    return dict(boxes=boxes, scores=scores, num=num, masks=masks.view(torch.bool), logits=logits, priors=priors, kernels=kernels)
+
+
+class AnimeInsSeg:
+    """reference animeinsseg/__init__.py:185.  `ckpt`: path to a checkpoint whose 'state_dict' uses mmdet parameter names, a state_dict,
+    or None for the seeded synthetic ConvNeXt-B RTMDet-Ins weights (BASELINE.json: 'random-init ConvNeXt-B RTMDet weights')."""
+
+    def __init__(self, ckpt=None, default_det_size: int = 640, device: str = None, refine_kwargs: dict = {'refine_method': 'none'},
+                 tagger_path: str = None, mask_thr=0.3) -> None:
+        self.device = torch.device('cuda' if device is None else device)
+        if self.device.type != 'cuda':
+            raise RuntimeError("cartoonsegmentation_b200 has no CPU path (the reference's device='cpu' mode is the oracle's job)")
+        if ckpt is None:
+            sd = synthetic_state_dict(0)
+        elif isinstance(ckpt, str):
+            obj = torch.load(ckpt, map_location='cpu')
+            sd = obj.get('state_dict', obj)
+        else:
+            sd = ckpt
+        net = RTMDetIns(sd, self.device)
+        test_cfg = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_threshold=0.6), max_per_img=100, min_bbox_size=0, mask_thr_binary=0.5)
+        self.model = SimpleNamespace(net=net, bbox_head=SimpleNamespace(test_cfg=test_cfg, prior_generator=SimpleNamespace(strides=[(s, s) for s in STRIDES])))
+        self.default_det_size = default_det_size
+        self.det_size = (default_det_size, default_det_size)
+        self.postprocess_refine = None
+        self.mask_thr = mask_thr
+        if refine_kwargs is not None:
+            self.set_refine_method(**refine_kwargs)
+
+    # ---- reference :395-399, :623-637, :704-708
+    def set_detect_size(self, det_size):
+        self.det_size = (det_size, det_size) if isinstance(det_size, int) else tuple(det_size)
+
+    def set_refine_method(self, refine_method: str = 'none', refine_size: int = 720):
+        if refine_method == 'none':
+            self.postprocess_refine = None
+        elif refine_method in ('animeseg', 'refinenet_isnet'):
+            raise NotImplementedError(f"refine method '{refine_method}' (ISNet mask refinement, SURVEY.md §8a row A10) is not built yet")
+        else:
+            raise NotImplementedError(f'Invalid refine method: {refine_method}')
+
+    def set_mask_threshold(self, mask_thr: float):
+        self.model.bbox_head.test_cfg['mask_thr_binary'] = mask_thr
+
+    def set_max_instance(self, num_ins):
+        self.model.bbox_head.test_cfg['max_per_img'] = num_ins
+
+    # ---- A1: mmdet Resize(keep_ratio) + Pad(size, 114) on the host (the reference does this in OpenCV on the CPU too)
+    def _prepare(self, img: np.ndarray):
+        import cv2
+        S = self.det_size
+        h, w = img.shape[:2]
+        sf = min(max(S) / max(h, w), min(S) / min(h, w))
+        nw, nh = int(w * sf + 0.5), int(h * sf + 0.5)
+        if (nw, nh) != (w, h):
+            img = cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
+        scale_factor = (nw / w, nh / h)
+        ph, pw = S[1], S[0]
+        if (nh, nw) != (ph, pw):
+            img = cv2.copyMakeBorder(img, 0, ph - nh, 0, pw - nw, cv2.BORDER_CONSTANT, value=(114, 114, 114))
+        return np.ascontiguousarray(img), scale_factor, (h, w)
+
+    @torch.no_grad()
+    def infer(self, imgs: Union[List, str, np.ndarray], pred_score_thr: float = 0.3, refine_kwargs: dict = None, output_type: str = "tensor",
+              det_size: int = None, save_dir: str = '', save_visualization: bool = False, save_annotation: str = '', infer_tags: bool = False,
+              obj_id_start: int = -1, img_id_start: int = -1, verbose: bool = False, infer_grey: bool = False, save_mask_only: bool = False,
+              val_dir=None, max_instances: int = 100, **kwargs):
+        if det_size is not None:
+            self.set_detect_size(det_size)
+        if refine_kwargs is not None:
+            self.set_refine_method(**refine_kwargs)
+        self.set_max_instance(max_instances)
+        if save_annotation or save_visualization or infer_tags:
+            raise NotImplementedError("annotation export / visualisation / tagging are outside the hot path (SURVEY.md §2 row 1)")
+        assert output_type in {'tensor', 'numpy'}
+        return_list = isinstance(imgs, list)
+        if not return_list:
+            imgs = [imgs]
+        loaded = []
+        for im in imgs:
+            if isinstance(im, str):
+                import cv2
+                im = cv2.imread(im)
+            loaded.append(im)
+        preds = [None] * len(loaded)
+        # images that share (shape after Resize/Pad, scale) go through the detector as ONE batch (the reference loops batch-1, :485)
+        groups = {}
+        for i, im in enumerate(loaded):
+            arr, sf, ori = self._prepare(im)
+            groups.setdefault((arr.shape, sf, ori), []).append((i, arr))
+        for (shape, sf, ori), items in groups.items():
+            batch = torch.from_numpy(np.stack([a for _, a in items])).to(self.device, non_blocking=True)
+            for j, inst in enumerate(self._det_forward(batch, sf, ori, pred_score_thr)):
+                preds[items[j][0]] = inst
+        for inst in preds:
+            if self.postprocess_refine is not None:
+                self.postprocess_refine(inst, None)
+            if output_type == 'numpy':
+                inst.to_numpy()
+        return preds if return_list else preds[0]
+
+    def _det_forward(self, batch_u8, scale_factor, ori_hw, pred_score_thr: float = 0.3):
+        """reference :447-462 for a batch: detector + post-process, then score filter, int32 truncation, xyxy -> xywh."""
+        cls, reg, ker, mask_feat = self.model.net.forward(batch_u8)
+        out = rtmdet_postprocess(cls, reg, ker, mask_feat, batch_u8.shape[1:3], self.model.bbox_head.test_cfg, ori_hw, scale_factor)
+        nums = out['num'].cpu().tolist()                                    # the one host read per batch
+        res = []
+        for n, k in enumerate(nums):
+            scores = out['scores'][n, :k]
+            keep = scores > pred_score_thr
+            if int(keep.sum()) < 1:
+                res.append(AnimeInstances())
+                continue
+            bboxes = out['boxes'][n, :k][keep].to(torch.int32)
+            bboxes[:, 2:] -= bboxes[:, :2]
+            res.append(AnimeInstances(out['masks'][n, :k][keep], bboxes, scores[keep]))
+        return res

@@ -78,17 +78,17 @@ def param_specs():
             for i in range(2):
                 _convmodule(s, f"bbox_head.{tower}.{lvl}.{i}", 256, 256, 3)
     for lvl in range(3):
-        s += [(f"bbox_head.rtm_cls.{lvl}.weight", (1, 256, 1, 1), 'conv_lin'), (f"bbox_head.rtm_cls.{lvl}.bias", (1,), 'cls_bias'),
+        s += [(f"bbox_head.rtm_cls.{lvl}.weight", (1, 256, 1, 1), 'conv_lin:25'), (f"bbox_head.rtm_cls.{lvl}.bias", (1,), 'cls_bias'),
               (f"bbox_head.rtm_reg.{lvl}.weight", (4, 256, 1, 1), 'conv_lin'), (f"bbox_head.rtm_reg.{lvl}.bias", (4,), 'reg_bias'),
-              (f"bbox_head.rtm_kernel.{lvl}.weight", (NUM_GEN_PARAMS, 256, 1, 1), 'conv_lin'), (f"bbox_head.rtm_kernel.{lvl}.bias", (NUM_GEN_PARAMS,), 'bias')]
+              (f"bbox_head.rtm_kernel.{lvl}.weight", (NUM_GEN_PARAMS, 256, 1, 1), 'conv_lin:4'), (f"bbox_head.rtm_kernel.{lvl}.bias", (NUM_GEN_PARAMS,), 'bias')]
     s += [("bbox_head.mask_head.fusion_conv.weight", (256, 768, 1, 1), 'conv_lin'), ("bbox_head.mask_head.fusion_conv.bias", (256,), 'bias')]
     for i in range(4):
         _convmodule(s, f"bbox_head.mask_head.stacked_convs.{i}", 256, 256, 3)
-    s += [("bbox_head.mask_head.projection.weight", (8, 256, 1, 1), 'conv_lin'), ("bbox_head.mask_head.projection.bias", (8,), 'bias')]
+    s += [("bbox_head.mask_head.projection.weight", (8, 256, 1, 1), 'conv_lin:4'), ("bbox_head.mask_head.projection.bias", (8,), 'bias')]
     return s
 
 
-def synthetic_state_dict(seed=0, cls_bias=-2.0):
+def synthetic_state_dict(seed=0, cls_bias=-5.0):
     """Seeded variance-preserving weights: conv std sqrt(2/fan_in) before SiLU/GELU/ReLU, 1/sqrt(fan_in) before linear
     outputs, biases U(-0.1,0.1), BN gamma U(0.8,1.2) beta U(-0.1,0.1) mean N(0,0.1) var U(0.8,1.2), LN gamma U(0.8,1.2), layer-scale 1.0.
     (The reference's 'random init' is PyTorch's default because init_weights() is never called, animeinsseg/__init__.py:204-209; that
@@ -99,12 +99,15 @@ def synthetic_state_dict(seed=0, cls_bias=-2.0):
     def u(shape, lo, hi):
         return torch.rand(shape, generator=g) * (hi - lo) + lo
     for name, shape, kind in param_specs():
+        gain = 1.0
+        if ':' in kind:                       # 'conv_lin:25' -> output gain, so that scores / mask logits are well spread (not clustered at 0)
+            kind, gain = kind.split(':')[0], float(kind.split(':')[1])
         if kind in ('conv_act', 'conv_lin', 'conv_res'):
             fan_in = 1
             for d in shape[1:]:
                 fan_in *= d
             std = math.sqrt(2.0 / fan_in) if kind == 'conv_act' else (0.5 / math.sqrt(fan_in) if kind == 'conv_res' else 1.0 / math.sqrt(fan_in))
-            sd[name] = torch.randn(shape, generator=g) * std
+            sd[name] = torch.randn(shape, generator=g) * (std * gain)
         elif kind in ('bias', 'bn_b', 'ln_b'):
             sd[name] = u(shape, -0.1, 0.1)
         elif kind in ('bn_w', 'ln_w', 'bn_v'):
@@ -255,10 +258,10 @@ class RTMDetIns:
         self.backbone(x16, {1: (cat3, 256), 2: (cat4, 512), 3: (c5, 0)})
         # ---- neck
         self.reduce[0](c5, out=catB5, out_coff=512)                                           # p5
-        E.resample_nhwc(catB5, h4, w4, 'nearest', out=cat4, xoff=512, yoff=0, C=512)
+        E.resample_nhwc(catB5, h4, w4, 'nearest', out=cat4, xoff=512, yoff=0, channels=512)
         t4 = self.top_down[0](cat4)
         self.reduce[1](t4, out=catB4, out_coff=256)                                           # p4
-        E.resample_nhwc(catB4, h3, w3, 'nearest', out=cat3, xoff=256, yoff=0, C=256)
+        E.resample_nhwc(catB4, h3, w3, 'nearest', out=cat3, xoff=256, yoff=0, channels=256)
         o3 = self.top_down[1](cat3)
         self.downs[0](o3, out=catB4, out_coff=0)
         o4 = self.bottom_up[0](catB4)

@@ -51,9 +51,9 @@ __device__ __forceinline__ void crop_px(const uint8_t* __restrict__ src, int H, 
 
 // resize.cpp: HResizeLinear<uchar,int,short,2048> + VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>.  6 B/px.
 __global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__ src, int H, int W, CropParams p, uint8_t* __restrict__ dst) {
-    const long long total = (long long) H * W;
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
-        int dx = (int) (i % W), dy = (int) (i / W);
+    const int total = H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int dx = i % W, dy = i / W;
         float fx = (float) ((dx + 0.5) * p.sx - 0.5);
         int ix = (int) floorf(fx);
         fx -= ix;
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__
         for (int c = 0; c < 3; ++c) {
             int s0 = c00[c] * ax0 + c01[c] * ax1, s1 = c10[c] * ax0 + c11[c] * ax1;
             int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
-            dst[i * 3 + c] = (uint8_t) clampi(v, 0, 255);
+            dst[(size_t) i * 3 + c] = (uint8_t) clampi(v, 0, 255);
         }
     }
 }

