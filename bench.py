@@ -105,58 +105,94 @@ def cpu_arm(imgs, disp, n_frames, threads):
 
 
 def run_reference(args):
-    """--impl reference: the reference Ken-Burns kernels are GPU-only cupy strings (anime_3dkenburns/common.py:74 hard-codes
-    .cuda()); its CPU implementation of this path is therefore the oracle port, run on all host cores."""
+    """--impl reference: the reference's CPU implementation of the same path on the host cores.  The real package cannot run here (mmdet /
+    mmcv / cupy absent, its Ken-Burns kernels are GPU-only cupy strings, anime_3dkenburns/common.py:74 hard-codes .cuda()), so this is the
+    oracle port: oracle/det_oracle.py (PyTorch fp32, all host threads) -> oracle/leres_oracle.py -> oracle/kb_oracle.c, one image per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import torch
+    from cartoonsegmentation_b200.animeinsseg import rtmdet
+    from cartoonsegmentation_b200.depth_modules import leres as L
+    from oracle import det_oracle as D, kb_oracle as orc, leres_oracle as LO
     cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    stages = [s_ for s_ in args.stages.split(",") if s_]
     imgs, disp = make_inputs(2)
-    per_step = cores                                          # one frame per host thread per step
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_arm(imgs, disp, per_step, cores)
+    det = D.RTMDetIns().eval(); det.load_state_dict(rtmdet.synthetic_state_dict(0))
+    ler = LO.RelDepthModel().eval(); ler.load_state_dict(L.synthetic_state_dict(0), strict=False)
+
+    def one(i):
+        img = imgs[i % 2]
+        masks = None
+        if 'seg' in stages:
+            masks = D.infer(det, img)['masks']
+        raw = LO.depth_est_leres(ler, img) if 'depth' in stages else disp[i % 2]
+        if masks is not None and len(masks):                       # depth_adjustment_animesseg (kenburns_effect.py:39-91)
+            d = torch.from_numpy(raw)[None, None].clone()
+            for m in masks.float():
+                plane = d * m
+                if plane.sum().item() == 0:
+                    continue
+                rows = (plane.sum([3], True) > 0.0).flatten().nonzero()
+                top, bottom = rows[0].item(), rows[-1].item()
+                d = ((1.0 - m) * d) + (m * plane[:, :, int(round(top + (0.97 * (bottom - top)))):, :].max())
+            raw = d[0, 0].numpy()
+        if 'warp' in stages:
+            cpu_frame(orc, img, np.ascontiguousarray(raw))
+    steps, warm = max(1, min(args.steps, 2)), min(args.warmup, 1)
+    for i in range(warm):
+        one(i)
     t0 = time.perf_counter()
-    steps = max(1, min(args.steps, 3))
-    for _ in range(steps):
-        cpu_arm(imgs, disp, per_step, cores)
+    for i in range(steps):
+        one(i)
     dt = time.perf_counter() - t0
-    fps = steps * per_step / dt
+    fps = steps / dt
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(per_step, 2),
+        "config": workload_config(1, 2, stages),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps x {per_step} frames of 1024x1024 (one per host thread), oracle/kb_oracle.c"},
+                         "sample": f"{steps} step(s) x 1 frame of 1024x1024 through the oracle port of every stage (PyTorch fp32 on {cores} threads + C)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
 
 
-def workload_config(batch, scenes):
-    return {"workload": "kenburns_warp_1024: disparity->cloud + shift + render(C=4) + disocclusion fill + u8 pack + crop/resize per input frame",
-            "stages_missing": ["seg (AnimeInsSeg.infer)", "depth forward (raw disparity is a synthetic input)"],
-            "frame": [H, W], "batch_frames_per_step": batch, "focal": FOCAL, "baseline": BASELINE,
-            "l2_policy": f"inputs cycle over {scenes} scenes (> 126 MB L2 footprint with per-scene clouds)"}
+def workload_config(batch, scenes, stages=("seg", "depth", "warp")):
+    names = {"seg": "AnimeInsSeg.infer body (ConvNeXt-B RTMDet-Ins forward @1024^2, det_size=1024, random-init seeded weights, decode/NMS/mask head/mask tail, "
+                    "max_instances=100, refine off)",
+             "depth": "LeReS depth (ResNeXt-101 32x8d + decoder @640^2) + reference host-side 16->8 bit quantisation + instance-guided depth flattening",
+             "warp": "disparity->cloud + camera shift + z-buffered render (C=4) + disocclusion fill + u8 pack + centre crop/resize: one Ken-Burns frame"}
+    missing = [v for k, v in {"seg": "seg", "depth": "depth (raw disparity is then a synthetic input)", "warp": "warp"}.items() if k not in stages]
+    missing += ["ISNet mask refine (A10)", "Inpaint net + autozoom (C4-C6: per-image, not per-frame)"]
+    return {"workload": "per input frame @1024x1024: " + " -> ".join(names[s_] for s_ in ("seg", "depth", "warp") if s_ in stages),
+            "stages": list(stages), "stages_missing": missing, "frame": [H, W], "batch_frames_per_step": batch, "focal": FOCAL, "baseline": BASELINE,
+            "l2_policy": f"inputs cycle over {scenes} distinct scenes; every frame streams > 126 MB of intermediates, so no input survives in L2 between uses"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--scenes", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--stages", default="seg,depth,warp", help="comma list out of seg,depth,warp (default: the full metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    stages = [s_ for s_ in args.stages.split(",") if s_]
 
     import torch
     import torch.distributed as dist
     from cartoonsegmentation_b200 import _lib
     from cartoonsegmentation_b200.anime_3dkenburns import kenburns_effect as kb
+    from cartoonsegmentation_b200.animeinsseg import AnimeInstances, rtmdet_postprocess
+    from cartoonsegmentation_b200.utils.dist import gather_counters, max_over_ranks
 
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -164,125 +200,158 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
+    B, S = args.batch, args.scenes
 
-    # ---- inputs: each rank owns `scenes` distinct scenes (weak scaling: per-GPU work fixed); seeds differ per rank
-    imgs_np, disp_np = make_inputs(args.scenes)
+    # ---- the reference call surface: one pipeline object per rank, weights replicated from the same seed
+    cfg = kb.KenBurnsConfig(det_size=H, max_size=H, depth_est='leres' if 'depth' in stages else 'external', depth_est_size=640, pred_score_thr=0.3)
+    pipe = kb.KenBurnsPipeline(cfg, device=dev)
+    seg = pipe.animeinsseg
+    seg.set_detect_size(H)
+    test_cfg = seg.model.bbox_head.test_cfg
+
+    # ---- inputs: each rank owns `scenes` distinct scenes (weak scaling: per-GPU work fixed)
+    imgs_np, disp_np = make_inputs(S)
     imgs_np = np.roll(imgs_np, rank, axis=0)
     imgs_pin = torch.from_numpy(imgs_np).pin_memory(); disp_pin = torch.from_numpy(disp_np).pin_memory()
     imgs_dev = imgs_pin.to(dev); disp_dev = disp_pin.to(dev)
-    S = args.scenes
     scratch = kb.FrameScratch(H, W, dev)
     clouds = [{k: torch.empty((1, c, H, W), device=dev) for k, c in (('disparity', 1), ('depth', 1), ('valid', 1), ('points', 3), ('unaltered', 3))} for _ in range(2)]
     data = [torch.empty((1, 4, H * W), device=dev) for _ in range(2)]
     scalars = torch.empty(8, device=dev); d2c_scratch = torch.empty(64, device=dev, dtype=torch.int64); shift_dev = torch.empty(3, device=dev)
-    outs = torch.empty((args.batch, H, W, 3), device=dev, dtype=torch.uint8)
-    outs_pin = torch.empty((args.batch, H, W, 3), dtype=torch.uint8).pin_memory()
-    stage_img = torch.empty((args.batch, H, W, 3), device=dev, dtype=torch.uint8); stage_disp = torch.empty((args.batch, H, W), device=dev)
+    adj_state = torch.empty(4, device=dev, dtype=torch.int32)
+    outs = torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8)
+    outs_pin = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+    stage_img = torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8)
     cd = ctypes.c_double
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    seg_sub = 8                                                      # detector sub-batch (activations of 8 x 1024^2 ~ 3 GB)
+    stats = {"instances": 0}
 
-    def frame(img_u8, raw, out, slot):
-        """One input frame, all on the current stream, no host sync."""
+    def warp(img_u8, raw, out, slot):
+        """disparity -> cloud -> camera shift -> render -> fill -> pack -> crop/resize, no host sync"""
         c = clouds[slot]
         _lib.check(lib.csb_disparity_to_cloud(_lib.ptr(raw), H, W, cd(FOCAL), cd(BASELINE), _lib.ptr(c['disparity']), _lib.ptr(c['depth']), _lib.ptr(c['valid']),
-                                              _lib.ptr(c['points']), _lib.ptr(c['unaltered']), _lib.ptr(scalars), _lib.ptr(d2c_scratch), _lib.ptr(img_u8), _lib.ptr(data[slot]), st()))
+                                              _lib.ptr(c['points']), _lib.ptr(c['unaltered']), _lib.ptr(scalars), _lib.ptr(d2c_scratch), _lib.ptr(img_u8),
+                                              _lib.ptr(data[slot]), st()))
         _lib.check(lib.csb_shift_from_scalars(_lib.ptr(scalars), W, H, cd(FOCAL), cd(SHIFT_U), cd(SHIFT_V), cd(DEPTH_RATIO), _lib.ptr(shift_dev), st()))
-        d = data[slot]
-        _lib.check(lib.csb_kenburns_frame(_lib.ptr(c['points']), _lib.ptr(d), H * W, H, W, cd(FOCAL), cd(BASELINE), None, _lib.ptr(shift_dev), CROP, CROP,
+        _lib.check(lib.csb_kenburns_frame(_lib.ptr(c['points']), _lib.ptr(data[slot]), H * W, H, W, cd(FOCAL), cd(BASELINE), None, _lib.ptr(shift_dev), CROP, CROP,
                                           cd(W / 2.0), cd(H / 2.0), _lib.ptr(scratch.zkey), _lib.ptr(scratch.zee), _lib.ptr(scratch.acc), _lib.ptr(scratch.packed),
                                           _lib.ptr(out), None, st()))
 
-    def step_resident(k):
-        for b in range(args.batch):
-            i = (k * args.batch + b) % S
-            frame(imgs_dev[i], disp_dev[i], outs[b], b & 1)
-
-    def step_e2e(k):
-        for b in range(args.batch):
-            i = (k * args.batch + b) % S
-            stage_img[b].copy_(imgs_pin[i], non_blocking=True)
-            stage_disp[b].copy_(disp_pin[i], non_blocking=True)
-            frame(stage_img[b], stage_disp[b], outs[b], b & 1)
-            outs_pin[b].copy_(outs[b], non_blocking=True)
-        torch.cuda.current_stream().synchronize()               # the caller receives the frames of this step
+    def step(k, e2e):
+        idx = [(k * B + b) % S for b in range(B)]
+        if e2e:                                                      # H2D of this step's inputs from pinned host memory
+            for b, i in enumerate(idx):
+                stage_img[b].copy_(imgs_pin[i], non_blocking=True)
+            batch = stage_img
+        else:
+            batch = imgs_dev[idx] if 'seg' in stages or 'depth' in stages else None
+        masks = nums = nums_dev = None
+        if 'seg' in stages:                                          # AnimeInsSeg.infer body: detector forward + post-process (A1-A9)
+            masks, nums_dev = [], []
+            for s0 in range(0, B, seg_sub):
+                sub = batch[s0:s0 + seg_sub]
+                cls, reg, ker, mf = seg.model.net.forward(sub)
+                o = rtmdet_postprocess(cls, reg, ker, mf, (H, W), test_cfg)
+                masks.append(o['masks']); nums_dev.append(o['num'])
+            nums = torch.cat(nums_dev).cpu().tolist()                # the one host read of the seg stage (instance counts for the caller)
+            stats["instances"] += sum(nums)
+        disp = None
+        if 'depth' in stages:                                        # LeReS forward + the reference's host-side quantisation tail (B5-B6)
+            disp = pipe._depth_est_leres_batch([imgs_np[i] for i in idx], imgs_dev=batch)
+        raws = torch.stack([(disp[b] if disp is not None else disp_dev[i]).reshape(H, W) for b, i in enumerate(idx)])       # [B,H,W] (a copy)
+        if masks is not None:                                        # instance-guided depth flattening (C2): one cooperative launch per sub-batch
+            for j, s0 in enumerate(range(0, B, seg_sub)):
+                kb.depth_adjust_batch(raws[s0:s0 + seg_sub], masks[j], nums_dev[j])
+        for b, i in enumerate(idx):
+            raw = raws[b]
+            if 'warp' in stages:
+                img_b = batch[b] if batch is not None else imgs_dev[i]
+                warp(img_b, raw, outs[b], b & 1)
+                if e2e:
+                    outs_pin[b].copy_(outs[b], non_blocking=True)
+        if e2e:
+            torch.cuda.current_stream().synchronize()               # the caller receives this step's frames
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(e2e, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
         for k in range(steps):
-            fn(k)
+            step(k, e2e)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _lib.launch_count() - l0
+        return max_over_ranks(e0.elapsed_time(e1), dev), _lib.launch_count() - l0
 
     for k in range(args.warmup):
-        step_resident(k); step_e2e(k)
+        step(k, False)
+    step(0, True)
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches = timed(step_resident, args.steps)
+    ms, launches = timed(False, args.steps)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e, _ = timed(True, args.steps)
 
-    # ---- per-kernel device time of the same steps (second pass with an event after every launch) -> roofline
+    # ---- per-kernel device time of the same step (second pass, a CUDA event after every launch) -> roofline
     torch.cuda.synchronize()
     lib.csb_profile_begin(st())
-    for k in range(min(args.steps, 5)):
-        step_resident(k)
+    step(0, False)
     buf = ctypes.create_string_buffer(1 << 16)
     lib.csb_profile_end(buf, len(buf))
     prof = json.loads(buf.value.decode())
-    prof_steps = min(args.steps, 5)
 
     # throughput counters: ONE all-gather of a per-rank struct over NCCL/NVLink (SURVEY §8e)
-    frames = args.steps * args.batch
-    counters = torch.tensor([frames, ms, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        gathered = [torch.empty_like(counters) for _ in range(world)]
-        dist.all_gather(gathered, counters)
-        total_frames = sum(float(g[0]) for g in gathered)
-    else:
-        total_frames = frames
+    frames = args.steps * B
+    gathered = gather_counters(torch.tensor([frames, ms, ms_e2e], device=dev, dtype=torch.float64))
+    total_frames = float(gathered[:, 0].sum())
 
     if rank == 0:
         peaks = {}
         pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(pk):
             peaks = json.load(open(pk))
-        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-        dom = max((k for k in prof if k not in ("memset",)), key=lambda k: prof[k]["ms"]) if prof else None
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+        tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         P = H * W
-        alg_bytes = {"k_splat": (12 + 16) * P + 4 * P + 20 * P,      # read points+data (28 B/pt) + z-buffer (4 B/px) ; write (C+1)*4 B/px
-                     "k_zpass": 12 * P + 4 * P, "k_degrid": 8 * P, "k_norm_fill_pack": 20 * P + 3 * P, "k_crop_resize": 6 * P,
-                     "k_d2c_max": 4 * P, "k_d2c_scale": 12 * P, "k_d2c_points": 55 * P}
+        dom = max((k for k in prof if k != "memset"), key=lambda k: prof[k]["ms"]) if prof else None
         roof = None
-        if dom:
+        if dom == "k_conv_tc":
+            # algorithmic FLOPs of the tensor-core launches of one step (SURVEY §8d): detector 1011.9 GFLOP / image @1024^2 (ConvNeXt-B 641.7 + neck 132.2
+            # + head 237.9), LeReS 591.9 GFLOP / image @640^2 input
+            gflop = (1011.9 if 'seg' in stages else 0.0) * B + (591.9 if 'depth' in stages else 0.0) * B
+            ach = gflop / prof[dom]["ms"]                             # GFLOP / ms = TFLOP/s
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
+                    "peak_source": "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback",
+                    "launches_per_step": prof[dom]["count"], "algorithmic_gflop_per_step": gflop, "avg_launch_us": 1e3 * prof[dom]["ms"] / prof[dom]["count"]}
+        elif dom:
+            alg_bytes = {"k_splat": 52 * P, "k_zpass": 16 * P, "k_degrid": 8 * P, "k_norm_pack_mark": 24 * P, "k_crop_resize": 6 * P, "k_d2c_max": 4 * P,
+                         "k_d2c_scale": 12 * P, "k_d2c_points": 55 * P}
             dur_ms = prof[dom]["ms"] / prof[dom]["count"]
             ab = alg_bytes.get(dom)
             ach = ab / (dur_ms * 1e-3) / 1e9 if ab else None
-            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "algorithmic_bytes_per_launch": ab,
-                    "per_kernel_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items()}}
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "traffic": None,
+                    "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "algorithmic_bytes_per_launch": ab}
+        if roof is not None:
+            roof["per_kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        h2d = B * H * W * 3 + (0 if 'depth' in stages else 0)
+        d2h = (B * H * W * 3 if 'warp' in stages else 0) + (B * 640 * 640 * 4 if 'depth' in stages else 0)
         out = {"metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": workload_config(args.batch, S), "clocks": clocks,
-               "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": args.batch * (H * W * 3 + H * W * 4),
-                       "d2h_bytes_per_step": args.batch * H * W * 3},
-               "gpu_launches": launches, "roofline": roof}
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate) / f32 render",
+               "data": "synthetic", "config": workload_config(B, S, stages), "clocks": clocks,
+               "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d + (B * H * W * 4 if 'depth' in stages else 0),
+                       "d2h_bytes_per_step": d2h},
+               "gpu_launches": launches, "roofline": roof,
+               "instances_per_image": stats["instances"] / max(1, (args.warmup + 1 + 2 * args.steps + 1) * B) if 'seg' in stages else None}
         if world == 1 and not args.no_cpu_baseline:
-            imgs2, disp2 = imgs_np[:2], disp_np[:2]
             n = 4
-            out["cpu_baseline"] = {"value": cpu_arm(imgs2, disp2, n, 1), "unit": "frames/s", "cores": 1, "kind": "port",
-                                   "sample": f"{n} frames of 1024x1024 on 1 thread, oracle/kb_oracle.c (scalar C port)"}
+            out["cpu_baseline"] = {"value": cpu_arm(imgs_np[:2], disp_np[:2], n, 1), "unit": "frames/s", "cores": 1, "kind": "port",
+                                   "sample": f"{n} frames of 1024x1024 on 1 thread through the WARP stage only (oracle/kb_oracle.c, scalar C port); the seg/depth "
+                                             "oracles are PyTorch fp32 and are timed by --impl reference"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

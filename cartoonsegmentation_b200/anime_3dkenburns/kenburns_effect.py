@@ -207,9 +207,31 @@ def scaledown_maxsize(img: np.ndarray, max_size: int, divisior: int = None):
 
 
 def depth_adjustment_animesseg(instances: AnimeInstances, tenDisparity, tenImage, use_medium=False):
-    """reference :39-91 -- per instance: flatten the disparity under the mask to the maximum found in the bottom 3% of its rows.
-    Host-orchestrated torch glue exactly as the reference (K sequential passes, .item() syncs); a segmented-reduction kernel is the
-    planned replacement."""
+    """reference :39-91 -- per instance, in order: flatten the disparity under the mask to the maximum found in the bottom 3% of its rows.
+    Same-size, non-median case (the pipeline's): csb_depth_adjust_batch, ONE cooperative launch and NO host sync (the reference does
+    ~8 ATen kernels and 5 `.item()` syncs per instance).  The resized / median variants keep the reference's torch formulation."""
+    assert tenDisparity.shape[0] == 1
+    same = tenDisparity.shape[2] == tenImage.shape[2] and tenDisparity.shape[3] == tenImage.shape[3]
+    if same and not use_medium and tenDisparity.is_cuda:
+        out = tenDisparity.contiguous().float().clone()
+        if instances is not None and not instances.is_empty:
+            masks = instances.masks.contiguous()
+            K, H, W = masks.shape
+            depth_adjust_batch(out.view(1, H, W), masks.view(1, K, H, W), torch.tensor([K], device=out.device, dtype=torch.int32))
+        return out
+    return depth_adjustment_animesseg_torch(instances, tenDisparity, tenImage, use_medium)
+
+
+def depth_adjust_batch(disparity, masks, num):
+    """csb_depth_adjust_batch: disparity [N,H,W] fp32 (in place), masks [N,Kmax,H,W] bool, num [N] int32 on the device -- one cooperative launch."""
+    N, Kmax, H, W = masks.shape
+    state = torch.empty(3 * N * Kmax + N, device=disparity.device, dtype=torch.int32)
+    check(lib().csb_depth_adjust_batch(ptr(disparity), ptr(masks.view(torch.uint8)), ptr(num), N, Kmax, H, W, ptr(state), stream()), "csb_depth_adjust_batch")
+    return disparity
+
+
+def depth_adjustment_animesseg_torch(instances: AnimeInstances, tenDisparity, tenImage, use_medium=False):
+    """The reference's own torch formulation (:39-91), kept for the resized / median variants."""
     assert tenDisparity.shape[0] == 1
     tenMasks = [] if instances is None or instances.is_empty else [instances.masks[i].float() for i in range(instances.masks.shape[0])]
     resized = tenDisparity.shape[2] != tenImage.shape[2] or tenDisparity.shape[3] != tenImage.shape[3]
@@ -261,13 +283,74 @@ class KenBurnsPipeline:
             ck = det_ckpt if det_ckpt is not None else (self.cfg.det_ckpt if isinstance(self.cfg.det_ckpt, str) and os.path.exists(self.cfg.det_ckpt) else None)
             self.animeinsseg = AnimeInsSeg(ck, default_det_size=self.cfg.det_size, device=self.device, refine_kwargs={'refine_method': 'none'})
 
-    def set_depth_estimation(self, depth_est: str):
+    def set_depth_estimation(self, depth_est: str, ckpt=None):
+        """reference :529-560.  'leres' is built (ResNeXt-101 32x8d + decoder on the tcgen05 engine); 'zoe' (BEiT-L DPT encoder), 'marigold'
+        and 'default' are not -- they raise at use time unless `depth_model` is set by the caller ('external')."""
         self.cfg.depth_est = depth_est
         if depth_est not in ('zoe', 'leres', 'marigold', 'default', 'external'):
             raise NotImplementedError(depth_est)
+        if depth_est == 'leres':
+            from ..depth_modules.leres import LeReS
+            if getattr(self, 'leres', None) is None:
+                sd = None
+                if ckpt is not None:
+                    obj = torch.load(ckpt, map_location='cpu')
+                    sd = obj.get('depth_model', obj)
+                    sd = {('depth_model.' + k if not k.startswith('depth_model.') else k): v for k, v in sd.items()}
+                self.leres = LeReS(sd, self.device)
+            self.depth_model = lambda img, img_tensor: self._depth_est_leres(img_tensor, img)
 
-    def set_inpainting(self, inpainting: str):
+    # ---- reference :563-581
+    def _leres_post(self, depth_logits: np.ndarray, ori_hw):
+        """apply_leres quantisation (leres/__init__.py:117-140) + resize back (:572-577), host numpy/OpenCV exactly as the reference."""
+        import cv2
+        from ..depth_modules.leres import quantise_depth
+        depth = quantise_depth(depth_logits)
+        k = depth.shape[0] / ori_hw[0]
+        depth = cv2.resize(depth, (ori_hw[1], ori_hw[0]), interpolation=cv2.INTER_LANCZOS4 if k > 1 else cv2.INTER_AREA)
+        return depth.astype(np.float32)
+
+    def _depth_est_leres(self, img_tensor, img, *args, **kwargs):
+        return self._depth_est_leres_batch([img])[0]
+
+    def _depth_est_leres_batch(self, imgs, imgs_dev=None):
+        """LeReS for a list of same-size BGR uint8 images -> list of disparity tensors [1,1,H,W] on the device.  The network runs as one
+        batch; the reference's host-side tail (16->8 bit quantisation, OpenCV resize) runs on a thread pool (OpenCV releases the GIL)."""
+        from concurrent.futures import ThreadPoolExecutor
+        ori_h, ori_w = imgs[0].shape[:2]
+        if imgs_dev is not None:            # device-resident inputs: scaledown_maxsize's cv2.resize(INTER_LINEAR) on the device, bit-exact
+            small_hw = scaledown_maxsize(np.empty((ori_h, ori_w, 1), np.uint8), self.cfg.depth_est_size, 32).shape[:2]
+            if small_hw != (ori_h, ori_w):
+                small = torch.empty((imgs_dev.shape[0], small_hw[0], small_hw[1], 3), device=self.device, dtype=torch.uint8)
+                for i in range(imgs_dev.shape[0]):
+                    check(lib().csb_resize_u8c3(ptr(imgs_dev[i]), ori_h, ori_w, ptr(small[i]), small_hw[0], small_hw[1], stream()), "csb_resize_u8c3")
+            else:
+                small = imgs_dev
+        else:
+            small = torch.from_numpy(np.stack([scaledown_maxsize(im, self.cfg.depth_est_size, 32) for im in imgs])).to(self.device)
+        logits = self.leres.forward(small).cpu().numpy()                      # [N,h,w] fp32, one D2H for the batch
+        if getattr(self, '_pool', None) is None:
+            import os
+            self._pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+        depth = list(self._pool.map(lambda d: self._leres_post(d, (ori_h, ori_w)), logits))
+        out = torch.from_numpy(np.stack(depth)).to(self.device)[:, None]      # [N,1,H,W]
+        res = []
+        for i in range(out.shape[0]):
+            d = out[i:i + 1]
+            d[d == 0] = d[d > 0].min()                                         # :577
+            res.append(d)
+        return res
+
+    def set_inpainting(self, inpainting: str, ckpt=None):
+        """reference :427-440.  'default' = the point-cloud Inpaint GridNet on the tcgen05 engine; 'ldm' / 'patchmatch' (stable-diffusion webui,
+        external PatchMatch .so) are out of scope."""
+        if inpainting not in ('default',):
+            raise NotImplementedError(f"inpaint_type '{inpainting}' is an optional external back-end outside the hot path")
         self.inpaint_type = inpainting
+        if self.kenburns_inpaintnet is None:
+            from .models.pointcloud_inpainting import Inpaint
+            sd = torch.load(ckpt, map_location='cpu') if ckpt is not None else None
+            self.kenburns_inpaintnet = Inpaint(sd, self.device)
 
     def set_depth_refinement(self, depth_refinement: str):
         raise NotImplementedError("Refine disparity net (SURVEY.md §8f rank 2) is not built yet")
@@ -343,7 +426,23 @@ class KenBurnsPipeline:
             return npy_frame_list
 
     def inpaint(self, tenShift, tenPoints, objCommon, verbose=False):
-        raise NotImplementedError("point-cloud Inpaint net (SURVEY.md §8a rows C5-C6) is not built yet; call process_kenburns(..., inpaint=False)")
+        """reference :441-512 ('default' branch): run the Inpaint net for the shifted view, lift its disparity to points, and append the pixels that
+        were holes in that view (tenExisting == 0) to the growing point cloud.  (The boolean-mask gathers are torch glue, as in the reference; the
+        `stage_inpainted_*` preview images of the reference, which need a D2H per call, are not produced.)"""
+        from .models.utils import depth_to_points, spatial_filter
+        sh = torch.as_tensor(tenShift, dtype=torch.float32).flatten()
+        o = self.kenburns_inpaintnet.forward(objCommon['tenRawImage'], objCommon['tenRawDisparity'], sh, objCommon, None)
+        focal, baseline = objCommon['fltFocal'], objCommon['fltBaseline']
+        depth = (focal * baseline) / (o['tenDisparity'] + 0.0000001)                                              # :454
+        valid = (spatial_filter(o['tenDisparity'] / o['tenDisparity'].max(), 'laplacian').abs() < 0.03).float()  # :455
+        points = depth_to_points(depth * valid, focal).view(1, 3, -1) - sh.view(1, 3, 1).to(self.device)          # :456-458
+        tenMask = (o['tenExisting'] == 0.0).view(1, 1, -1)                                                        # :462
+        pick = lambda t, c: t.reshape(1, c, -1)[tenMask.repeat(1, c, 1)].view(1, c, -1)
+        objCommon.inpainted_img = torch.cat([objCommon.inpainted_img, pick(o['tenImage'], 3)], 2)                 # :472
+        objCommon['tenInpaDisparity'] = torch.cat([objCommon['tenInpaDisparity'], pick(o['tenDisparity'], 1)], 2)  # :510
+        objCommon['tenInpaDepth'] = torch.cat([objCommon['tenInpaDepth'], pick(depth, 1)], 2)                     # :511
+        objCommon['tenInpaPoints'] = torch.cat([objCommon['tenInpaPoints'], pick(points, 3)], 2)                  # :512
+        return o
 
     # ---- reference :979-1081
     def process_kenburns(self, objSettings, objCommon: KenBurnsConfig, inpaint: bool = True, verbose: bool = False):

@@ -71,6 +71,8 @@ class AnimeInsSeg:
         self.default_det_size = default_det_size
         self.det_size = (default_det_size, default_det_size)
         self.postprocess_refine = None
+        self.refinenet = None
+        self.refine_size = 720
         self.mask_thr = mask_thr
         if refine_kwargs is not None:
             self.set_refine_method(**refine_kwargs)
@@ -79,13 +81,54 @@ class AnimeInsSeg:
     def set_detect_size(self, det_size):
         self.det_size = (det_size, det_size) if isinstance(det_size, int) else tuple(det_size)
 
-    def set_refine_method(self, refine_method: str = 'none', refine_size: int = 720):
+    def set_refine_method(self, refine_method: str = 'none', refine_size: int = 720, refine_ckpt=None):
+        """reference :623-633.  'refinenet_isnet' = ISNetDIS(in_ch=4) on the tcgen05 engine (isnet.py); 'animeseg' (the alternative
+        anime-seg matting net, AnimeSegmentation.try_load) is outside the default path and not built."""
         if refine_method == 'none':
             self.postprocess_refine = None
-        elif refine_method in ('animeseg', 'refinenet_isnet'):
-            raise NotImplementedError(f"refine method '{refine_method}' (ISNet mask refinement, SURVEY.md §8a row A10) is not built yet")
+        elif refine_method == 'refinenet_isnet':
+            if self.refinenet is None:
+                from .isnet import ISNetDIS
+                sd = None
+                if refine_ckpt is not None:
+                    sd = torch.load(refine_ckpt, map_location='cpu')
+                self.refinenet = ISNetDIS(sd, self.device)
+            self.refine_size = refine_size
+            self.postprocess_refine = self._postprocess_refine
+        elif refine_method == 'animeseg':
+            raise NotImplementedError("refine method 'animeseg' (anime-seg isnet_is matting net) is not on the default path and not built")
         else:
             raise NotImplementedError(f'Invalid refine method: {refine_method}')
+
+    def _postprocess_refine(self, instances: AnimeInstances, img: np.ndarray, refine_size: int = None, max_refine_batch: int = 16, **kwargs):
+        """reference :638-665 + prepare_refine_batch :37-55, entirely on the device: [BGR/255 | mask] at refine_size^2 (shrink-only resize, pad
+        bottom/right) -> ISNet d1 -> sigmoid -> un-pad -> bilinear(align_corners=True) to (H,W) -> > self.mask_thr.  Sub-batches of 16
+        instead of the reference's 4 (results do not depend on the grouping)."""
+        if instances.is_empty:
+            return
+        from ..anime_3dkenburns.kenburns_effect import scaledown_maxsize
+        S = self.refine_size if refine_size is None else refine_size
+        was_numpy = instances.is_numpy
+        masks = instances.masks if instances.is_tensor else torch.from_numpy(instances.masks)
+        masks = masks.to(self.device).contiguous()
+        K, H, W = masks.shape
+        img_dev = torch.from_numpy(np.ascontiguousarray(img)).to(self.device) if isinstance(img, np.ndarray) else img
+        h, w = scaledown_maxsize(np.empty((H, W, 1), np.uint8), S).shape[:2]                  # same rounding as the reference's resize_pad
+        if (h, w) != (H, W):
+            small = torch.empty((h, w, 3), device=self.device, dtype=torch.uint8)
+            check(lib().csb_resize_u8c3(ptr(img_dev), H, W, ptr(small), h, w, stream()), "csb_resize_u8c3")
+        else:
+            small = img_dev
+        out = torch.empty((K, H, W), device=self.device, dtype=torch.uint8)
+        for k0 in range(0, K, max_refine_batch):
+            k1 = min(K, k0 + max_refine_batch)
+            x16 = torch.empty((k1 - k0, S, S, 16), device=self.device, dtype=torch.float16)
+            check(lib().csb_refine_prep(ptr(small), h, w, ptr(masks[k0:k1].view(torch.uint8)), k1 - k0, H, W, S, ptr(x16), stream()), "csb_refine_prep")
+            d1 = self.refinenet.forward(x16)
+            check(lib().csb_refine_post(ptr(d1), k1 - k0, S, h, w, H, W, C.c_float(self.mask_thr), ptr(out[k0:k1]), stream()), "csb_refine_post")
+        instances.masks = out.view(torch.bool)
+        if was_numpy:
+            instances.masks = instances.masks.cpu().numpy()
 
     def set_mask_threshold(self, mask_thr: float):
         self.model.bbox_head.test_cfg['mask_thr_binary'] = mask_thr
@@ -140,9 +183,9 @@ class AnimeInsSeg:
             batch = torch.from_numpy(np.stack([a for _, a in items])).to(self.device, non_blocking=True)
             for j, inst in enumerate(self._det_forward(batch, sf, ori, pred_score_thr)):
                 preds[items[j][0]] = inst
-        for inst in preds:
+        for inst, im in zip(preds, loaded):
             if self.postprocess_refine is not None:
-                self.postprocess_refine(inst, None)
+                self.postprocess_refine(inst, im)
             if output_type == 'numpy':
                 inst.to_numpy()
         return preds if return_list else preds[0]

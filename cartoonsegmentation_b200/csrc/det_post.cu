@@ -251,27 +251,61 @@ __device__ __forceinline__ float up8(const float* __restrict__ lg, int h, int w,
     return ly0 * (lx0 * __ldg(lg + y0 * w + x0) + lx1 * __ldg(lg + y0 * w + x1)) + ly1 * (lx0 * __ldg(lg + y1 * w + x0) + lx1 * __ldg(lg + y1 * w + x1));
 }
 
+__device__ __forceinline__ unsigned char mask_decide(float v, float thr, float thr_logit) {
+    // sigmoid(v) > thr.  Away from the decision boundary the sign of v - logit(thr) decides; within 1e-3 of it the reference expression is evaluated.
+    const float d = v - thr_logit;
+    if (fabsf(d) > 1e-3f) return d > 0.f ? 1 : 0;
+    return (1.0f / (1.0f + expf(-v))) > thr ? 1 : 0;
+}
+
+// 4 consecutive output pixels per thread -> one 32-bit store; the vertical interpolation set-up is shared by the 4 pixels.
 __global__ void __launch_bounds__(256) k_mask_tail(const float* __restrict__ logits, const int* __restrict__ num, int max_per_img, int h, int w, int up,
-                                                   int H2, int W2, float sy2, float sx2, int identity2, int H, int W, float thr,
+                                                   int H2, int W2, float sy2, float sx2, int identity2, int H, int W, float thr, float thr_logit,
                                                    unsigned char* __restrict__ masks) {
     const int inst = blockIdx.y, img = blockIdx.z;
     if (inst >= num[img]) return;
     const float* lg = logits + ((size_t) img * max_per_img + inst) * h * w;
     unsigned char* out = masks + ((size_t) img * max_per_img + inst) * H * W;
     const int HU = h * up, WU = w * up;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
-        const int x = i % W, y = i / W;
-        float v;
+    const int Wq = (W + 3) / 4;
+    const bool vec = (W % 4 == 0) && (((size_t) H * W) % 4 == 0);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * Wq; i += gridDim.x * blockDim.x) {
+        const int xq = i % Wq, y = i / Wq;
+        unsigned char r[4] = {0, 0, 0, 0};
         if (identity2) {
-            v = up8(lg, h, w, up, y, x);
+            int y0, y1;
+            float ly0, ly1;
+            src_index(1.0f / (float) up, y, h, y0, y1, ly0, ly1);
+            const float* r0 = lg + y0 * w;
+            const float* r1 = lg + y1 * w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = xq * 4 + j;
+                if (x >= W) break;
+                int x0, x1;
+                float lx0, lx1;
+                src_index(1.0f / (float) up, x, w, x0, x1, lx0, lx1);
+                const float v = ly0 * (lx0 * __ldg(r0 + x0) + lx1 * __ldg(r0 + x1)) + ly1 * (lx0 * __ldg(r1 + x0) + lx1 * __ldg(r1 + x1));
+                r[j] = mask_decide(v, thr, thr_logit);
+            }
         } else {       // second F.interpolate(size=[H2,W2], align_corners=False) on the x8 map, then crop [:H,:W]
-            int y0, y1, x0, x1;
-            float ly0, ly1, lx0, lx1;
+            int y0, y1;
+            float ly0, ly1;
             src_index(sy2, y, HU, y0, y1, ly0, ly1);
-            src_index(sx2, x, WU, x0, x1, lx0, lx1);
-            v = ly0 * (lx0 * up8(lg, h, w, up, y0, x0) + lx1 * up8(lg, h, w, up, y0, x1)) + ly1 * (lx0 * up8(lg, h, w, up, y1, x0) + lx1 * up8(lg, h, w, up, y1, x1));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = xq * 4 + j;
+                if (x >= W) break;
+                int x0, x1;
+                float lx0, lx1;
+                src_index(sx2, x, WU, x0, x1, lx0, lx1);
+                const float v = ly0 * (lx0 * up8(lg, h, w, up, y0, x0) + lx1 * up8(lg, h, w, up, y0, x1)) + ly1 * (lx0 * up8(lg, h, w, up, y1, x0) + lx1 * up8(lg, h, w, up, y1, x1));
+                r[j] = mask_decide(v, thr, thr_logit);
+            }
         }
-        out[i] = (1.0f / (1.0f + expf(-v))) > thr ? 1 : 0;                    // sigmoid() > mask_thr_binary
+        if (vec) *reinterpret_cast<uchar4*>(out + (size_t) y * W + xq * 4) = make_uchar4(r[0], r[1], r[2], r[3]);
+        else
+            for (int j = 0; j < 4 && xq * 4 + j < W; ++j) out[(size_t) y * W + xq * 4 + j] = r[j];
     }
 }
 
@@ -323,9 +357,10 @@ extern "C" int csb_rtmdet_masks(const float* mask_feat, const float* kernels, co
     const int identity2 = resized_h == HU && resized_w == WU;
     // F.interpolate(size=...) without scale_factor: source scale = in/out
     const float sy2 = (float) HU / (float) resized_h, sx2 = (float) WU / (float) resized_w;
-    int gx = (out_h * out_w + 255) / 256;
-    gx = gx > 1024 ? 1024 : gx;
+    int gx = (out_h * ((out_w + 3) / 4) + 255) / 256;
+    gx = gx > 256 ? 256 : gx;
+    const float thr_logit = (mask_thr > 0.f && mask_thr < 1.f) ? logf(mask_thr / (1.0f - mask_thr)) : (mask_thr <= 0.f ? -INFINITY : INFINITY);
     k_mask_tail<<<dim3(gx, max_per_img, N), 256, 0, st>>>(logits, num, max_per_img, h, w, stride0, resized_h, resized_w, sy2, sx2, identity2, out_h, out_w,
-                                                          mask_thr, masks);
+                                                          mask_thr, thr_logit, masks);
     return csb::launched("k_mask_tail", st);
 }

@@ -50,10 +50,10 @@ __device__ __forceinline__ void crop_px(const uint8_t* __restrict__ src, int H, 
 }
 
 // resize.cpp: HResizeLinear<uchar,int,short,2048> + VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>.  6 B/px.
-__global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__ src, int H, int W, CropParams p, uint8_t* __restrict__ dst) {
-    const int total = H * W;
+__global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__ src, int H, int W, CropParams p, int Ho, int Wo, uint8_t* __restrict__ dst) {
+    const int total = Ho * Wo;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int dx = i % W, dy = i / W;
+        const int dx = i % Wo, dy = i / Wo;
         float fx = (float) ((dx + 0.5) * p.sx - 0.5);
         int ix = (int) floorf(fx);
         fx -= ix;
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(256) k_fill_holes(const float* __restrict__ ac
     }
 }
 
-int make_crop(int H, int W, int pw, int ph, double cx, double cy, CropParams& p) {
+int make_crop(int Ho, int Wo, int pw, int ph, double cx, double cy, CropParams& p) {
+    const int H = Ho, W = Wo;
     if (pw <= 0 || ph <= 0) return CSB_ERR_INVALID;
     float fcx = (float) cx, fcy = (float) cy;
     fcx -= (pw - 1) * 0.5f;
@@ -216,7 +217,16 @@ extern "C" int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw,
     CSB_REQUIRE(H > 0 && W > 0, "bad shape");
     CropParams p;
     CSB_REQUIRE(make_crop(H, W, pw, ph, cx, cy, p) == CSB_OK, "bad crop size");
-    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(frame, H, W, p, out);
+    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(frame, H, W, p, H, W, out);
+    return csb::launched("k_crop_resize", (cudaStream_t) stream);
+}
+
+extern "C" int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream) {
+    CSB_REQUIRE(src && dst && src != dst && H > 0 && W > 0 && Ho > 0 && Wo > 0, "bad arguments");
+    CSB_REQUIRE(!(W == 2 * Wo && H == 2 * Ho), "exact 2x decimation takes OpenCV's INTER_AREA fast path, not implemented");
+    CropParams p;   // full-frame 'crop' at integer offset 0: getRectSubPix degenerates to a copy, leaving cv2.resize(INTER_LINEAR)
+    CSB_REQUIRE(make_crop(Ho, Wo, W, H, (W - 1) * 0.5, (H - 1) * 0.5, p) == CSB_OK, "bad size");
+    k_crop_resize<<<csb::wave_grid((long long) Ho * Wo, 256, 8), 256, 0, (cudaStream_t) stream>>>(src, H, W, p, Ho, Wo, dst);
     return csb::launched("k_crop_resize", (cudaStream_t) stream);
 }
 
@@ -240,6 +250,6 @@ extern "C" int csb_kenburns_frame(const float* points, const float* data, int N,
     CSB_TRY(csb::launched("k_norm_pack_mark", st));
     k_fill_holes<<<csb::num_sms() * 8, 256, 0, st>>>(acc, mask, zkey, nholes, H, W, packed, depth_out);
     CSB_TRY(csb::launched("k_fill_holes", st));
-    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, out);
+    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, H, W, out);
     return csb::launched("k_crop_resize", st);
 }

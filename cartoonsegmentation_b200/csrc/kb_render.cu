@@ -18,6 +18,8 @@
 //   acc    [B,H,W,CP] fp32         CP = roundup(C+1, 4): channel-INTERLEAVED accumulator, weight in slot C, so
 //                                  one corner of one point is CP/4 vector reductions (RED.ADD.F32x4) instead of
 //                                  C+1 scalar atomics (:268-298: 4*(C+1) atomicAdds per point).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -211,6 +213,78 @@ __global__ void __launch_bounds__(256) k_splat(const float* __restrict__ pts, co
     }
 }
 
+// Splat with an fp16 channel-INTERLEAVED payload [N, ld] (the 68-channel context render of the Inpaint net, pointcloud_inpainting.py:135: the
+// payload comes straight from the conv engine in NHWC fp16, each point reads one contiguous run of C halves).
+__global__ void __launch_bounds__(256) k_splat_h16(const float* __restrict__ pts, const __half* __restrict__ data, int ld, const float* __restrict__ zee, int N,
+                                                   int C, int CP, int H, int W, double focal, double fb, Shift sh_, float* __restrict__ acc) {
+    const Shift sh = resolve(sh_);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        float x = __ldg(pts + n), y = __ldg(pts + N + n), z = __ldg(pts + 2 * (size_t) N + n);
+        if (sh.on) apply_shift(x, y, z, sh.sx, sh.sy, sh.sz);
+        Proj p = project(x, y, z, H, W, focal, fb);
+        if (!p.ok) continue;
+        size_t off[4];
+        unsigned pass = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int cx = p.x0 + (k & 1), cy = p.y0 + (k >> 1);
+            off[k] = 0;
+            if (cx >= 0 && cx < W && cy >= 0 && cy < H) {
+                size_t o = (size_t) cy * W + cx;
+                if ((double) p.err <= (double) __ldg(zee + o) + 1.0) { pass |= 1u << k; off[k] = o * CP; }
+            }
+        }
+        if (!pass) continue;
+        const __half* D = data + (size_t) n * ld;
+        for (int g = 0; g < CP; g += 4) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int c = g + j;
+                v[j] = c < C ? __half2float(D[c]) : (c == C ? 1.0f : 0.0f);
+            }
+            const bool single = (g == C);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!(pass & (1u << k))) continue;
+                const float w = p.w[k];
+                if (single) atomicAdd(acc + off[k] + g, __fmul_rn(v[0], w));
+                else red_add_v4(acc + off[k] + g, __fmul_rn(v[0], w), __fmul_rn(v[1], w), __fmul_rn(v[2], w), __fmul_rn(v[3], w));
+            }
+        }
+    }
+}
+
+// Inpaint-net input assembly (pointcloud_inpainting.py:140-146): tenExisting = (existing > 0) * median5(existing > 0); render *= tenExisting;
+// netInput sees cat([render, existing]).  flags: pass 1 writes (w > 0) per pixel, pass 2 takes the 5x5 reflect-padded majority (median of 25
+// zeros/ones = 1 iff at least 13 ones), normalises and writes NHWC fp16 with the existing flag in channel C.
+__global__ void __launch_bounds__(256) k_cov_flags(const float* __restrict__ acc, int CP, int C, int HW, uint8_t* __restrict__ flags) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) flags[i] = acc[(size_t) i * CP + C] > 0.0f ? 1 : 0;
+}
+__device__ __forceinline__ int reflect_idx(int v, int n) {
+    if (v < 0) v = -v;
+    if (v >= n) v = 2 * (n - 1) - v;
+    return v;
+}
+__global__ void __launch_bounds__(256) k_inpaint_input(const float* __restrict__ acc, const uint8_t* __restrict__ flags, int CP, int C, int H, int W, int ldo,
+                                                       __half* __restrict__ out, float* __restrict__ existing) {
+    const int HW = H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int x = i % W, y = i / W;
+        int cnt = 0;
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) cnt += flags[(size_t) reflect_idx(y + dy, H) * W + reflect_idx(x + dx, W)];
+        const float e = (flags[i] && cnt >= 13) ? 1.0f : 0.0f;
+        existing[i] = e;
+        const float* A = acc + (size_t) i * CP;
+        const float d = __fadd_rn(A[C], 0.0000001f);
+        __half* o = out + (size_t) i * ldo;
+        for (int c = 0; c < ldo; ++c) o[c] = __float2half_rn(c < C ? __fmul_rn(__fdiv_rn(A[c], d), e) : (c == C ? e : 0.0f));
+    }
+}
+
 // host tail :315 -- render = acc[:C] / (acc[C] + 1e-7), existing = acc[C]; interleaved -> planar.
 __global__ void __launch_bounds__(256) k_normalise(const float* __restrict__ acc, int B, int C, int CP, int H, int W,
                                                    float* __restrict__ render, float* __restrict__ existing) {
@@ -400,4 +474,24 @@ extern "C" int csb_shift_from_scalars(const float* scalars, int W, int H, double
     CSB_REQUIRE(scalars && shift_dev, "null pointer");
     k_shift_scalars<<<1, 32, 0, (cudaStream_t) stream>>>(scalars, W, H, focal, shiftU, shiftV, depth_ratio, 1.0, shift_dev);
     return csb::launched("k_shift_scalars", (cudaStream_t) stream);
+}
+
+extern "C" int csb_inpaint_context_render(const float* points, const void* data16, int ld, int N, int C, int H, int W, double focal, double baseline,
+                                          const float* shift, int32_t* zkey, float* zee, float* acc, uint8_t* flags, void* out16, int ldo, float* existing,
+                                          void* stream) {
+    CSB_REQUIRE(points && data16 && shift && zkey && zee && acc && flags && out16 && existing, "null pointer");
+    CSB_REQUIRE(N > 0 && C > 0 && C <= ld && H > 0 && W > 0 && ldo >= C + 1 && ldo % 8 == 0, "bad shape");
+    cudaStream_t st = (cudaStream_t) stream;
+    const int CP = csb_render_acc_channels(C);
+    CSB_TRY(zpass_impl(points, 1, N, H, W, focal, baseline, shift, nullptr, zkey, st));
+    CSB_TRY(csb_pointcloud_degrid(zkey, 1, H, W, zee, st));
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t) H * W * CP, st), "memset acc"));
+    csb::memset_done(st);
+    k_splat_h16<<<csb::wave_grid(N, 256, 8), 256, 0, st>>>(points, (const __half*) data16, ld, zee, N, C, CP, H, W, focal, focal * baseline,
+                                                            make_shift(shift, nullptr), acc);
+    CSB_TRY(csb::launched("k_splat_h16", st));
+    k_cov_flags<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(acc, CP, C, H * W, flags);
+    CSB_TRY(csb::launched("k_cov_flags", st));
+    k_inpaint_input<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(acc, flags, CP, C, H, W, ldo, (__half*) out16, existing);
+    return csb::launched("k_inpaint_input", st);
 }

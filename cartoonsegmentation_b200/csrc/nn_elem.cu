@@ -51,78 +51,100 @@ constexpr int kMaxVec = 8;   // up to 8 x 8 channels per lane = C <= 2048
 
 // Depthwise KxK (stride 1, zero pad K/2) + bias, then optionally LayerNorm over C (eps, affine) or an activation.
 //   x [N,H,W,ldx] (+xoff), w [K][K][C] fp32, y [N,H,W,ldy] (+yoff).  Algorithmic bytes: 2*2*C per pixel (read + write) + weights.
-template <int K>
+// One warp owns T consecutive output pixels of a row and ALL channels (lane l -> channel vectors 8*(l + 32 j)), so the LayerNorm
+// reduction is a warp shuffle.  For every filter row the warp loads the T+K-1 input vectors once into registers (converted to fp32
+// once) and slides the K taps over them: (T+K-1)/T loads per output row-tap group instead of K -- the kernel is L1-bandwidth bound, this
+// is the reuse that matters (measured: the untiled version spent 66% of the detector forward here).
+template <int K, int T, int NV>
 __global__ void __launch_bounds__(256) k_dwconv(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
                                                 const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                                                 float eps, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy, int yoff) {
+    constexpr int R = K / 2;
     const int lane = threadIdx.x & 31;
-    const long long npix = (long long) N * H * W;
-    const int nvec = C / 256 + ((C % 256) ? 1 : 0);     // 8-channel vectors per lane (lane handles channels 8*(lane + 32*j) ..)
-    for (long long pix = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += (long long) gridDim.x * (blockDim.x >> 5)) {
-        const int px = (int) (pix % W), py = (int) ((pix / W) % H);
-        const long long img = pix / ((long long) W * H);
-        float acc[kMaxVec][8];
+    const int groups_w = (W + T - 1) / T;
+    const long long ngroups = (long long) N * H * groups_w;
+    for (long long gidx = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gidx < ngroups; gidx += (long long) gridDim.x * (blockDim.x >> 5)) {
+        const int gx = (int) (gidx % groups_w), py = (int) ((gidx / groups_w) % H);
+        const long long img = gidx / ((long long) groups_w * H);
+        const int px0 = gx * T;
+        float acc[T][NV][8];
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
+        for (int j = 0; j < NV; ++j) {
             const int c0 = 8 * (lane + 32 * j);
-            if (j < nvec && c0 < C) {
+            float b8[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[j][e] = bias ? __ldg(bias + c0 + e) : 0.0f;
-            }
+            for (int e = 0; e < 8; ++e) b8[e] = (bias && c0 < C) ? __ldg(bias + c0 + e) : 0.0f;
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[t][j][e] = b8[e];
         }
+#pragma unroll 1
         for (int r = 0; r < K; ++r) {
-            const int iy = py + r - K / 2;
+            const int iy = py + r - R;
             if (iy < 0 || iy >= H) continue;
-            for (int s = 0; s < K; ++s) {
-                const int ix = px + s - K / 2;
-                if (ix < 0 || ix >= W) continue;
-                const __half* xp = x + ((img * H + iy) * W + ix) * ldx + xoff;
-                const float* wp = w + (size_t) (r * K + s) * C;
+            const __half* xrow = x + ((img * H + iy) * W) * ldx + xoff;
 #pragma unroll
-                for (int j = 0; j < kMaxVec; ++j) {
-                    const int c0 = 8 * (lane + 32 * j);
-                    if (j < nvec && c0 < C) {
-                        float f[8];
-                        unpack8(*reinterpret_cast<const H8*>(xp + c0), f);
-                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + c0)), w1 = __ldg(reinterpret_cast<const float4*>(wp + c0 + 4));
-                        acc[j][0] = fmaf(f[0], w0.x, acc[j][0]); acc[j][1] = fmaf(f[1], w0.y, acc[j][1]);
-                        acc[j][2] = fmaf(f[2], w0.z, acc[j][2]); acc[j][3] = fmaf(f[3], w0.w, acc[j][3]);
-                        acc[j][4] = fmaf(f[4], w1.x, acc[j][4]); acc[j][5] = fmaf(f[5], w1.y, acc[j][5]);
-                        acc[j][6] = fmaf(f[6], w1.z, acc[j][6]); acc[j][7] = fmaf(f[7], w1.w, acc[j][7]);
+            for (int j = 0; j < NV; ++j) {
+                const int c0 = 8 * (lane + 32 * j);
+                if (c0 >= C) continue;
+                float xin[T + K - 1][8];
+#pragma unroll
+                for (int s = 0; s < T + K - 1; ++s) {
+                    const int ix = px0 + s - R;
+                    if (ix >= 0 && ix < W) unpack8(*reinterpret_cast<const H8*>(xrow + (size_t) ix * ldx + c0), xin[s]);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) xin[s][e] = 0.0f;
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float* wp = w + (size_t) (r * K + k) * C + c0;
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int t = 0; t < T; ++t)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[t][j][e] = fmaf(xin[t + k][e], wv[e], acc[t][j][e]);
+                }
             }
         }
-        float mean = 0.0f, rstd = 1.0f;
-        if (ln_g) {
-            float s1 = 0.0f;
 #pragma unroll
-            for (int j = 0; j < kMaxVec; ++j)
-                if (j < nvec && 8 * (lane + 32 * j) < C)
+        for (int t = 0; t < T; ++t) {
+            const int px = px0 + t;
+            if (px >= W) break;
+            float mean = 0.0f, rstd = 1.0f;
+            if (ln_g) {
+                float s1 = 0.0f;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) s1 += acc[j][e];
-            mean = warp_sum(s1) / (float) C;
-            float s2 = 0.0f;
+                for (int j = 0; j < NV; ++j)
+                    if (8 * (lane + 32 * j) < C)
 #pragma unroll
-            for (int j = 0; j < kMaxVec; ++j)
-                if (j < nvec && 8 * (lane + 32 * j) < C)
+                        for (int e = 0; e < 8; ++e) s1 += acc[t][j][e];
+                mean = warp_sum(s1) / (float) C;
+                float s2 = 0.0f;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) { float d = acc[j][e] - mean; s2 += d * d; }
-            rstd = rsqrtf(warp_sum(s2) / (float) C + eps);
-        }
-        __half* yp = y + pix * ldy + yoff;
+                for (int j = 0; j < NV; ++j)
+                    if (8 * (lane + 32 * j) < C)
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
-            const int c0 = 8 * (lane + 32 * j);
-            if (j < nvec && c0 < C) {
-                float o[8];
+                        for (int e = 0; e < 8; ++e) { float d = acc[t][j][e] - mean; s2 += d * d; }
+                rstd = rsqrtf(warp_sum(s2) / (float) C + eps);
+            }
+            __half* yp = y + (((img * H + py) * W) + px) * ldy + yoff;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float v = acc[j][e];
-                    if (ln_g) v = (v - mean) * rstd * __ldg(ln_g + c0 + e) + __ldg(ln_b + c0 + e);
-                    o[e] = act_f(v, act);
+            for (int j = 0; j < NV; ++j) {
+                const int c0 = 8 * (lane + 32 * j);
+                if (c0 < C) {
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float v = acc[t][j][e];
+                        if (ln_g) v = (v - mean) * rstd * __ldg(ln_g + c0 + e) + __ldg(ln_b + c0 + e);
+                        o[e] = act_f(v, act);
+                    }
+                    *reinterpret_cast<H8*>(yp + c0) = pack8(o);
                 }
-                *reinterpret_cast<H8*>(yp + c0) = pack8(o);
             }
         }
     }
@@ -221,7 +243,205 @@ __global__ void __launch_bounds__(256) k_image_prep(const uint8_t* __restrict__ 
     }
 }
 
+// MaxPool2d(K, stride, pad[, ceil_mode]) NHWC fp16 on channel slices: one thread per (output pixel, 8-channel vector).
+__global__ void __launch_bounds__(256) k_maxpool(const __half* __restrict__ x, int ldx, int xoff, int N, int H, int W, int C, int K, int stride, int pad,
+                                                 int Ho, int Wo, __half* __restrict__ y, int ldy, int yoff) {
+    const int cv = C / 8;
+    const long long total = (long long) N * Ho * Wo * cv;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int c0 = (int) (i % cv) * 8;
+        const long long p = i / cv;
+        const int ox = (int) (p % Wo), oy = (int) ((p / Wo) % Ho);
+        const long long n = p / ((long long) Wo * Ho);
+        float m[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+        for (int r = 0; r < K; ++r) {
+            const int iy = oy * stride - pad + r;
+            if (iy < 0 || iy >= H) continue;
+            for (int s2 = 0; s2 < K; ++s2) {
+                const int ix = ox * stride - pad + s2;
+                if (ix < 0 || ix >= W) continue;
+                float f[8];
+                unpack8(*reinterpret_cast<const H8*>(x + ((n * H + iy) * W + ix) * ldx + xoff + c0), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], f[e]);
+            }
+        }
+        *reinterpret_cast<H8*>(y + p * ldy + yoff + c0) = pack8(m);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_add(const __half* __restrict__ a, int lda, int aoff, const __half* __restrict__ b, int ldb, int boff, long long npix,
+                                             int C, __half* __restrict__ y, int ldy, int yoff) {
+    const int cv = C / 8;
+    const long long total = npix * cv;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int c0 = (int) (i % cv) * 8;
+        const long long p = i / cv;
+        float fa[8], fb[8];
+        unpack8(*reinterpret_cast<const H8*>(a + p * lda + aoff + c0), fa);
+        unpack8(*reinterpret_cast<const H8*>(b + p * ldb + boff + c0), fb);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) fa[e] += fb[e];
+        *reinterpret_cast<H8*>(y + p * ldy + yoff + c0) = pack8(fa);
+    }
+}
+
+// y = PReLU(x) with per-channel slopes (the pre-activation of the GridNet blocks, pointcloud_inpainting.py:10-13).  4*C B/px.
+__global__ void __launch_bounds__(256) k_prelu(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ slope, long long npix, int C,
+                                               __half* __restrict__ y, int ldy, int yoff) {
+    const int cv = C / 8;
+    const long long total = npix * cv;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int c0 = (int) (i % cv) * 8;
+        const long long p = i / cv;
+        float f[8];
+        unpack8(*reinterpret_cast<const H8*>(x + p * ldx + xoff + c0), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.f ? f[e] : f[e] * __ldg(slope + c0 + e);
+        *reinterpret_cast<H8*>(y + p * ldy + yoff + c0) = pack8(f);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_resample_f32(const float* __restrict__ x, int N, int Hi, int Wi, int Ho, int Wo, int ac, float* __restrict__ y) {
+    const long long total = (long long) N * Ho * Wo;
+    const float sh = ac ? (Ho > 1 ? (float) (Hi - 1) / (float) (Ho - 1) : 0.f) : (float) Hi / (float) Ho;
+    const float sw = ac ? (Wo > 1 ? (float) (Wi - 1) / (float) (Wo - 1) : 0.f) : (float) Wi / (float) Wo;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int ox = (int) (i % Wo), oy = (int) ((i / Wo) % Ho);
+        const float* xb = x + (i / ((long long) Wo * Ho)) * Hi * Wi;
+        const float fy = ac ? oy * sh : fmaxf((oy + 0.5f) * sh - 0.5f, 0.f), fx = ac ? ox * sw : fmaxf((ox + 0.5f) * sw - 0.5f, 0.f);
+        const int y0 = min((int) fy, Hi - 1), x0 = min((int) fx, Wi - 1), y1 = min(y0 + 1, Hi - 1), x1 = min(x0 + 1, Wi - 1);
+        const float ly = fy - y0, lx = fx - x0;
+        y[i] = (1.f - ly) * ((1.f - lx) * xb[y0 * Wi + x0] + lx * xb[y0 * Wi + x1]) + ly * ((1.f - lx) * xb[y1 * Wi + x0] + lx * xb[y1 * Wi + x1]);
+    }
+}
+
 }  // namespace
+
+static int pool_out(int H, int K, int stride, int pad, int ceil_mode) {
+    int o = ceil_mode ? (H + 2 * pad - K + stride - 1) / stride + 1 : (H + 2 * pad - K) / stride + 1;
+    if (ceil_mode && (o - 1) * stride >= H + pad) --o;      // PyTorch: the last window must start inside the (left-padded) input
+    return o;
+}
+
+extern "C" int csb_maxpool2d_nhwc(const void* x, int ldx, int xoff, int N, int H, int W, int C, int K, int stride, int pad, int ceil_mode, void* y, int ldy,
+                                  int yoff, void* stream) {
+    CSB_REQUIRE(x && y && C % 8 == 0 && N > 0 && H > 0 && W > 0 && K > 0 && stride > 0 && (ldx | xoff | ldy | yoff) % 8 == 0, "bad arguments");
+    const int Ho = pool_out(H, K, stride, pad, ceil_mode), Wo = pool_out(W, K, stride, pad, ceil_mode);
+    k_maxpool<<<csb::wave_grid((long long) N * Ho * Wo * (C / 8), 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) x, ldx, xoff, N, H, W, C, K, stride, pad,
+                                                                                                            Ho, Wo, (__half*) y, ldy, yoff);
+    return csb::launched("k_maxpool", (cudaStream_t) stream);
+}
+
+extern "C" int csb_maxpool_nhwc(const void* x, int N, int H, int W, int C, void* y, void* stream) {
+    return csb_maxpool2d_nhwc(x, C, 0, N, H, W, C, 3, 2, 1, 0, y, C, 0, stream);
+}
+
+extern "C" int csb_add_nhwc(const void* a, int lda, int aoff, const void* b, int ldb, int boff, long long npix, int C, void* y, int ldy, int yoff, void* stream) {
+    CSB_REQUIRE(a && b && y && C % 8 == 0 && (lda | aoff | ldb | boff | ldy | yoff) % 8 == 0, "bad arguments");
+    k_add<<<csb::wave_grid(npix * (C / 8), 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) a, lda, aoff, (const __half*) b, ldb, boff, npix, C, (__half*) y, ldy, yoff);
+    return csb::launched("k_add", (cudaStream_t) stream);
+}
+
+extern "C" int csb_prelu_nhwc(const void* x, int ldx, int xoff, const float* slope, long long npix, int C, void* y, int ldy, int yoff, void* stream) {
+    CSB_REQUIRE(x && y && slope && C % 8 == 0 && (ldx | xoff | ldy | yoff) % 8 == 0, "bad arguments");
+    k_prelu<<<csb::wave_grid(npix * (C / 8), 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) x, ldx, xoff, slope, npix, C, (__half*) y, ldy, yoff);
+    return csb::launched("k_prelu", (cudaStream_t) stream);
+}
+
+extern "C" int csb_resample_f32(const float* x, int N, int Hi, int Wi, int Ho, int Wo, int align_corners, float* y, void* stream) {
+    CSB_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bad arguments");
+    k_resample_f32<<<csb::wave_grid((long long) N * Ho * Wo, 256, 8), 256, 0, (cudaStream_t) stream>>>(x, N, Hi, Wi, Ho, Wo, align_corners, y);
+    return csb::launched("k_resample_f32", (cudaStream_t) stream);
+}
+
+// Spatially tiled depthwise KxK: each thread owns 2 channels (one half2) and a 4x4 block of output pixels, a warp owns 64 consecutive channels
+// of one tile (128 B coalesced rows), so every loaded input is reused by up to K*K/((4+K-1)^2/16) outputs from registers: L1 traffic drops from
+// ~84 B to ~12 B per output element compared with the one-pixel-per-warp kernel above.  No LayerNorm here (a pixel's channels are spread over
+// several warps): the ConvNeXt block runs this kernel followed by k_layernorm in place.
+template <int K>
+__global__ void __launch_bounds__(256) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy,
+                                                     int yoff) {
+    constexpr int R = K / 2, TS = 4, IN = TS + K - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = C / 64;
+    const int tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
+    const long long ntasks = (long long) N * tiles_y * tiles_x * chunks;
+    for (long long task = (long long) blockIdx.x * 8 + warp; task < ntasks; task += (long long) gridDim.x * 8) {
+        const int tx = (int) (task % tiles_x);           // consecutive warps -> horizontally adjacent tiles of the same channel chunk (halo reuse in L1)
+        long long t2 = task / tiles_x;
+        const int chunk = (int) (t2 % chunks);
+        t2 /= chunks;
+        const int ty = (int) (t2 % tiles_y);
+        const long long img = t2 / tiles_y;
+        const int c0 = chunk * 64 + lane * 2;
+        const int ox0 = tx * TS, oy0 = ty * TS;
+        float2 acc[TS][TS];
+        const float2 b2 = bias ? __ldg(reinterpret_cast<const float2*>(bias + c0)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < TS; ++i)
+#pragma unroll
+            for (int j = 0; j < TS; ++j) acc[i][j] = b2;
+        const __half* xb = x + (img * H * W) * ldx + xoff + c0;
+#pragma unroll
+        for (int iy = 0; iy < IN; ++iy) {
+            const int gy = oy0 + iy - R;
+            float2 xr[IN];
+            const bool rowok = gy >= 0 && gy < H;
+#pragma unroll
+            for (int ix = 0; ix < IN; ++ix) {
+                const int gx = ox0 + ix - R;
+                xr[ix] = (rowok && gx >= 0 && gx < W) ? __half22float2(*reinterpret_cast<const __half2*>(xb + ((size_t) gy * W + gx) * ldx)) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const int oy = iy - r;
+                if (oy < 0 || oy >= TS) continue;            // resolved at compile time (iy, r are unrolled constants)
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float2 wv = __ldg(reinterpret_cast<const float2*>(w + (size_t) (r * K + k) * C + c0));
+#pragma unroll
+                    for (int t = 0; t < TS; ++t) {
+                        acc[oy][t].x = fmaf(xr[t + k].x, wv.x, acc[oy][t].x);
+                        acc[oy][t].y = fmaf(xr[t + k].y, wv.y, acc[oy][t].y);
+                    }
+                }
+            }
+        }
+        __half* yb = y + (img * H * W) * ldy + yoff + c0;
+#pragma unroll
+        for (int i = 0; i < TS; ++i) {
+            const int gy = oy0 + i;
+            if (gy >= H) break;
+#pragma unroll
+            for (int j = 0; j < TS; ++j) {
+                const int gx = ox0 + j;
+                if (gx >= W) break;
+                *reinterpret_cast<__half2*>(yb + ((size_t) gy * W + gx) * ldy) = __floats2half2_rn(act_f(acc[i][j].x, act), act_f(acc[i][j].y, act));
+            }
+        }
+    }
+}
+
+template <int K>
+static int launch_dwconv(const __half* xh, int ldx, int xoff, const float* w, const float* bias, const float* g, const float* b, float eps, int act, int N, int H,
+                         int W, int C, __half* yh, int ldy, int yoff, cudaStream_t st) {
+    const int nv = (C + 255) / 256;
+#define CSB_DW(T_, NV_)                                                                                                                        \
+    do {                                                                                                                                       \
+        const long long groups = (long long) N * H * ((W + T_ - 1) / T_);                                                                      \
+        k_dwconv<K, T_, NV_><<<csb::wave_grid(groups * 32, 256, 8), 256, 0, st>>>(xh, ldx, xoff, w, bias, g, b, eps, act, N, H, W, C, yh, ldy, yoff); \
+    } while (0)
+    if (nv == 1) CSB_DW(4, 1);
+    else if (nv == 2) CSB_DW(4, 2);
+    else if (nv <= 4) CSB_DW(2, 4);
+    else CSB_DW(1, 8);
+#undef CSB_DW
+    return csb::launched("k_dwconv", st);
+}
 
 extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w, const float* bias, const float* ln_gamma, const float* ln_beta,
                                float eps, int act, int N, int H, int W, int C, int K, void* y, int ldy, int yoff, void* stream) {
@@ -230,14 +450,24 @@ extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w,
     CSB_REQUIRE(ldx % 8 == 0 && xoff % 8 == 0 && ldy % 8 == 0 && yoff % 8 == 0, "channel strides/offsets must be multiples of 8");
     CSB_REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "LayerNorm needs both gamma and beta");
     cudaStream_t st = (cudaStream_t) stream;
-    const long long npix = (long long) N * H * W;
-    const int grid = csb::wave_grid(npix * 32, 256, 8);
     const __half* xh = (const __half*) x;
     __half* yh = (__half*) y;
-    if (K == 3) k_dwconv<3><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff);
-    else if (K == 5) k_dwconv<5><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff);
-    else k_dwconv<7><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff);
-    return csb::launched("k_dwconv", st);
+    if ((K == 5 || K == 7) && C % 64 == 0 && (ldx | xoff | ldy | yoff) % 2 == 0) {
+        // tiled path: depthwise conv (+ bias, + activation when there is no LayerNorm), then LayerNorm in place
+        const long long ntasks = (long long) N * ((H + 3) / 4) * ((W + 3) / 4) * (C / 64);
+        const int grid = csb::wave_grid(ntasks * 32, 256, 4);
+        const int a = ln_gamma ? CSB_ACT_NONE : act;
+        if (K == 5) k_dwconv_tile<5><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
+        else k_dwconv_tile<7><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
+        CSB_TRY(csb::launched("k_dwconv_tile", st));
+        if (!ln_gamma) return CSB_OK;
+        CSB_REQUIRE(act == CSB_ACT_NONE, "LayerNorm followed by an activation is not used on this path");
+        k_layernorm<<<csb::wave_grid((long long) N * H * W * 32, 256, 8), 256, 0, st>>>(yh, ldy, yoff, ln_gamma, ln_beta, eps, (long long) N * H * W, C, yh, ldy, yoff);
+        return csb::launched("k_layernorm", st);
+    }
+    if (K == 3) return launch_dwconv<3>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
+    if (K == 5) return launch_dwconv<5>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
+    return launch_dwconv<7>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
 }
 
 extern "C" int csb_layernorm_nhwc(const void* x, int ldx, int xoff, const float* gamma, const float* beta, float eps, long long npix, int C, void* y,

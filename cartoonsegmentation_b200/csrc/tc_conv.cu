@@ -47,6 +47,7 @@ struct ConvKernelParams {
     int bh, bw, tiles_h, tiles_w, tiles_m, tiles_n, block_n;
     int bk, kchunks, stages;     // bk: channels per k-block (64/32/16) -> swizzle 128/64/32 B
     int in_coff;
+    int grouped;                 // 1: block-diagonal conv in 64-channel slices (ResNeXt grouped 3x3): n-tile j reads only input slice j
     // epilogue
     const float* bias;
     const void* residual;
@@ -127,7 +128,8 @@ template <int ACT>
 __device__ __forceinline__ float apply_act(float x, float slope) {
     if constexpr (ACT == CSB_ACT_RELU) return fmaxf(x, 0.0f);
     else if constexpr (ACT == CSB_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
-    else if constexpr (ACT == CSB_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    else if constexpr (ACT == CSB_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));   // exact-erf GELU (measured faster than an
+                                                                                                           // A&S 7.1.26 rational form with rcp.rn)
     else if constexpr (ACT == CSB_ACT_PRELU) return x > 0.0f ? x : x * slope;
     else if constexpr (ACT == CSB_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
     else if constexpr (ACT == CSB_ACT_SOFTPLUS) return x > 20.0f ? x : log1pf(__expf(x));
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             const uint32_t a_dst = smem_base + (uint32_t) stage * stage_bytes, b_dst = a_dst + a_bytes;
                             mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
-                            tma_load_4d(a_dst, &tmA, full_bar(stage), p.in_coff + kc * p.bk, ow0 * p.stride + s * p.dil - p.pad,
+                            tma_load_4d(a_dst, &tmA, full_bar(stage), p.in_coff + (p.grouped ? n0 : kc * p.bk), ow0 * p.stride + s * p.dil - p.pad,
                                         oh0 * p.stride + r * p.dil - p.pad, img);
                             tma_load_2d(b_dst, &tmB, full_bar(stage), ((r * p.S + s) * p.kchunks + kc) * p.bk, n0);
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -411,8 +413,14 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
     p.Cin = d->Cin; p.Cout = d->Cout; p.R = d->R; p.S = d->S; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil;
     p.bk = d->Cin % 64 == 0 ? 64 : (d->Cin % 32 == 0 ? 32 : 16);
     p.kchunks = d->Cin / p.bk;
+    p.grouped = d->groups > 1;
+    if (p.grouped) {
+        CSB_REQUIRE(d->Cin == d->Cout && d->Cin % 64 == 0 && d->Cin % d->groups == 0 && 64 % (d->Cin / d->groups) == 0,
+                    "grouped conv needs Cin == Cout, a multiple of 64, with 64 % (Cin/groups) == 0");
+        p.kchunks = 1;      // w is [Cout][R][S][64]: the 64x64 diagonal block of each output slice (zeros outside the groups)
+    }
     p.in_coff = d->in_coff;
-    const bool flat = d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0;
+    const bool flat = d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0 && !p.grouped;
     cuuint64_t gdim[4], gstr[3];
     cuuint32_t box[4], estr[4];
     const cuuint64_t esz = 2;
@@ -434,7 +442,7 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
         gstr[0] = (cuuint64_t) d->in_ld * esz; gstr[1] = gstr[0] * d->Win; gstr[2] = gstr[1] * d->Hin;
     }
     p.tiles_h = (p.H + p.bh - 1) / p.bh; p.tiles_w = (p.W + p.bw - 1) / p.bw; p.tiles_m = p.N * p.tiles_h * p.tiles_w;
-    p.block_n = d->Cout >= 256 ? 256 : ((d->Cout + 15) / 16) * 16;
+    p.block_n = p.grouped ? 64 : (d->Cout >= 256 ? 256 : ((d->Cout + 15) / 16) * 16);
     p.tiles_n = (d->Cout + p.block_n - 1) / p.block_n;
     box[0] = (cuuint32_t) p.bk; box[1] = (cuuint32_t) (p.bw * d->stride); box[2] = (cuuint32_t) (p.bh * d->stride); box[3] = 1;
     estr[0] = 1; estr[1] = (cuuint32_t) d->stride; estr[2] = (cuuint32_t) d->stride; estr[3] = 1;
@@ -443,7 +451,7 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
     CUresult r = enc(&tmA, dt, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(p.bk),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_conv2d_nhwc", "cuTensorMapEncodeTiled(A) failed");
-    const cuuint64_t ktot = (cuuint64_t) d->R * d->S * d->Cin;
+    const cuuint64_t ktot = (cuuint64_t) d->R * d->S * (p.grouped ? 64 : d->Cin);
     cuuint64_t wdim[2] = {ktot, (cuuint64_t) d->Cout}, wstr[1] = {ktot * esz};
     cuuint32_t wbox[2] = {(cuuint32_t) p.bk, (cuuint32_t) p.block_n}, westr[2] = {1, 1};
     r = enc(&tmB, dt, 2, const_cast<void*>(w), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(p.bk),

@@ -14,7 +14,7 @@ ACT = {None: 0, 'none': 0, 'relu': 1, 'silu': 2, 'gelu': 3, 'prelu': 4, 'sigmoid
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("N", "Hin", "Win", "Cin", "in_ld", "in_coff", "Cout", "R", "S", "stride", "pad", "dil",
-                                       "out_ld", "out_coff", "act", "res_mode", "res_ld", "res_coff", "dtype")]
+                                       "out_ld", "out_coff", "act", "res_mode", "res_ld", "res_coff", "dtype", "groups")]
 
 
 def pack_conv_weight(w, dtype=torch.float16, cin_pad=None):
@@ -30,12 +30,27 @@ def out_hw(Hin, Win, R, S, stride, pad, dil):
     return (Hin + 2 * pad - dil * (R - 1) - 1) // stride + 1, (Win + 2 * pad - dil * (S - 1) - 1) // stride + 1
 
 
+def pack_grouped_weight(w, groups, dtype=torch.float16):
+    """torch grouped conv weight [Cout, Cin/groups, R, S] (Cin == Cout) -> [Cout, R, S, 64]: for each output channel the weights over the
+    64-channel input slice that contains its group (zeros outside the group) -- the block-diagonal form csb_conv2d_nhwc(groups>1) expects."""
+    Cout, cpg, R, S = w.shape
+    assert Cout % 64 == 0 and 64 % cpg == 0 and Cout // groups == cpg
+    out = torch.zeros((Cout, R, S, 64), device=w.device, dtype=torch.float32)
+    co = torch.arange(Cout, device=w.device)
+    base = ((co % 64) // cpg) * cpg                       # first input channel of the group inside the 64-slice
+    idx = base[:, None] + torch.arange(cpg, device=w.device)[None]          # [Cout, cpg]
+    out.view(Cout, R * S, 64).scatter_(2, idx[:, None, :].expand(Cout, R * S, cpg), w.permute(0, 2, 3, 1).reshape(Cout, R * S, cpg).float())
+    return out.contiguous().to(dtype)
+
+
 def conv2d_nhwc(x, w, bias=None, stride=1, pad=0, dil=1, act=None, act_param=None, residual=None, res_mode=0, out=None, out_coff=0,
-                in_coff=0, cin=None, res_coff=0, out_f32=False):
+                in_coff=0, cin=None, res_coff=0, out_f32=False, groups=1):
     """x: [N,H,W,Cx] NHWC fp16/bf16 (channels in_coff..in_coff+cin used); w: packed [Cout,R,S,Cin]; -> y [N,Ho,Wo,Cout] (or `out`
     written at channel offset out_coff).  residual: NHWC tensor added before (res_mode=1) / after (res_mode=2) the activation."""
     N, H, W, Cx = x.shape
     Cout, R, S, Cin = w.shape
+    if groups > 1:
+        Cin = Cout
     cin = Cin if cin is None else cin
     assert cin == Cin and x.dtype == w.dtype and x.dtype in (torch.float16, torch.bfloat16)
     Ho, Wo = out_hw(H, W, R, S, stride, pad, dil)
@@ -45,7 +60,7 @@ def conv2d_nhwc(x, w, bias=None, stride=1, pad=0, dil=1, act=None, act_param=Non
     if residual is not None and res_mode == 0:
         res_mode = 1
     d = ConvDesc(N, H, W, Cin, Cx, in_coff, Cout, R, S, stride, pad, dil, out.shape[3], out_coff, ACT[act], res_mode,
-                 residual.shape[3] if residual is not None else 0, res_coff, 1 if x.dtype == torch.bfloat16 else 0)
+                 residual.shape[3] if residual is not None else 0, res_coff, 1 if x.dtype == torch.bfloat16 else 0, groups)
     is_f32 = out.dtype == torch.float32
     check(lib().csb_conv2d_nhwc(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(act_param), ptr(residual), None if is_f32 else ptr(out),
                                 ptr(out) if is_f32 else None, stream()), "csb_conv2d_nhwc")
@@ -97,4 +112,45 @@ def image_prep_nhwc(img_u8, mean, std, swap_rb=False, CP=16):
     out = torch.empty((N, H, W, CP), device=img_u8.device, dtype=torch.float16)
     m = (C.c_float * 3)(*[float(v) for v in mean]); s = (C.c_float * 3)(*[float(v) for v in std])
     check(lib().csb_image_prep_nhwc(ptr(img_u8), C.c_longlong(N * H * W), m, s, int(swap_rb), CP, ptr(out), stream()), "csb_image_prep_nhwc")
+    return out
+
+
+def maxpool3s2_nhwc(x):
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), device=x.device, dtype=x.dtype)
+    check(lib().csb_maxpool_nhwc(ptr(x), N, H, W, Cc, ptr(out), stream()), "csb_maxpool_nhwc")
+    return out
+
+
+def add_nhwc(a, b, out=None):
+    Cc = a.shape[-1]
+    npix = a.numel() // Cc
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().csb_add_nhwc(ptr(a), Cc, 0, ptr(b), b.shape[-1], 0, C.c_longlong(npix), Cc, ptr(out), out.shape[-1], 0, stream()), "csb_add_nhwc")
+    return out
+
+
+def resample_f32(x, Ho, Wo, align_corners):
+    """x [N,Hi,Wi] fp32 -> [N,Ho,Wo] bilinear"""
+    N, Hi, Wi = x.shape
+    out = torch.empty((N, Ho, Wo), device=x.device, dtype=torch.float32)
+    check(lib().csb_resample_f32(ptr(x), N, Hi, Wi, Ho, Wo, int(align_corners), ptr(out), stream()), "csb_resample_f32")
+    return out
+
+
+def pool_out(H, K, stride, pad, ceil_mode):
+    o = (H + 2 * pad - K + stride - 1) // stride + 1 if ceil_mode else (H + 2 * pad - K) // stride + 1
+    if ceil_mode and (o - 1) * stride >= H + pad:
+        o -= 1
+    return o
+
+
+def maxpool2d_nhwc(x, K=2, stride=2, pad=0, ceil_mode=False, xoff=0, channels=None, out=None, yoff=0):
+    N, H, W, ldx = x.shape
+    Cc = ldx if channels is None else channels
+    Ho, Wo = pool_out(H, K, stride, pad, ceil_mode), pool_out(W, K, stride, pad, ceil_mode)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cc), device=x.device, dtype=x.dtype)
+    check(lib().csb_maxpool2d_nhwc(ptr(x), ldx, xoff, N, H, W, Cc, K, stride, pad, int(ceil_mode), ptr(out), out.shape[3], yoff, stream()), "csb_maxpool2d_nhwc")
     return out

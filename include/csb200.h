@@ -74,9 +74,25 @@ CSB_API int csb_autozoom_coverage(const float* points, int N, int H, int W, doub
                           const float* shifts, int S, int32_t* zkey, float* zee, uint8_t* cover, int32_t* counts,
                           void* stream);
 
+/* Context render of the Inpaint net -- anime_3dkenburns/models/pointcloud_inpainting.py:135-146: render_pointcloud of a C-channel payload given as
+ * fp16 channel-interleaved [N, ld] (straight from the conv engine), then tenExisting = (existing > 0) * median-5(existing > 0), render *= tenExisting,
+ * written as the NHWC fp16 input of netInput: out16 [H,W,ldo] = {render[0..C), tenExisting, 0...}; existing [H,W] fp32 (0/1).
+ * scratch: zkey/zee/acc as csb_pointcloud_render (CP = csb_render_acc_channels(C)), flags [H*W] uint8.  shift: 3 host floats. */
+CSB_API int csb_inpaint_context_render(const float* points, const void* data16, int ld, int N, int C, int H, int W, double focal, double baseline,
+                               const float* shift, int32_t* zkey, float* zee, float* acc, uint8_t* flags, void* out16, int ldo, float* existing,
+                               void* stream);
+
 /* fill_disocclusion -- anime_3dkenburns/common.py:145-247 (kernel_discfill_updateOutput :149-245).
  *   input [B,C,H,W], depth [B,1,H,W] -> output [B,C,H,W] (output may not alias input). */
 CSB_API int csb_disocclusion_fill(const float* input, const float* depth, int B, int C, int H, int W, float* output, void* stream);
+
+/* depth_adjustment_animesseg -- anime_3dkenburns/kenburns_effect.py:39-91 (non-median branch), all K instance masks applied in order
+ * on the device without host syncs.  disparity [H,W] fp32 in place; masks [K,H,W] uint8 0/1 (torch.bool); state: 16 bytes of device scratch.
+ * (The reference's `.sum() == 0` skip and row tests are evaluated as "any plane > 0", identical for non-negative disparities.) */
+CSB_API int csb_depth_adjust_instances(float* disparity, const uint8_t* masks, int K, int H, int W, void* state, void* stream);
+/* The same for a batch in ONE cooperative launch: disparity [N,H,W] in place, masks [N,Kmax,H,W], num [N] device int32 (instances per image,
+ * e.g. straight from csb_rtmdet_select), state: (3*N*Kmax + N) int32 of device scratch.  N <= number of SMs. */
+CSB_API int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, const int* num, int N, int Kmax, int H, int W, int32_t* state, void* stream);
 
 /* process_shift scalar part -- anime_3dkenburns/common.py:60-72, evaluated on the device in double precision from the
  * `scalars` written by csb_disparity_to_cloud (closest point = argmin of the depth crop): fltShiftU/V as in the reference,
@@ -110,6 +126,9 @@ CSB_API int csb_disparity_to_cloud(const float* raw, int H, int W, double focal,
  *   csb_frame_crop_resize:  frame [H,W,3] u8 -> out [H,W,3] u8 (crop pw x ph around (cx,cy), resize to W x H) */
 CSB_API int csb_frame_pack_u8(const float* render, int H, int W, uint8_t* frame, void* stream);
 CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, int ph, double cx, double cy, uint8_t* out, void* stream);
+
+/* cv2.resize(src, (Wo,Ho), interpolation=INTER_LINEAR) on uint8 HWC images, bit-exact (used for scaledown_maxsize, utils/io_utils.py:254-274). */
+CSB_API int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream);
 
 /* Fused Ken-Burns frame: shift + render (C=4: BGR + depth) + normalise + disocclusion fill + u8 pack, then
  * crop+resize -- the body of the reference's frame loop, kenburns_effect.py:1028-1040,1069-1070, as 6 launches.
@@ -150,6 +169,9 @@ typedef struct csb_conv_desc {
     int act;
     int res_mode, res_ld, res_coff;
     int dtype;                /* 0 fp16, 1 bf16 */
+    int groups;               /* 0/1 dense; > 1: grouped conv (Cin == Cout, Cin % 64 == 0, 64 % (Cin/groups) == 0) with w given as
+                                 [Cout][R][S][64] = the 64x64 block-diagonal slice of each 64 output channels (ResNeXt 32x8d 3x3 convs,
+                                 depth_modules/leres/leres/Resnext_torch.py:70-118) */
 } csb_conv_desc;
 
 CSB_API int csb_conv2d_nhwc(const csb_conv_desc* desc, const void* x, const void* w, const float* bias, const float* act_param,
@@ -171,6 +193,17 @@ CSB_API int csb_layernorm_nhwc(const void* x, int ldx, int xoff, const float* ga
 CSB_API int csb_resample_nhwc(const void* x, int ldx, int xoff, int N, int Hi, int Wi, int C, int Ho, int Wo, int mode, void* y, int ldy, int yoff,
                       void* stream);
 CSB_API int csb_image_prep_nhwc(const uint8_t* img, long long npix, const float* mean3, const float* std3, int swap_rb, int CP, void* y, void* stream);
+/*   csb_maxpool_nhwc    MaxPool2d(kernel 3, stride 2, padding 1) (ResNeXt stem, Resnext_torch.py:160).
+ *   csb_add_nhwc        y = a + b on channel slices (FFM skip add, network_auxi.py:207).
+ *   csb_resample_f32    single-channel fp32 bilinear resize, align_corners selectable (AO output upsample, network_auxi.py:251). */
+CSB_API int csb_maxpool_nhwc(const void* x, int N, int H, int W, int C, void* y, void* stream);
+/*   csb_maxpool2d_nhwc  general MaxPool2d(K, stride, pad, ceil_mode) on channel slices (ISNet's 2x2 ceil-mode pools, isnet.py:130). */
+CSB_API int csb_maxpool2d_nhwc(const void* x, int ldx, int xoff, int N, int H, int W, int C, int K, int stride, int pad, int ceil_mode, void* y, int ldy,
+                       int yoff, void* stream);
+CSB_API int csb_add_nhwc(const void* a, int lda, int aoff, const void* b, int ldb, int boff, long long npix, int C, void* y, int ldy, int yoff, void* stream);
+/*   csb_prelu_nhwc      y = PReLU(x), per-channel slopes (pre-activations of the Inpaint GridNet, pointcloud_inpainting.py:10-13). */
+CSB_API int csb_prelu_nhwc(const void* x, int ldx, int xoff, const float* slope, long long npix, int C, void* y, int ldy, int yoff, void* stream);
+CSB_API int csb_resample_f32(const float* x, int N, int Hi, int Wi, int Ho, int Wo, int align_corners, float* y, void* stream);
 
 /* RTMDet-Ins post-processing (csrc/det_post.cu) -- SURVEY.md §8a rows A5-A8; mmdet predict_by_feat / mmcv batched_nms restated in
  * SURVEY.md Appendix A.7, mask head animeinsseg/models/rtmdet_inshead_custom.py:253-303, mask tail animeinsseg/__init__.py:361-370.
@@ -188,6 +221,13 @@ CSB_API int csb_rtmdet_select(const float* const* cls, const float* const* reg, 
                       float* cand, int* cand_count, float* boxes, float* scores, float* priors, float* kernels, int* num, void* stream);
 CSB_API int csb_rtmdet_masks(const float* mask_feat, const float* kernels, const float* priors, const int* num, int N, int max_per_img, int h, int w,
                      int stride0, int out_h, int out_w, int resized_h, int resized_w, float mask_thr, float* logits, uint8_t* masks, void* stream);
+
+/* ISNet mask refinement glue (csrc/det_refine.cu) -- animeinsseg/__init__.py:37-55 (prepare_refine_batch), :638-665 (_postprocess_refine).
+ *   csb_refine_prep: img [h,w,3] u8 (the image already scaled down to <= S), masks [K,H,W] u8 0/1 -> x16 [K,S,S,16] fp16 NHWC =
+ *                    {B,G,R}/255, mask resized like cv2.resize(float, INTER_LINEAR), zero padded bottom/right (resize_pad, utils/io_utils.py:277-292).
+ *   csb_refine_post: d1 [K,S,S] fp32 logits -> sigmoid -> crop [:h,:w] -> bilinear(align_corners=True) to (H,W) -> > mask_thr -> masks_out [K,H,W] u8. */
+CSB_API int csb_refine_prep(const uint8_t* img_hw3, int h, int w, const uint8_t* masks, int K, int H, int W, int S, void* x16, void* stream);
+CSB_API int csb_refine_post(const float* d1, int K, int S, int h, int w, int H, int W, float mask_thr, uint8_t* masks_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,73 @@
+"""GPU parity of the ISNet mask refinement: the ISNetDIS forward against golden outputs of the UNMODIFIED reference
+module (tests/golden/make_isnet_golden.py), and the device-side prepare / post-process against the reference's host formulation (OpenCV + torch)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["isnet_ref_96x128.npz", "isnet_ref_144x112.npz"])
+def test_isnet_forward_vs_reference_golden(built_lib, name):
+    from cartoonsegmentation_b200.animeinsseg import isnet as I
+    g = np.load(os.path.join(GOLD, name))
+    H, W = g['mask'].shape
+    x = np.zeros((1, H, W, 16), np.float16)
+    x[0, ..., :3] = (g['image'].astype(np.float32) / 255.0).astype(np.float16)
+    x[0, ..., 3] = g['mask'].astype(np.float16)
+    net = I.ISNetDIS(I.synthetic_state_dict(0))
+    d1 = net.forward(torch.from_numpy(x).cuda())[0].cpu().numpy()
+    ref = g['d1']
+    rel = np.sqrt(((d1 - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean())
+    relc = np.sqrt((((d1 - d1.mean()) - (ref - ref.mean())) ** 2).mean()) / ref.std()
+    print(f"{name}: relative RMS error {rel:.5f} (centred {relc:.5f})")
+    assert d1.shape == ref.shape and rel < 1e-2 and relc < 2e-2
+    # decision parity at the data's own median level (random weights give all-positive logits; the median puts the threshold inside the data)
+    t = np.median(ref)
+    assert ((d1 > t) != (ref > t)).mean() < 5e-3
+
+
+def test_refine_prep_and_post_vs_reference_host_code(built_lib):
+    import ctypes as C
+    import cv2
+    from cartoonsegmentation_b200._lib import lib, ptr, stream, check
+    from cartoonsegmentation_b200.utils.synthetic import ellipse_masks, smooth_image
+    H, W, S = 200, 260, 128                       # forces the shrink path (max side 260 > 128) and bottom/right padding
+    img = smooth_image(H, W, seed=1)
+    masks = ellipse_masks(H, W, k=3, seed=2)
+    # reference: resize_pad(img) / resize_pad(seg.astype(float32)) with scaledown_maxsize -> cv2.resize INTER_LINEAR, pad bottom/right with 0
+    r = S / max(H, W)
+    h, w = int(round(H * r)), int(round(W * r))
+    img_s = cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)
+    ref = np.zeros((3, S, S, 4), np.float32)
+    for k in range(3):
+        ref[k, :h, :w, :3] = img_s.astype(np.float32) / 255.0
+        ref[k, :h, :w, 3] = cv2.resize(masks[k].astype(np.float32), (w, h), interpolation=cv2.INTER_LINEAR)
+    small = torch.empty((h, w, 3), device='cuda', dtype=torch.uint8)
+    check(lib().csb_resize_u8c3(ptr(torch.from_numpy(img).cuda()), H, W, ptr(small), h, w, stream()))
+    assert np.array_equal(small.cpu().numpy(), img_s)                                        # cv2.resize on uint8: bit exact
+    x16 = torch.empty((3, S, S, 16), device='cuda', dtype=torch.float16)
+    check(lib().csb_refine_prep(ptr(small), h, w, ptr(torch.from_numpy(masks).cuda().view(torch.uint8)), 3, H, W, S, ptr(x16), stream()))
+    got = x16.float().cpu().numpy()
+    assert np.abs(got[..., :4] - ref).max() < 1e-3 and np.abs(got[..., 4:]).max() == 0       # fp16 storage of [0,1] values
+    # post: sigmoid -> crop -> interpolate(align_corners=True) -> > thr
+    d1 = torch.randn(3, S, S, device='cuda') * 3
+    out = torch.empty((3, H, W), device='cuda', dtype=torch.uint8)
+    check(lib().csb_refine_post(ptr(d1), 3, S, h, w, H, W, C.c_float(0.3), ptr(out), stream()))
+    preds = F.interpolate(d1.sigmoid()[:, None, :h, :w], (H, W), mode='bilinear', align_corners=True)[:, 0]
+    assert ((preds > 0.3) != out.bool()).float().mean().item() < 1e-4
+
+
+def test_infer_with_refinement_runs(built_lib):
+    from cartoonsegmentation_b200.animeinsseg import AnimeInsSeg
+    from cartoonsegmentation_b200.utils.synthetic import smooth_image
+    img = smooth_image(256, 256, seed=4)
+    seg = AnimeInsSeg(None, default_det_size=256, refine_kwargs={'refine_method': 'refinenet_isnet', 'refine_size': 128})
+    a = seg.infer(img, det_size=256, max_instances=6)
+    b = seg.infer(img, det_size=256, max_instances=6, refine_kwargs={'refine_method': 'none'})
+    assert len(a) == len(b) and a.masks.shape == b.masks.shape and a.masks.dtype == torch.bool
+    assert torch.equal(a.bboxes, b.bboxes)                                                   # refinement replaces masks only

@@ -1,0 +1,68 @@
+"""GPU parity of the LeReS depth forward against golden outputs of the UNMODIFIED reference network run on
+the CPU with the same seeded weights (tests/golden/make_leres_golden.py), plus the new engine pieces against plain PyTorch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    from cartoonsegmentation_b200 import engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return engine
+
+
+@pytest.mark.parametrize("C,groups,stride,H,W", [(256, 32, 1, 20, 24), (512, 32, 2, 24, 20), (1024, 32, 1, 10, 12), (2048, 32, 2, 8, 8), (128, 2, 1, 16, 16)])
+def test_grouped_conv_vs_torch(eng, C, groups, stride, H, W):
+    g = torch.Generator(device='cuda').manual_seed(C + stride)
+    x = torch.randn(2, H, W, C, device='cuda', generator=g).half()
+    w = torch.randn(C, C // groups, 3, 3, device='cuda', generator=g) / (9 * C // groups) ** 0.5
+    b = torch.randn(C, device='cuda', generator=g) * 0.1
+    y = eng.conv2d_nhwc(x, eng.pack_grouped_weight(w, groups), b, stride=stride, pad=1, act='relu', groups=groups)
+    r = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, stride=stride, padding=1, groups=groups)).permute(0, 2, 3, 1)
+    assert y.shape == r.shape
+    assert (y.float() - r).abs().max().item() <= 2e-3 * r.abs().max().item() + 1e-3
+
+
+def test_pool_add_resample_vs_torch(eng):
+    g = torch.Generator(device='cuda').manual_seed(0)
+    x = torch.randn(2, 17, 22, 64, device='cuda', generator=g).half()
+    r = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(eng.maxpool3s2_nhwc(x).float(), r)
+    y = torch.randn_like(x)
+    assert (eng.add_nhwc(x, y).float() - (x.float() + y.float())).abs().max().item() < 4e-3
+    d = torch.randn(2, 13, 19, device='cuda', generator=g)
+    for ac in (True, False):
+        o = eng.resample_f32(d, 26, 38, ac)
+        rr = F.interpolate(d[:, None], size=(26, 38), mode='bilinear', align_corners=ac)[:, 0]
+        assert (o - rr).abs().max().item() < 1e-5
+    s1 = torch.randn(1, 16, 16, 64, device='cuda', generator=g).half()              # 1x1 stride-2 conv (ResNeXt downsample)
+    w = torch.randn(128, 64, 1, 1, device='cuda', generator=g) / 8
+    o = eng.conv2d_nhwc(s1, eng.pack_conv_weight(w), None, stride=2)
+    rr = F.conv2d(s1.float().permute(0, 3, 1, 2), w.half().float(), stride=2).permute(0, 2, 3, 1)
+    assert (o.float() - rr).abs().max().item() <= 2e-3 * rr.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("name", ["leres_ref_96x128.npz", "leres_ref_160x128.npz"])
+def test_leres_forward_vs_reference_golden(eng, name):
+    from cartoonsegmentation_b200.depth_modules import leres as L
+    gold = np.load(os.path.join(GOLD, name))
+    net = L.LeReS(L.synthetic_state_dict(0))
+    out = net.forward(torch.from_numpy(gold['image']).cuda())[0].cpu().numpy()
+    ref = gold['depth']
+    rel = np.sqrt(((out - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean())
+    rel_c = np.sqrt((((out - out.mean()) - (ref - ref.mean())) ** 2).mean()) / ref.std()
+    print(f"{name}: relative RMS error {rel:.5f}, centred (what min-max normalisation sees) {rel_c:.5f}")
+    assert out.shape == ref.shape and rel < 2e-2 and rel_c < 3e-2
+    # after the reference's own 16 -> 8 bit quantisation (apply_leres) the maps agree to a few grey levels
+    qa, qb = L.quantise_depth(out), L.quantise_depth(ref)
+    d = np.abs(qa.astype(int) - qb.astype(int))
+    print(f"   8-bit depth image: max |diff| {d.max()} levels, mean {d.mean():.3f}")
+    assert d.mean() < 2.0 and np.percentile(d, 99) <= 6

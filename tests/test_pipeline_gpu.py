@@ -52,8 +52,13 @@ def test_generate_config_and_frames_vs_oracle(pipe):
         assert diff.max() <= 2 and (diff > 0).mean() < 0.08, (fltStep, diff.max(), (diff > 0).mean())     # the reference's own fp32-order envelope
     frames2 = pipe.autozoom(kcfg, inpaint=False)
     assert len(frames2) == kcfg.num_frame
-    with pytest.raises(NotImplementedError):
-        pipe.autozoom(kcfg)                      # inpaint=True needs the Inpaint net: fails loudly, never silently skipped
+    n0 = kcfg['tenInpaPoints'].shape[2]
+    frames3 = pipe.autozoom(kcfg)                # the reference's run_kenburns.py path: autozoom + 2 inpaint passes + num_frame frames
+    assert len(frames3) == kcfg.num_frame and frames3[0].shape == (H, W, 3)
+    n1 = kcfg['tenInpaPoints'].shape[2]
+    assert n1 > n0 and kcfg.inpainted_img.shape[2] == n1 and kcfg['tenInpaDepth'].shape[2] == n1      # the cloud grew by the inpainted holes
+    # inpainting can only add points: the frames of the inpainted cloud have no more holes than before at the end pose
+    assert (frames3[-1].sum(-1) == 0).sum() <= (frames2[-1].sum(-1) == 0).sum()
 
 
 def test_pipeline_with_detector_instances(pipe):
@@ -63,3 +68,54 @@ def test_pipeline_with_detector_instances(pipe):
     kcfg = pipe.generate_kenburns_config(img, disparity=torch.from_numpy(raw).cuda())       # runs AnimeInsSeg.infer + depth adjustment
     assert kcfg.instances is not None and kcfg['tenRawDisparity'].shape == (1, 1, H, W)
     assert float(kcfg['tenRawDisparity'].max()) == pytest.approx(kcfg.baseline, rel=1e-6)
+
+
+def test_depth_adjustment_kernel_matches_reference_formulation(built_lib):
+    """csb_depth_adjust_instances == the reference's torch code (kenburns_effect.py:39-91) run on the GPU, bit for bit, with overlapping,
+    empty and full-frame masks."""
+    from cartoonsegmentation_b200.animeinsseg import AnimeInstances
+    from cartoonsegmentation_b200.anime_3dkenburns import kenburns_effect as kb
+    from cartoonsegmentation_b200.utils.synthetic import ellipse_masks
+    H, W = 200, 260
+    disp = torch.from_numpy(smooth_disparity(H, W, seed=3)).cuda()
+    masks = torch.from_numpy(ellipse_masks(H, W, k=9, seed=4)).cuda()
+    masks[3] = False                         # empty instance -> skipped
+    masks[5] = True                          # full-frame instance
+    masks[7, H - 1, :] = True                # touches the last row
+    inst = AnimeInstances(masks, torch.zeros(9, 4, dtype=torch.int32, device='cuda'), torch.ones(9, device='cuda'))
+    img = torch.zeros(1, 3, H, W, device='cuda')
+    a = kb.depth_adjustment_animesseg(inst, disp, img)                       # csb_depth_adjust_batch (one cooperative launch)
+    b = kb.depth_adjustment_animesseg_torch(inst, disp.clone(), img)
+    assert torch.equal(a, b)
+    from cartoonsegmentation_b200._lib import check, lib, ptr, stream
+    c = disp.clone().contiguous()
+    state = torch.empty(4, device='cuda', dtype=torch.int32)                 # csb_depth_adjust_instances (per-instance launches)
+    check(lib().csb_depth_adjust_instances(ptr(c), ptr(masks.contiguous().view(torch.uint8)), 9, H, W, ptr(state), stream()))
+    assert torch.equal(c, b)
+    # batch of 3 images with different instance counts (0, 9, 4)
+    d3 = disp[0].repeat(3, 1, 1).contiguous()
+    m3 = masks[None].repeat(3, 1, 1, 1).contiguous()
+    kb.depth_adjust_batch(d3, m3, torch.tensor([0, 9, 4], device='cuda', dtype=torch.int32))
+    assert torch.equal(d3[0], disp[0, 0]) and torch.equal(d3[1], b[0, 0])
+    b4 = kb.depth_adjustment_animesseg_torch(AnimeInstances(masks[:4], torch.zeros(4, 4, dtype=torch.int32, device='cuda'), torch.ones(4, device='cuda')), disp.clone(), img)
+    assert torch.equal(d3[2], b4[0, 0])
+    assert torch.equal(kb.depth_adjustment_animesseg(AnimeInstances(), disp, img), disp)
+
+
+def test_inpaint_net_vs_reference_golden(built_lib):
+    """Inpaint.forward (tcgen05 engine + context render kernels) against the UNMODIFIED reference module run on the CPU with the same seeded
+    weights (tests/golden/make_inpaint_golden.py)."""
+    import os
+    from cartoonsegmentation_b200.anime_3dkenburns.models import pointcloud_inpainting as P
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "inpaint_ref_96x128.npz"))
+    H, W = g['disparity'].shape[-2:]
+    net = P.Inpaint(P.synthetic_state_dict(0))
+    img = torch.from_numpy(np.ascontiguousarray(g['image'].transpose(2, 0, 1)[None].astype(np.float32) * (1.0 / 255.0))).cuda()
+    o = net.forward(img, torch.from_numpy(g['disparity']).cuda(), g['shift'], {'fltFocal': 512.0, 'fltBaseline': 40.0, 'intWidth': W, 'intHeight': H})
+    ex = o['tenExisting'].cpu().numpy()
+    assert (ex != g['tenExisting']).mean() < 2e-3                                   # coverage + median-5: discrete, order-noise only at the z-test margin
+    for k in ('tenImage', 'tenDisparity'):
+        a, b = o[k].cpu().numpy(), g[k]
+        rel = np.sqrt(((a - b) ** 2).mean()) / np.sqrt((b ** 2).mean())
+        print(f"{k}: relative RMS error {rel:.5f}, max abs {np.abs(a - b).max():.4f}")
+        assert a.shape == b.shape and rel < 2e-2
