@@ -247,6 +247,9 @@ def main():
         else:
             batch = imgs_dev[idx] if 'seg' in stages or 'depth' in stages else None
         masks = nums = nums_dev = None
+        depth_handle = None
+        if 'depth' in stages:                                        # LeReS forward + D2H of its logits enqueued FIRST, so that the reference's
+            depth_handle = pipe.leres_enqueue(None, imgs_dev=batch)  # host-side tail (below) overlaps with the detector running on the GPU
         if 'seg' in stages:                                          # AnimeInsSeg.infer body: detector forward + post-process (A1-A9)
             masks, nums_dev = [], []
             for s0 in range(0, B, seg_sub):
@@ -254,11 +257,12 @@ def main():
                 cls, reg, ker, mf = seg.model.net.forward(sub)
                 o = rtmdet_postprocess(cls, reg, ker, mf, (H, W), test_cfg)
                 masks.append(o['masks']); nums_dev.append(o['num'])
+        disp = None
+        if depth_handle is not None:                                 # the reference's host-side quantisation tail (B5) while the GPU runs the detector
+            disp = pipe.leres_finish(depth_handle)
+        if 'seg' in stages:
             nums = torch.cat(nums_dev).cpu().tolist()                # the one host read of the seg stage (instance counts for the caller)
             stats["instances"] += sum(nums)
-        disp = None
-        if 'depth' in stages:                                        # LeReS forward + the reference's host-side quantisation tail (B5-B6)
-            disp = pipe._depth_est_leres_batch([imgs_np[i] for i in idx], imgs_dev=batch)
         raws = torch.stack([(disp[b] if disp is not None else disp_dev[i]).reshape(H, W) for b, i in enumerate(idx)])       # [B,H,W] (a copy)
         if masks is not None:                                        # instance-guided depth flattening (C2): one cooperative launch per sub-batch
             for j, s0 in enumerate(range(0, B, seg_sub)):

@@ -225,7 +225,7 @@ def depth_adjustment_animesseg(instances: AnimeInstances, tenDisparity, tenImage
 def depth_adjust_batch(disparity, masks, num):
     """csb_depth_adjust_batch: disparity [N,H,W] fp32 (in place), masks [N,Kmax,H,W] bool, num [N] int32 on the device -- one cooperative launch."""
     N, Kmax, H, W = masks.shape
-    state = torch.empty(3 * N * Kmax + N, device=disparity.device, dtype=torch.int32)
+    state = torch.empty(5 * N * Kmax + N, device=disparity.device, dtype=torch.int32)
     check(lib().csb_depth_adjust_batch(ptr(disparity), ptr(masks.view(torch.uint8)), ptr(num), N, Kmax, H, W, ptr(state), stream()), "csb_depth_adjust_batch")
     return disparity
 
@@ -314,10 +314,14 @@ class KenBurnsPipeline:
         return self._depth_est_leres_batch([img])[0]
 
     def _depth_est_leres_batch(self, imgs, imgs_dev=None):
-        """LeReS for a list of same-size BGR uint8 images -> list of disparity tensors [1,1,H,W] on the device.  The network runs as one
-        batch; the reference's host-side tail (16->8 bit quantisation, OpenCV resize) runs on a thread pool (OpenCV releases the GIL)."""
-        from concurrent.futures import ThreadPoolExecutor
-        ori_h, ori_w = imgs[0].shape[:2]
+        """LeReS for a list of same-size BGR uint8 images -> list of disparity tensors [1,1,H,W] on the device."""
+        return self.leres_finish(self.leres_enqueue(imgs, imgs_dev))
+
+    def leres_enqueue(self, imgs, imgs_dev=None):
+        """Phase 1 (asynchronous): scaledown_maxsize + network forward + D2H of the logits into pinned memory, all enqueued on the current
+        stream.  Returns a handle; the caller may enqueue other GPU work (e.g. the detector) before calling leres_finish, so that the
+        reference's host-side tail overlaps with it."""
+        ori_h, ori_w = (imgs[0].shape[:2] if imgs is not None else imgs_dev.shape[1:3])
         if imgs_dev is not None:            # device-resident inputs: scaledown_maxsize's cv2.resize(INTER_LINEAR) on the device, bit-exact
             small_hw = scaledown_maxsize(np.empty((ori_h, ori_w, 1), np.uint8), self.cfg.depth_est_size, 32).shape[:2]
             if small_hw != (ori_h, ori_w):
@@ -328,18 +332,35 @@ class KenBurnsPipeline:
                 small = imgs_dev
         else:
             small = torch.from_numpy(np.stack([scaledown_maxsize(im, self.cfg.depth_est_size, 32) for im in imgs])).to(self.device)
-        logits = self.leres.forward(small).cpu().numpy()                      # [N,h,w] fp32, one D2H for the batch
+        logits = self.leres.forward(small)                                     # [N,h,w] fp32
+        key = tuple(logits.shape)
+        if getattr(self, '_leres_pin', None) is None or tuple(self._leres_pin.shape) != key:
+            self._leres_pin = torch.empty(key, dtype=torch.float32).pin_memory()
+        self._leres_pin.copy_(logits, non_blocking=True)                       # one D2H for the batch
+        ev = torch.cuda.Event()
+        ev.record()
+        return (ev, (ori_h, ori_w), logits.shape[0])
+
+    def leres_finish(self, handle):
+        """Phase 2: wait for the logits, run the reference's host-side tail (16->8 bit quantisation, OpenCV resize; a thread pool -- OpenCV and
+        numpy release the GIL), upload the disparities."""
+        from concurrent.futures import ThreadPoolExecutor
+        ev, (ori_h, ori_w), n = handle
+        ev.synchronize()
+        logits = self._leres_pin.numpy()
         if getattr(self, '_pool', None) is None:
             import os
             self._pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
-        depth = list(self._pool.map(lambda d: self._leres_post(d, (ori_h, ori_w)), logits))
-        out = torch.from_numpy(np.stack(depth)).to(self.device)[:, None]      # [N,1,H,W]
-        res = []
-        for i in range(out.shape[0]):
-            d = out[i:i + 1]
-            d[d == 0] = d[d > 0].min()                                         # :577
-            res.append(d)
-        return res
+        depth = list(self._pool.map(lambda d: self._leres_post(d, (ori_h, ori_w)), [logits[i] for i in range(n)]))
+        if getattr(self, '_disp_pin', None) is None or tuple(self._disp_pin.shape) != (n, 1, ori_h, ori_w):
+            self._disp_pin = torch.empty((n, 1, ori_h, ori_w), dtype=torch.float32).pin_memory()
+        for i, d in enumerate(depth):
+            self._disp_pin[i, 0] = torch.from_numpy(d)
+        out = self._disp_pin.to(self.device, non_blocking=True)               # [N,1,H,W]
+        # depth[depth == 0] = depth[depth > 0].min()  (:577), per image, without a host sync
+        pos_min = torch.where(out > 0, out, torch.full_like(out, float('inf'))).amin(dim=(1, 2, 3), keepdim=True)
+        out = torch.where(out == 0, pos_min, out)
+        return [out[i:i + 1] for i in range(n)]
 
     def set_inpainting(self, inpainting: str, ckpt=None):
         """reference :427-440.  'default' = the point-cloud Inpaint GridNet on the tcgen05 engine; 'ldm' / 'patchmatch' (stable-diffusion webui,

@@ -99,8 +99,8 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target
 }
 
 __global__ void __launch_bounds__(512) k_adj_batch(float* __restrict__ disp, const uint8_t* __restrict__ masks, const int* __restrict__ num, int Kmax, int H, int W,
-                                                   int G, int* __restrict__ tops, int* __restrict__ bottoms, unsigned* __restrict__ vbits,
-                                                   unsigned* __restrict__ bars) {
+                                                   int G, int* __restrict__ tops, int* __restrict__ bottoms, int* __restrict__ mtops,
+                                                   int* __restrict__ mbottoms, unsigned* __restrict__ vbits, unsigned* __restrict__ bars) {
     const int img = blockIdx.x / G, g = blockIdx.x % G;
     const int K = min(num[img], Kmax);
     float* D = disp + (size_t) img * H * W;
@@ -110,22 +110,25 @@ __global__ void __launch_bounds__(512) k_adj_batch(float* __restrict__ disp, con
     for (int k = 0; k < K; ++k) {
         const uint8_t* M = masks + ((size_t) img * Kmax + k) * H * W;
         const int slot = img * Kmax + k;
-        // phase A: rows with plane > 0
+        // phase A: rows with plane > 0 (top/bottom of the reference) and rows touched by the mask at all (extent of phase C).  The only full
+        // pass over the 1 B/px mask; phases B and C are confined to the instance's rows.
         for (int y = g * nwarp + warp; y < H; y += G * nwarp) {
-            bool pos = false;
+            bool pos = false, any = false;
             for (int x = lane; x < W; x += 32)
-                if (M[(size_t) y * W + x]) pos |= D[(size_t) y * W + x] > 0.f;
+                if (M[(size_t) y * W + x]) { any = true; pos |= D[(size_t) y * W + x] > 0.f; }
             pos = __any_sync(0xffffffffu, pos);
+            any = __any_sync(0xffffffffu, any);
             if (lane == 0 && pos) { atomicMin(tops + slot, y); atomicMax(bottoms + slot, y); }
+            if (lane == 0 && any) { atomicMin(mtops + slot, y); atomicMax(mbottoms + slot, y); }
         }
         target += G;
         group_barrier(bar, target);
         const int top = ((volatile int*) tops)[slot], bottom = ((volatile int*) bottoms)[slot];
         if (bottom < 0) continue;                                   // plane.sum() == 0: skipped by every CTA of the image alike
         const int cut = py_round_to_int((double) top + (0.97 * (double) (bottom - top)));
-        // phase B: max of plane over rows >= cut
+        // phase B: max of plane over rows >= cut (rows below `bottom` hold plane <= 0 and cannot raise a maximum that starts at 0)
         float m = 0.f;
-        const long long n = (long long) (H - cut) * W;
+        const long long n = (long long) (bottom - cut + 1) * W;
         for (long long i = (long long) g * blockDim.x + threadIdx.x; i < n; i += (long long) G * blockDim.x) {
             const size_t o = (size_t) cut * W + i;
             m = fmaxf(m, M[o] ? D[o] : 0.f);
@@ -136,11 +139,12 @@ __global__ void __launch_bounds__(512) k_adj_batch(float* __restrict__ disp, con
         target += G;
         group_barrier(bar, target);
         const float v = __uint_as_float(((volatile unsigned*) vbits)[slot]);
-        // phase C: flatten
-        const long long hw = (long long) H * W;
+        // phase C: flatten -- ((1 - m) * d) + (m * v); with m == 0 the value is unchanged, so only the mask's rows are visited
+        const int mt = ((volatile int*) mtops)[slot], mb = ((volatile int*) mbottoms)[slot];
+        const long long hw = (long long) (mb - mt + 1) * W, base = (long long) mt * W;
         for (long long i = (long long) g * blockDim.x + threadIdx.x; i < hw; i += (long long) G * blockDim.x) {
-            const float mk = M[i] ? 1.0f : 0.0f;
-            D[i] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, mk), D[i]), __fmul_rn(mk, v));
+            const float mk = M[base + i] ? 1.0f : 0.0f;
+            D[base + i] = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, mk), D[base + i]), __fmul_rn(mk, v));
         }
         target += G;
         group_barrier(bar, target);
@@ -157,15 +161,17 @@ extern "C" int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, co
     CSB_REQUIRE(G >= 1, "at most one image per SM (N <= SM count): split the batch");
     G = G > 16 ? 16 : G;
     const size_t slots = (size_t) N * Kmax;
-    int* tops = state;
-    int* bottoms = state + slots;
-    unsigned* vbits = reinterpret_cast<unsigned*>(state + 2 * slots);
-    unsigned* bars = reinterpret_cast<unsigned*>(state + 3 * slots);
-    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(tops, 0x7f, sizeof(int) * slots, st), "memset"));
-    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(bottoms, 0xff, sizeof(int) * slots, st), "memset"));
+    int* tops = state;                       // [tops | mtops] initialised to 0x7f7f7f7f, [bottoms | mbottoms] to -1, [vbits | bars] to 0
+    int* mtops = state + slots;
+    int* bottoms = state + 2 * slots;
+    int* mbottoms = state + 3 * slots;
+    unsigned* vbits = reinterpret_cast<unsigned*>(state + 4 * slots);
+    unsigned* bars = reinterpret_cast<unsigned*>(state + 5 * slots);
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(tops, 0x7f, sizeof(int) * 2 * slots, st), "memset"));
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(bottoms, 0xff, sizeof(int) * 2 * slots, st), "memset"));
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(vbits, 0, sizeof(int) * (slots + N), st), "memset"));
     csb::memset_done(st);
-    void* args[] = {&disparity, &masks, &num, &Kmax, &H, &W, &G, &tops, &bottoms, &vbits, &bars};
+    void* args[] = {&disparity, &masks, &num, &Kmax, &H, &W, &G, &tops, &bottoms, &mtops, &mbottoms, &vbits, &bars};
     // cooperative launch: the runtime verifies that all N*G CTAs are co-resident, which the software barriers rely on
     CSB_TRY(csb::cuda_ok(cudaLaunchCooperativeKernel((void*) k_adj_batch, dim3(N * G), dim3(512), args, 0, st), "cudaLaunchCooperativeKernel(k_adj_batch)"));
     return csb::launched("k_adj_batch", st);

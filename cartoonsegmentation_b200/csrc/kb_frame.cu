@@ -80,6 +80,16 @@ __global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__
     }
 }
 
+// cv2.resize(INTER_LINEAR) with an exact 2x decimation takes OpenCV's INTER_AREA fast path: (a + b + c + d + 2) >> 2 per channel.
+__global__ void __launch_bounds__(256) k_resize_half_u8c3(const uint8_t* __restrict__ src, int W, int Ho, int Wo, uint8_t* __restrict__ dst) {
+    const int total = Ho * Wo * 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % 3, x = (i / 3) % Wo, y = i / (3 * Wo);
+        const uint8_t* p = src + ((size_t) (2 * y) * W + 2 * x) * 3 + c;
+        dst[i] = (uint8_t) ((p[0] + p[3] + p[(size_t) W * 3] + p[(size_t) W * 3 + 3] + 2) >> 2);
+    }
+}
+
 // Fused normalise + depth mask + disocclusion fill + u8 pack for C = 4 (BGR + depth), CP = 8, in two launches.
 // acc pixel = {b*w, g*w, r*w, depth*w, w, 0, 0, 0} (32 B, one sector).
 //
@@ -223,7 +233,10 @@ extern "C" int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw,
 
 extern "C" int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream) {
     CSB_REQUIRE(src && dst && src != dst && H > 0 && W > 0 && Ho > 0 && Wo > 0, "bad arguments");
-    CSB_REQUIRE(!(W == 2 * Wo && H == 2 * Ho), "exact 2x decimation takes OpenCV's INTER_AREA fast path, not implemented");
+    if (W == 2 * Wo && H == 2 * Ho) {
+        k_resize_half_u8c3<<<csb::wave_grid((long long) Ho * Wo * 3, 256, 8), 256, 0, (cudaStream_t) stream>>>(src, W, Ho, Wo, dst);
+        return csb::launched("k_resize_half_u8c3", (cudaStream_t) stream);
+    }
     CropParams p;   // full-frame 'crop' at integer offset 0: getRectSubPix degenerates to a copy, leaving cv2.resize(INTER_LINEAR)
     CSB_REQUIRE(make_crop(Ho, Wo, W, H, (W - 1) * 0.5, (H - 1) * 0.5, p) == CSB_OK, "bad size");
     k_crop_resize<<<csb::wave_grid((long long) Ho * Wo, 256, 8), 256, 0, (cudaStream_t) stream>>>(src, H, W, p, Ho, Wo, dst);

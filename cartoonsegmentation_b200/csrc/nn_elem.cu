@@ -151,43 +151,73 @@ __global__ void __launch_bounds__(256) k_dwconv(const __half* __restrict__ x, in
 }
 
 // LayerNorm over the channels of each pixel (LayerNorm2d / channels-last LN).  4*C bytes per pixel.
+// One warp normalises PIX pixels per iteration: all PIX*NV 16-byte loads are issued before the first reduction (memory-level parallelism --
+// the one-pixel-at-a-time version ran at ~1/7 of HBM speed), lanes own interleaved 8-channel vectors.
+template <int NV, int PIX>
 __global__ void __launch_bounds__(256) k_layernorm(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ g,
                                                    const float* __restrict__ b, float eps, long long npix, int C, __half* __restrict__ y, int ldy, int yoff) {
     const int lane = threadIdx.x & 31;
-    const int nvec = C / 256 + ((C % 256) ? 1 : 0);
-    for (long long pix = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += (long long) gridDim.x * (blockDim.x >> 5)) {
-        const __half* xp = x + pix * ldx + xoff;
-        float v[kMaxVec][8];
-        float s1 = 0.0f;
+    const long long ngroups = (npix + PIX - 1) / PIX;
+    for (long long grp = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < ngroups; grp += (long long) gridDim.x * (blockDim.x >> 5)) {
+        H8 raw[PIX][NV];
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
-            const int c0 = 8 * (lane + 32 * j);
-            if (j < nvec && c0 < C) {
-                unpack8(*reinterpret_cast<const H8*>(xp + c0), v[j]);
+        for (int p = 0; p < PIX; ++p) {
+            const long long pix = grp * PIX + p;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) s1 += v[j][e];
+            for (int j = 0; j < NV; ++j) {
+                const int c0 = 8 * (lane + 32 * j);
+                if (pix < npix && c0 < C) raw[p][j] = *reinterpret_cast<const H8*>(x + pix * ldx + xoff + c0);
             }
         }
-        const float mean = warp_sum(s1) / (float) C;
-        float s2 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j)
-            if (j < nvec && 8 * (lane + 32 * j) < C)
+        for (int p = 0; p < PIX; ++p) {
+            const long long pix = grp * PIX + p;
+            if (pix >= npix) break;
+            float v[NV][8];
+            float s1 = 0.0f;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { float d = v[j][e] - mean; s2 += d * d; }
-        const float rstd = rsqrtf(warp_sum(s2) / (float) C + eps);
-        __half* yp = y + pix * ldy + yoff;
+            for (int j = 0; j < NV; ++j)
+                if (8 * (lane + 32 * j) < C) {
+                    unpack8(raw[p][j], v[j]);
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
-            const int c0 = 8 * (lane + 32 * j);
-            if (j < nvec && c0 < C) {
-                float o[8];
+                    for (int e = 0; e < 8; ++e) s1 += v[j][e];
+                }
+            const float mean = warp_sum(s1) / (float) C;
+            float s2 = 0.0f;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * __ldg(g + c0 + e) + __ldg(b + c0 + e);
-                *reinterpret_cast<H8*>(yp + c0) = pack8(o);
+            for (int j = 0; j < NV; ++j)
+                if (8 * (lane + 32 * j) < C)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { float d = v[j][e] - mean; s2 += d * d; }
+            const float rstd = rsqrtf(warp_sum(s2) / (float) C + eps);
+            __half* yp = y + pix * ldy + yoff;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int c0 = 8 * (lane + 32 * j);
+                if (c0 < C) {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(g + c0 + 4));
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(b + c0 + 4));
+                    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = (v[j][e] - mean) * rstd * gg[e] + bb[e];
+                    *reinterpret_cast<H8*>(yp + c0) = pack8(o);
+                }
             }
         }
     }
+}
+
+static int launch_layernorm(const __half* x, int ldx, int xoff, const float* g, const float* b, float eps, long long npix, int C, __half* y, int ldy, int yoff,
+                            cudaStream_t st) {
+    const int nv = (C + 255) / 256;
+#define CSB_LN(NV_, PIX_) k_layernorm<NV_, PIX_><<<csb::wave_grid((npix + PIX_ - 1) / PIX_ * 32, 256, 8), 256, 0, st>>>(x, ldx, xoff, g, b, eps, npix, C, y, ldy, yoff)
+    if (nv == 1) CSB_LN(1, 8);
+    else if (nv == 2) CSB_LN(2, 4);
+    else if (nv <= 4) CSB_LN(4, 2);
+    else CSB_LN(8, 1);
+#undef CSB_LN
+    return csb::launched("k_layernorm", st);
 }
 
 // Resample NHWC into a channel slice: mode 0 nearest (F.interpolate 'nearest': src = floor(dst * in/out)), 1 bilinear
@@ -362,7 +392,7 @@ extern "C" int csb_resample_f32(const float* x, int N, int Hi, int Wi, int Ho, i
 // ~84 B to ~12 B per output element compared with the one-pixel-per-warp kernel above.  No LayerNorm here (a pixel's channels are spread over
 // several warps): the ConvNeXt block runs this kernel followed by k_layernorm in place.
 template <int K>
-__global__ void __launch_bounds__(256) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
                                                      const float* __restrict__ bias, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy,
                                                      int yoff) {
     constexpr int R = K / 2, TS = 4, IN = TS + K - 1;
@@ -455,15 +485,14 @@ extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w,
     if ((K == 5 || K == 7) && C % 64 == 0 && (ldx | xoff | ldy | yoff) % 2 == 0) {
         // tiled path: depthwise conv (+ bias, + activation when there is no LayerNorm), then LayerNorm in place
         const long long ntasks = (long long) N * ((H + 3) / 4) * ((W + 3) / 4) * (C / 64);
-        const int grid = csb::wave_grid(ntasks * 32, 256, 4);
+        const int grid = csb::wave_grid(ntasks * 32, 256, 2);
         const int a = ln_gamma ? CSB_ACT_NONE : act;
         if (K == 5) k_dwconv_tile<5><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
         else k_dwconv_tile<7><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
         CSB_TRY(csb::launched("k_dwconv_tile", st));
         if (!ln_gamma) return CSB_OK;
         CSB_REQUIRE(act == CSB_ACT_NONE, "LayerNorm followed by an activation is not used on this path");
-        k_layernorm<<<csb::wave_grid((long long) N * H * W * 32, 256, 8), 256, 0, st>>>(yh, ldy, yoff, ln_gamma, ln_beta, eps, (long long) N * H * W, C, yh, ldy, yoff);
-        return csb::launched("k_layernorm", st);
+        return launch_layernorm(yh, ldy, yoff, ln_gamma, ln_beta, eps, (long long) N * H * W, C, yh, ldy, yoff, st);
     }
     if (K == 3) return launch_dwconv<3>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
     if (K == 5) return launch_dwconv<5>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
@@ -474,9 +503,7 @@ extern "C" int csb_layernorm_nhwc(const void* x, int ldx, int xoff, const float*
                                   int ldy, int yoff, void* stream) {
     CSB_REQUIRE(x && gamma && beta && y, "null pointer");
     CSB_REQUIRE(C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && xoff % 8 == 0 && ldy % 8 == 0 && yoff % 8 == 0, "C, strides and offsets must be multiples of 8");
-    k_layernorm<<<csb::wave_grid(npix * 32, 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) x, ldx, xoff, gamma, beta, eps, npix, C, (__half*) y,
-                                                                                     ldy, yoff);
-    return csb::launched("k_layernorm", (cudaStream_t) stream);
+    return launch_layernorm((const __half*) x, ldx, xoff, gamma, beta, eps, npix, C, (__half*) y, ldy, yoff, (cudaStream_t) stream);
 }
 
 extern "C" int csb_resample_nhwc(const void* x, int ldx, int xoff, int N, int Hi, int Wi, int C, int Ho, int Wo, int mode, void* y, int ldy, int yoff,

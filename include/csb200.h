@@ -91,7 +91,7 @@ CSB_API int csb_disocclusion_fill(const float* input, const float* depth, int B,
  * (The reference's `.sum() == 0` skip and row tests are evaluated as "any plane > 0", identical for non-negative disparities.) */
 CSB_API int csb_depth_adjust_instances(float* disparity, const uint8_t* masks, int K, int H, int W, void* state, void* stream);
 /* The same for a batch in ONE cooperative launch: disparity [N,H,W] in place, masks [N,Kmax,H,W], num [N] device int32 (instances per image,
- * e.g. straight from csb_rtmdet_select), state: (3*N*Kmax + N) int32 of device scratch.  N <= number of SMs. */
+ * e.g. straight from csb_rtmdet_select), state: (5*N*Kmax + N) int32 of device scratch.  N <= number of SMs. */
 CSB_API int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, const int* num, int N, int Kmax, int H, int W, int32_t* state, void* stream);
 
 /* process_shift scalar part -- anime_3dkenburns/common.py:60-72, evaluated on the device in double precision from the

@@ -50,6 +50,9 @@ def test_refine_prep_and_post_vs_reference_host_code(built_lib):
     small = torch.empty((h, w, 3), device='cuda', dtype=torch.uint8)
     check(lib().csb_resize_u8c3(ptr(torch.from_numpy(img).cuda()), H, W, ptr(small), h, w, stream()))
     assert np.array_equal(small.cpu().numpy(), img_s)                                        # cv2.resize on uint8: bit exact
+    half = torch.empty((H // 2, W // 2, 3), device='cuda', dtype=torch.uint8)                 # exact 2x decimation: OpenCV's INTER_AREA fast path
+    check(lib().csb_resize_u8c3(ptr(torch.from_numpy(img).cuda()), H, W, ptr(half), H // 2, W // 2, stream()))
+    assert np.array_equal(half.cpu().numpy(), cv2.resize(img, (W // 2, H // 2), interpolation=cv2.INTER_LINEAR))
     x16 = torch.empty((3, S, S, 16), device='cuda', dtype=torch.float16)
     check(lib().csb_refine_prep(ptr(small), h, w, ptr(torch.from_numpy(masks).cuda().view(torch.uint8)), 3, H, W, S, ptr(x16), stream()))
     got = x16.float().cpu().numpy()
