@@ -389,50 +389,58 @@ extern "C" int csb_resample_f32(const float* x, int N, int Hi, int Wi, int Ho, i
 
 // Spatially tiled depthwise KxK: each thread owns 2 channels (one half2) and a 4x4 block of output pixels, a warp owns 64 consecutive channels
 // of one tile (128 B coalesced rows), so every loaded input is reused by up to K*K/((4+K-1)^2/16) outputs from registers: L1 traffic drops from
-// ~84 B to ~12 B per output element compared with the one-pixel-per-warp kernel above.  No LayerNorm here (a pixel's channels are spread over
-// several warps): the ConvNeXt block runs this kernel followed by k_layernorm in place.
+// ~84 B to ~12 B per output element compared with the one-pixel-per-warp kernel above.  A CTA works on ONE 64-channel chunk (blockIdx.y): its
+// K*K x 64 filter taps sit in shared memory (conflict-free LDS.64, no L1 tag traffic) and are reused by every tile the CTA walks; input rows are
+// prefetched one row ahead.  No LayerNorm here (a pixel's channels are spread over several CTAs): the ConvNeXt block runs this kernel followed by
+// k_layernorm in place.
 template <int K>
 __global__ void __launch_bounds__(256, 2) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
-                                                     const float* __restrict__ bias, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy,
-                                                     int yoff) {
+                                                        const float* __restrict__ bias, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy,
+                                                        int yoff) {
     constexpr int R = K / 2, TS = 4, IN = TS + K - 1;
+    __shared__ float2 wsm[K * K * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int chunks = C / 64;
+    const int chunk = blockIdx.y;
+    const int c0 = chunk * 64 + lane * 2;
+    for (int i = threadIdx.x; i < K * K * 32; i += blockDim.x) wsm[i] = __ldg(reinterpret_cast<const float2*>(w + (size_t) (i / 32) * C + chunk * 64 + (i % 32) * 2));
+    __syncthreads();
     const int tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
-    const long long ntasks = (long long) N * tiles_y * tiles_x * chunks;
-    for (long long task = (long long) blockIdx.x * 8 + warp; task < ntasks; task += (long long) gridDim.x * 8) {
-        const int tx = (int) (task % tiles_x);           // consecutive warps -> horizontally adjacent tiles of the same channel chunk (halo reuse in L1)
-        long long t2 = task / tiles_x;
-        const int chunk = (int) (t2 % chunks);
-        t2 /= chunks;
-        const int ty = (int) (t2 % tiles_y);
-        const long long img = t2 / tiles_y;
-        const int c0 = chunk * 64 + lane * 2;
+    const long long ntiles = (long long) N * tiles_y * tiles_x;
+    const float2 b2 = bias ? __ldg(reinterpret_cast<const float2*>(bias + c0)) : make_float2(0.f, 0.f);
+    for (long long task = (long long) blockIdx.x * 8 + warp; task < ntiles; task += (long long) gridDim.x * 8) {
+        const int tx = (int) (task % tiles_x), ty = (int) ((task / tiles_x) % tiles_y);
+        const long long img = task / ((long long) tiles_x * tiles_y);
         const int ox0 = tx * TS, oy0 = ty * TS;
         float2 acc[TS][TS];
-        const float2 b2 = bias ? __ldg(reinterpret_cast<const float2*>(bias + c0)) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < TS; ++i)
 #pragma unroll
             for (int j = 0; j < TS; ++j) acc[i][j] = b2;
         const __half* xb = x + (img * H * W) * ldx + xoff + c0;
-#pragma unroll
-        for (int iy = 0; iy < IN; ++iy) {
+        auto load_row = [&](int iy, __half2 (&row)[IN]) {
             const int gy = oy0 + iy - R;
-            float2 xr[IN];
             const bool rowok = gy >= 0 && gy < H;
 #pragma unroll
             for (int ix = 0; ix < IN; ++ix) {
                 const int gx = ox0 + ix - R;
-                xr[ix] = (rowok && gx >= 0 && gx < W) ? __half22float2(*reinterpret_cast<const __half2*>(xb + ((size_t) gy * W + gx) * ldx)) : make_float2(0.f, 0.f);
+                row[ix] = (rowok && gx >= 0 && gx < W) ? *reinterpret_cast<const __half2*>(xb + ((size_t) gy * W + gx) * ldx) : __floats2half2_rn(0.f, 0.f);
             }
+        };
+        __half2 nxt[IN];
+        load_row(0, nxt);
+#pragma unroll
+        for (int iy = 0; iy < IN; ++iy) {
+            float2 xr[IN];
+#pragma unroll
+            for (int ix = 0; ix < IN; ++ix) xr[ix] = __half22float2(nxt[ix]);
+            if (iy + 1 < IN) load_row(iy + 1, nxt);              // prefetch the next input row while this one is consumed
 #pragma unroll
             for (int r = 0; r < K; ++r) {
                 const int oy = iy - r;
-                if (oy < 0 || oy >= TS) continue;            // resolved at compile time (iy, r are unrolled constants)
+                if (oy < 0 || oy >= TS) continue;                // resolved at compile time (iy, r are unrolled constants)
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const float2 wv = __ldg(reinterpret_cast<const float2*>(w + (size_t) (r * K + k) * C + c0));
+                    const float2 wv = wsm[(r * K + k) * 32 + lane];
 #pragma unroll
                     for (int t = 0; t < TS; ++t) {
                         acc[oy][t].x = fmaf(xr[t + k].x, wv.x, acc[oy][t].x);
@@ -484,8 +492,13 @@ extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w,
     __half* yh = (__half*) y;
     if ((K == 5 || K == 7) && C % 64 == 0 && (ldx | xoff | ldy | yoff) % 2 == 0) {
         // tiled path: depthwise conv (+ bias, + activation when there is no LayerNorm), then LayerNorm in place
-        const long long ntasks = (long long) N * ((H + 3) / 4) * ((W + 3) / 4) * (C / 64);
-        const int grid = csb::wave_grid(ntasks * 32, 256, 2);
+        const long long ntiles = (long long) N * ((H + 3) / 4) * ((W + 3) / 4);
+        const int chunks = C / 64;
+        int gx = (2 * csb::num_sms() + chunks - 1) / chunks;               // ~2 CTAs per SM in total, each walking many tiles of its chunk
+        const long long need = (ntiles + 7) / 8;
+        gx = gx > need ? (int) need : gx;
+        gx = gx < 1 ? 1 : gx;
+        const dim3 grid(gx, chunks);
         const int a = ln_gamma ? CSB_ACT_NONE : act;
         if (K == 5) k_dwconv_tile<5><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
         else k_dwconv_tile<7><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);

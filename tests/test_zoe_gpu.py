@@ -1,0 +1,24 @@
+"""GPU parity of the ZoeDepth metric head against the UNMODIFIED reference head driven by a fake core
+(tests/golden/make_zoe_golden.py).  The BEiT-L DPT encoder (row B3) is not built: the head is fed the golden's feature maps."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_zoe_head_vs_reference_golden(built_lib):
+    from cartoonsegmentation_b200.depth_modules import zoedepth as Z
+    g = np.load(os.path.join(GOLD, "zoe_head_ref_64x96.npz"))
+    nhwc = lambda a: torch.from_numpy(a.astype(np.float16)).permute(0, 2, 3, 1).contiguous().cuda()
+    feats = [nhwc(g[f"feat{i}"]) for i in range(6)]
+    head = Z.ZoeHead(Z.synthetic_state_dict(0))
+    d = head.forward(torch.from_numpy(g['rel']).cuda(), feats[0], feats[1], feats[2:])[0].cpu().numpy()
+    ref = g['metric_depth']
+    rel = np.sqrt(((d - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean())
+    relc = np.sqrt((((d - d.mean()) - (ref - ref.mean())) ** 2).mean()) / ref.std()
+    print(f"ZoeDepth head: relative RMS error {rel:.5f} (centred {relc:.5f}), max abs {np.abs(d - ref).max():.5f}")
+    assert d.shape == ref.shape and rel < 5e-3 and relc < 5e-2
