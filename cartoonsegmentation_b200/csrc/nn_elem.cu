@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -387,79 +388,103 @@ extern "C" int csb_resample_f32(const float* x, int N, int Hi, int Wi, int Ho, i
     return csb::launched("k_resample_f32", (cudaStream_t) stream);
 }
 
-// Spatially tiled depthwise KxK: each thread owns 2 channels (one half2) and a 4x4 block of output pixels, a warp owns 64 consecutive channels
-// of one tile (128 B coalesced rows), so every loaded input is reused by up to K*K/((4+K-1)^2/16) outputs from registers: L1 traffic drops from
-// ~84 B to ~12 B per output element compared with the one-pixel-per-warp kernel above.  A CTA works on ONE 64-channel chunk (blockIdx.y): its
-// K*K x 64 filter taps sit in shared memory (conflict-free LDS.64, no L1 tag traffic) and are reused by every tile the CTA walks; input rows are
-// prefetched one row ahead.  No LayerNorm here (a pixel's channels are spread over several CTAs): the ConvNeXt block runs this kernel followed by
-// k_layernorm in place.
-template <int K>
-__global__ void __launch_bounds__(256, 2) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
+// Spatially tiled depthwise KxK: each thread owns 2 channels (one half2) and a 2 x 8 block of output pixels; a warp owns 64 consecutive channels of
+// one tile (128 B coalesced rows).  A CTA works on ONE 64-channel chunk (blockIdx.y): its K*K x 64 filter taps sit in shared memory (conflict-free
+// LDS.64) and are reused by every tile the CTA walks.  The kernel is L1/shared-bandwidth bound unless operands are reused from registers, so the
+// loop runs over filter ROWS with both output rows' input rows resident (fp32, converted once): each tap is read once per tile and feeds 32 FMAs, the
+// two input rows slide down by one per iteration (one new row is fetched -- prefetched as half2 during the previous iteration's FMAs -- and the other
+// is kept), i.e. per 16 x 2 outputs: (2+K-1) x (8+K-1) half2 loads + K*K LDS.64 for 32*K*K FMAs.  The row loop stays rolled (compact code).
+// No LayerNorm here (a pixel's channels are spread over several CTAs): the ConvNeXt block runs this kernel followed by k_layernorm in place.
+constexpr int kDwThreads = 128;
+template <int K, int ACT>       // ACT: the fused activation, compiled in (CSB_ACT_NONE / CSB_ACT_SILU), or -1 = decided at run time from `act`
+__global__ void __launch_bounds__(kDwThreads, 3) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
                                                         const float* __restrict__ bias, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy,
                                                         int yoff) {
-    constexpr int R = K / 2, TS = 4, IN = TS + K - 1;
+    constexpr int R = K / 2, TSY = 2, TSX = 8, INX = TSX + K - 1;
     __shared__ float2 wsm[K * K * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = blockIdx.y;
     const int c0 = chunk * 64 + lane * 2;
     for (int i = threadIdx.x; i < K * K * 32; i += blockDim.x) wsm[i] = __ldg(reinterpret_cast<const float2*>(w + (size_t) (i / 32) * C + chunk * 64 + (i % 32) * 2));
     __syncthreads();
-    const int tiles_x = (W + TS - 1) / TS, tiles_y = (H + TS - 1) / TS;
+    const int tiles_x = (W + TSX - 1) / TSX, tiles_y = (H + TSY - 1) / TSY;
     const long long ntiles = (long long) N * tiles_y * tiles_x;
     const float2 b2 = bias ? __ldg(reinterpret_cast<const float2*>(bias + c0)) : make_float2(0.f, 0.f);
-    for (long long task = (long long) blockIdx.x * 8 + warp; task < ntiles; task += (long long) gridDim.x * 8) {
+    for (long long task = (long long) blockIdx.x * (kDwThreads / 32) + warp; task < ntiles; task += (long long) gridDim.x * (kDwThreads / 32)) {
         const int tx = (int) (task % tiles_x), ty = (int) ((task / tiles_x) % tiles_y);
         const long long img = task / ((long long) tiles_x * tiles_y);
-        const int ox0 = tx * TS, oy0 = ty * TS;
-        float2 acc[TS][TS];
-#pragma unroll
-        for (int i = 0; i < TS; ++i)
-#pragma unroll
-            for (int j = 0; j < TS; ++j) acc[i][j] = b2;
+        const int ox0 = tx * TSX, oy0 = ty * TSY;
         const __half* xb = x + (img * H * W) * ldx + xoff + c0;
-        auto load_row = [&](int iy, __half2 (&row)[IN]) {
-            const int gy = oy0 + iy - R;
-            const bool rowok = gy >= 0 && gy < H;
+        const bool interior = ox0 - R >= 0 && ox0 + TSX + R <= W && oy0 - R >= 0 && oy0 + TSY + R <= H;       // warp-uniform
+        unsigned colmask = 0;
 #pragma unroll
-            for (int ix = 0; ix < IN; ++ix) {
-                const int gx = ox0 + ix - R;
-                row[ix] = (rowok && gx >= 0 && gx < W) ? *reinterpret_cast<const __half2*>(xb + ((size_t) gy * W + gx) * ldx) : __floats2half2_rn(0.f, 0.f);
+        for (int ix = 0; ix < INX; ++ix) colmask |= ((ox0 + ix - R) >= 0 && (ox0 + ix - R) < W) ? (1u << ix) : 0u;
+        auto load_row = [&](int iy, __half2 (&row)[INX]) {              // input row iy (0 .. TSY+K-2) of the tile's halo window
+            const int gy = oy0 + iy - R;
+            const __half* xrow = xb + ((long long) gy * W + (ox0 - R)) * ldx;
+            if (interior) {
+#pragma unroll
+                for (int ix = 0; ix < INX; ++ix) row[ix] = *reinterpret_cast<const __half2*>(xrow + (size_t) ix * ldx);
+            } else {
+                const unsigned m = (gy >= 0 && gy < H) ? colmask : 0u;
+#pragma unroll
+                for (int ix = 0; ix < INX; ++ix)
+                    row[ix] = ((m >> ix) & 1u) ? *reinterpret_cast<const __half2*>(xrow + (long long) ix * ldx) : __floats2half2_rn(0.f, 0.f);
             }
         };
-        __half2 nxt[IN];
+        float2 acc0[TSX], acc1[TSX], xa[INX], xc[INX];                  // xa / xc: input rows feeding output rows 0 / 1 at the current filter row
+        __half2 nxt[INX];
+#pragma unroll
+        for (int j = 0; j < TSX; ++j) acc0[j] = acc1[j] = b2;
         load_row(0, nxt);
 #pragma unroll
-        for (int iy = 0; iy < IN; ++iy) {
-            float2 xr[IN];
+        for (int ix = 0; ix < INX; ++ix) xa[ix] = __half22float2(nxt[ix]);
+        load_row(1, nxt);
 #pragma unroll
-            for (int ix = 0; ix < IN; ++ix) xr[ix] = __half22float2(nxt[ix]);
-            if (iy + 1 < IN) load_row(iy + 1, nxt);              // prefetch the next input row while this one is consumed
+        for (int ix = 0; ix < INX; ++ix) xc[ix] = __half22float2(nxt[ix]);
+        load_row(2, nxt);
+        // filter row r: output row 0 reads input row r (held in `top`), output row 1 reads input row r+1 (`bot`)
+        auto taps = [&](int r, const float2 (&top)[INX], const float2 (&bot)[INX]) {
 #pragma unroll
-            for (int r = 0; r < K; ++r) {
-                const int oy = iy - r;
-                if (oy < 0 || oy >= TS) continue;                // resolved at compile time (iy, r are unrolled constants)
+            for (int k = 0; k < K; ++k) {
+                const float2 wv = wsm[(r * K + k) * 32 + lane];
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float2 wv = wsm[(r * K + k) * 32 + lane];
-#pragma unroll
-                    for (int t = 0; t < TS; ++t) {
-                        acc[oy][t].x = fmaf(xr[t + k].x, wv.x, acc[oy][t].x);
-                        acc[oy][t].y = fmaf(xr[t + k].y, wv.y, acc[oy][t].y);
-                    }
+                for (int t = 0; t < TSX; ++t) {
+                    acc0[t].x = fmaf(top[t + k].x, wv.x, acc0[t].x);
+                    acc0[t].y = fmaf(top[t + k].y, wv.y, acc0[t].y);
+                    acc1[t].x = fmaf(bot[t + k].x, wv.x, acc1[t].x);
+                    acc1[t].y = fmaf(bot[t + k].y, wv.y, acc1[t].y);
                 }
             }
+        };
+        // the two-row window slides down one row per filter row; unrolled by two so the buffers swap roles instead of being copied
+#pragma unroll 1
+        for (int r = 0; r + 1 < K; r += 2) {
+            taps(r, xa, xc);
+#pragma unroll
+            for (int ix = 0; ix < INX; ++ix) xa[ix] = __half22float2(nxt[ix]);          // input row r+2
+            load_row(r + 3, nxt);                                                       // r+3 <= K always holds here
+            taps(r + 1, xc, xa);
+#pragma unroll
+            for (int ix = 0; ix < INX; ++ix) xc[ix] = __half22float2(nxt[ix]);          // input row r+3
+            if (r + 4 <= K) load_row(r + 4, nxt);
         }
-        __half* yb = y + (img * H * W) * ldy + yoff + c0;
+        taps(K - 1, xa, xc);                                                            // K is odd: rows K-1 / K sit in xa / xc
+        if (ACT != CSB_ACT_NONE) {
+            const int a = ACT < 0 ? act : ACT;
 #pragma unroll
-        for (int i = 0; i < TS; ++i) {
-            const int gy = oy0 + i;
-            if (gy >= H) break;
-#pragma unroll
-            for (int j = 0; j < TS; ++j) {
-                const int gx = ox0 + j;
-                if (gx >= W) break;
-                *reinterpret_cast<__half2*>(yb + ((size_t) gy * W + gx) * ldy) = __floats2half2_rn(act_f(acc[i][j].x, act), act_f(acc[i][j].y, act));
+            for (int j = 0; j < TSX; ++j) {
+                acc0[j].x = act_f(acc0[j].x, a), acc0[j].y = act_f(acc0[j].y, a);
+                acc1[j].x = act_f(acc1[j].x, a), acc1[j].y = act_f(acc1[j].y, a);
             }
+        }
+        __half* yb = y + ((img * H + oy0) * W + ox0) * ldy + yoff + c0;
+        const bool row1 = oy0 + 1 < H;
+#pragma unroll
+        for (int j = 0; j < TSX; ++j) {
+            if (ox0 + j >= W) break;
+            *reinterpret_cast<__half2*>(yb + (size_t) j * ldy) = __floats2half2_rn(acc0[j].x, acc0[j].y);
+            if (row1) *reinterpret_cast<__half2*>(yb + ((size_t) W + j) * ldy) = __floats2half2_rn(acc1[j].x, acc1[j].y);
         }
     }
 }
@@ -492,16 +517,19 @@ extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w,
     __half* yh = (__half*) y;
     if ((K == 5 || K == 7) && C % 64 == 0 && (ldx | xoff | ldy | yoff) % 2 == 0) {
         // tiled path: depthwise conv (+ bias, + activation when there is no LayerNorm), then LayerNorm in place
-        const long long ntiles = (long long) N * ((H + 3) / 4) * ((W + 3) / 4);
+        static const int ctas = [] { const char* e = getenv("CSB_DW_CTAS"); return e ? atoi(e) : 3; }();        // CTAs per SM (tuning knob)
+        const long long ntiles = (long long) N * ((H + 1) / 2) * ((W + 7) / 8);
         const int chunks = C / 64;
-        int gx = (2 * csb::num_sms() + chunks - 1) / chunks;               // ~2 CTAs per SM in total, each walking many tiles of its chunk
-        const long long need = (ntiles + 7) / 8;
+        int gx = ctas * csb::num_sms() / chunks;                           // at most ONE wave of resident CTAs (floor), each walking many tiles of its chunk
+        const long long need = (ntiles + kDwThreads / 32 - 1) / (kDwThreads / 32);
         gx = gx > need ? (int) need : gx;
         gx = gx < 1 ? 1 : gx;
         const dim3 grid(gx, chunks);
         const int a = ln_gamma ? CSB_ACT_NONE : act;
-        if (K == 5) k_dwconv_tile<5><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
-        else k_dwconv_tile<7><<<grid, 256, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
+#define CSB_DW_LAUNCH(KK, AA) k_dwconv_tile<KK, AA><<<grid, kDwThreads, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff)
+        if (K == 5) { if (a == CSB_ACT_NONE) CSB_DW_LAUNCH(5, CSB_ACT_NONE); else if (a == CSB_ACT_SILU) CSB_DW_LAUNCH(5, CSB_ACT_SILU); else CSB_DW_LAUNCH(5, -1); }
+        else { if (a == CSB_ACT_NONE) CSB_DW_LAUNCH(7, CSB_ACT_NONE); else if (a == CSB_ACT_SILU) CSB_DW_LAUNCH(7, CSB_ACT_SILU); else CSB_DW_LAUNCH(7, -1); }
+#undef CSB_DW_LAUNCH
         CSB_TRY(csb::launched("k_dwconv_tile", st));
         if (!ln_gamma) return CSB_OK;
         CSB_REQUIRE(act == CSB_ACT_NONE, "LayerNorm followed by an activation is not used on this path");
