@@ -1,5 +1,7 @@
 // Library-wide state of libcsb200.so: version, thread-local error text, launch counter, per-kernel profiler.
+#include <cstdlib>
 #include <map>
+#include <set>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -16,7 +18,13 @@ std::mutex g_mu;
 std::vector<cudaEvent_t> g_pool;
 std::vector<std::pair<const char*, cudaEvent_t>> g_marks;
 size_t g_next = 0;
+std::set<std::string> g_labels;
 }  // namespace
+
+const char* profile_intern(const char* text) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_labels.insert(text).first->c_str();
+}
 
 void profile_mark(const char* what, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -42,7 +50,8 @@ extern "C" int csb_profile_begin(void* stream) {
         csb::g_next = 0;
     }
     csb::profile_mark("begin", (cudaStream_t) stream);
-    csb::g_profiling.store(1);
+    const char* detail = getenv("CSB_PROFILE_DETAIL");
+    csb::g_profiling.store(detail && detail[0] == '1' ? 2 : 1);
     return CSB_OK;
 }
 

@@ -21,7 +21,8 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
 // Per-kernel profiling (csb_profile_begin/end): when on, a CUDA event is recorded on the launching stream after every
 // launch; consecutive events bracket each kernel (kernels of one stream run back to back).
 void profile_mark(const char* what, cudaStream_t st);
-extern std::atomic<int> g_profiling;
+extern std::atomic<int> g_profiling;   // 0 off, 1 per kernel name, 2 detailed (conv launches keyed by layer shape; CSB_PROFILE_DETAIL=1)
+const char* profile_intern(const char* text);   // stable copy of a transient label
 
 // Call after every kernel launch: counts it and converts a launch error into a status.
 inline int launched(const char* what, cudaStream_t st) {

@@ -395,6 +395,14 @@ extern "C" int csb_resample_f32(const float* x, int N, int Hi, int Wi, int Ho, i
 // two input rows slide down by one per iteration (one new row is fetched -- prefetched as half2 during the previous iteration's FMAs -- and the other
 // is kept), i.e. per 16 x 2 outputs: (2+K-1) x (8+K-1) half2 loads + K*K LDS.64 for 32*K*K FMAs.  The row loop stays rolled (compact code).
 // No LayerNorm here (a pixel's channels are spread over several CTAs): the ConvNeXt block runs this kernel followed by k_layernorm in place.
+// sm_100 packed fp32 FMA: d.xy = a.xy * b.xy + c.xy in one issue slot.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 constexpr int kDwThreads = 128;
 template <int K, int ACT>       // ACT: the fused activation, compiled in (CSB_ACT_NONE / CSB_ACT_SILU), or -1 = decided at run time from `act`
 __global__ void __launch_bounds__(kDwThreads, 3) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
@@ -449,11 +457,9 @@ __global__ void __launch_bounds__(kDwThreads, 3) k_dwconv_tile(const __half* __r
             for (int k = 0; k < K; ++k) {
                 const float2 wv = wsm[(r * K + k) * 32 + lane];
 #pragma unroll
-                for (int t = 0; t < TSX; ++t) {
-                    acc0[t].x = fmaf(top[t + k].x, wv.x, acc0[t].x);
-                    acc0[t].y = fmaf(top[t + k].y, wv.y, acc0[t].y);
-                    acc1[t].x = fmaf(bot[t + k].x, wv.x, acc1[t].x);
-                    acc1[t].y = fmaf(bot[t + k].y, wv.y, acc1[t].y);
+                for (int t = 0; t < TSX; ++t) {                       // the channel pair is one packed FFMA2
+                    acc0[t] = ffma2(top[t + k], wv, acc0[t]);
+                    acc1[t] = ffma2(bot[t + k], wv, acc1[t]);
                 }
             }
         };
