@@ -83,6 +83,8 @@ def kenburns_frame(tenPoints, tenData, intWidth, intHeight, fltFocal, fltBaselin
         scratch = FrameScratch(H, W, pts.device)
     if out is None:
         out = torch.empty((H, W, 3), device=pts.device, dtype=torch.uint8)
+    elif out is False:                      # stop after `scratch.packed` (the bokeh stage crops later)
+        out = None
     depth = torch.empty((H, W), device=pts.device, dtype=torch.float32) if want_depth else None
     sh, sh_dev = split_shift(shift)
     check(lib().csb_kenburns_frame(ptr(pts), ptr(dat), N, H, W, C.c_double(fltFocal), C.c_double(fltBaseline),
@@ -101,6 +103,7 @@ from dataclasses import dataclass, field, fields
 from typing import Any, Optional, Union
 
 from ..animeinsseg import AnimeInsSeg, AnimeInstances
+from ..utils import effects as fx
 from .common import process_autozoom, shift_scalars
 
 _ALIASES = {'fltFocal': 'focal', 'fltBaseline': 'baseline', 'intWidth': 'int_width', 'intHeight': 'int_height', 'fltDispmin': 'disparity_min',
@@ -421,6 +424,8 @@ class KenBurnsPipeline:
             else:
                 img_tensor = (img_u8.permute(2, 0, 1)[None].float() * (1.0 / 255.0))
                 disparity = depth_adjustment_animesseg(instances, disparity.to(self.device).float(), img_tensor, use_medium=self.cfg.depthest_use_medium)
+            if img.shape[0] <= 256 or img.shape[1] <= 256:            # the reference dies in cv2.minMaxLoc on the empty crop (:937)
+                raise ValueError(f"image {img.shape[1]}x{img.shape[0]}: the depth centre crop [128:-128, 128:-128] is empty (needs > 256 x 256)")
             c = disparity_to_cloud(disparity, cfg.focal, cfg.baseline, image_u8=img_u8)                  # :928-937 fused, one D2H of 8 floats
             cfg['fltDispmin'], cfg['fltDispmax'], cfg['objDepthrange'] = c['dispmin'], c['dispmax'], c['depthrange']
             H, W = img.shape[:2]
@@ -488,8 +493,6 @@ class KenBurnsPipeline:
                 for fltStep in [0.0, 1.0]:
                     sh = np.array(shift_scalars(camera(fltStep), objCommon), np.float32)
                     self.inpaint(1.1 * sh, None, objCommon, verbose)
-            if objCommon.depth_field:
-                raise NotImplementedError("depth-of-field bokeh (SURVEY.md §8f rank 1) is not built yet")
             pts = objCommon['tenInpaPoints']
             N = pts.shape[2]
             data = getattr(objCommon, '_render_data', None)
@@ -501,10 +504,26 @@ class KenBurnsPipeline:
                 self._frame_scratch = FrameScratch(H, W, pts.device)
             out_dev = torch.empty((len(steps), H, W, 3), device=pts.device, dtype=torch.uint8)
             out_host = torch.empty((len(steps), H, W, 3), dtype=torch.uint8).pin_memory()
+            bokeh = None
+            if objCommon.depth_field:                                              # :1042-1067, all on the device (utils/effects.py)
+                ins = objCommon.instances
+                masks = None if ins is None or ins.is_empty else ins.masks
+                bokeh = fx.BokehScratch(H, W, 0 if masks is None else int(masks.shape[0]), pts.device, objCommon.lightness_factor)
             for i, fltStep in enumerate(steps):                                    # the reference frame loop, :1015-1072
                 sh = np.array(shift_scalars(camera(fltStep), objCommon), np.float32)
-                kenburns_frame(pts, data, W, H, objCommon['fltFocal'], objCommon['fltBaseline'], sh, pw, ph, W / 2.0, H / 2.0,
-                               scratch=self._frame_scratch, out=out_dev[i])
+                if bokeh is None:
+                    kenburns_frame(pts, data, W, H, objCommon['fltFocal'], objCommon['fltBaseline'], sh, pw, ph, W / 2.0, H / 2.0,
+                                   scratch=self._frame_scratch, out=out_dev[i])
+                else:
+                    _, depth = kenburns_frame(pts, data, W, H, objCommon['fltFocal'], objCommon['fltBaseline'], sh, pw, ph, W / 2.0, H / 2.0,
+                                              scratch=self._frame_scratch, out=False, want_depth=True)
+                    d8 = fx.colorize_gray_r(depth, bokeh)                          # colorize(depth_rendered, cmap='gray_r')[..., 0]
+                    if i == 0:
+                        fx.focal_plane_range(d8, masks, bokeh)                     # focalplane_start / _end, :1045-1059
+                    blurred = fx.bokeh_blur(self._frame_scratch.packed, d8, 32, objCommon.lightness_factor, objCommon.depth_factor, True,
+                                            scratch=bokeh, focal_int=fx.focal_interp(fltStep, objCommon.dof_speed))
+                    check(lib().csb_frame_crop_resize(ptr(blurred), H, W, int(pw), int(ph), C.c_double(W / 2.0), C.c_double(H / 2.0),
+                                                      ptr(out_dev[i]), stream()), "csb_frame_crop_resize")
                 out_host[i].copy_(out_dev[i], non_blocking=True)                   # D2H overlaps the next frame's render
             torch.cuda.current_stream().synchronize()
             frames = [out_host[i].numpy() for i in range(len(steps))]

@@ -247,7 +247,7 @@ extern "C" int csb_kenburns_frame(const float* points, const float* data, int N,
                                   const float* shift, const float* shift_dev, int pw, int ph, double cx, double cy, int32_t* zkey,
                                   float* zee, float* acc,
                                   uint8_t* packed, uint8_t* out, float* depth_out, void* stream) {
-    CSB_REQUIRE(((points && data) || N == 0) && zkey && zee && acc && packed && out, "null pointer");
+    CSB_REQUIRE(((points && data) || N == 0) && zkey && zee && acc && packed, "null pointer");
     CSB_REQUIRE(N >= 0 && H > 0 && W > 0 && (long long) H * W >= 8, "bad shape");
     CSB_REQUIRE(((uintptr_t) acc & 15) == 0, "acc must be 16-byte aligned");
     CropParams p;
@@ -263,6 +263,7 @@ extern "C" int csb_kenburns_frame(const float* points, const float* data, int N,
     CSB_TRY(csb::launched("k_norm_pack_mark", st));
     k_fill_holes<<<csb::num_sms() * 8, 256, 0, st>>>(acc, mask, zkey, nholes, H, W, packed, depth_out);
     CSB_TRY(csb::launched("k_fill_holes", st));
+    if (!out) return CSB_OK;                       // caller post-processes `packed` (bokeh) and crops with csb_frame_crop_resize
     k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, H, W, out);
     return csb::launched("k_crop_resize", st);
 }

@@ -130,10 +130,31 @@ CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, in
 /* cv2.resize(src, (Wo,Ho), interpolation=INTER_LINEAR) on uint8 HWC images, bit-exact (used for scaledown_maxsize, utils/io_utils.py:254-274). */
 CSB_API int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream);
 
+/* Bokeh depth-of-field of the frame loop -- kenburns_effect.py:1042-1067, utils/effects.py:12-84,143-182,
+ * depth_modules/zoedepth/utils/misc.py:97-150 -- on the device; the reference does all but the three gathers in numpy on the host.
+ *   ws: csb_bokeh_workspace_bytes(H, W, K) bytes of device memory, shared by the three calls of a frame.
+ *   csb_depth_colorize_u8:  depth [H,W] fp32 -> colorize(depth, cmap='gray_r')[..., 0] [H,W] u8: exact np.percentile(2) / (85) (linear
+ *                           method) -> normalise in fp32 -> matplotlib Colormap index rule -> lut256 (the gray_r byte table, host-built);
+ *                           -99 (invalid_val) -> 128.
+ *   csb_focal_plane_range:  depth8 + masks [K,H,W] u8 (0/1) -> start_end[2] (device doubles): focalplane_end = max_k np.median(depth8[mask_k]),
+ *                           focalplane_start = 255 if |255-end| > |end| else 0; K == 0 -> (0, 255)   (kenburns_effect.py:1045-1059)
+ *   csb_bokeh_blur:         frame [H,W,3] u8 + depth8 -> out [H,W,3] u8 = bokeh_blur(frame, depth8, nsamples, lightness, depth_factor,
+ *                           use_cuda=True, focal_plane).  highlight_lut[256] = np.power(arange(256, f32)/255, lightness) (device, host-built);
+ *                           inv_lightness = float32(1/lightness); focal plane = focal_int*range[1] + (1-focal_int)*range[0] when focal_range
+ *                           (device) is given (kenburns_effect.py:1065-1066), else `focal_plane`.  kernel_bokeh's planar-buffer /
+ *                           interleaved-index mix-up (effects.py:36-38 on a np2flatten_tensor buffer) is reproduced. */
+CSB_API size_t csb_bokeh_workspace_bytes(int H, int W, int K);
+CSB_API int csb_depth_colorize_u8(const float* depth, int H, int W, const uint8_t* lut256, uint8_t* out8, void* ws, void* stream);
+CSB_API int csb_focal_plane_range(const uint8_t* depth8, const uint8_t* masks, int K, int H, int W, double* start_end, void* ws, void* stream);
+CSB_API int csb_bokeh_blur(const uint8_t* frame, const uint8_t* depth8, int H, int W, int nsamples, const float* highlight_lut, float inv_lightness,
+                           const double* focal_range, double focal_int, double focal_plane, int depth_factor, uint8_t* out, void* ws,
+                           void* stream);
+
 /* Fused Ken-Burns frame: shift + render (C=4: BGR + depth) + normalise + disocclusion fill + u8 pack, then
  * crop+resize -- the body of the reference's frame loop, kenburns_effect.py:1028-1040,1069-1070, as 6 launches.
  *   points [1,3,N], data [1,4,N]; scratch as csb_pointcloud_render (C=4); packed [H,W,3] u8 scratch;
- *   out [H,W,3] u8;  depth_out [H,W] fp32 or NULL (filled depth plane, needed only by the bokeh stage). */
+ *   out [H,W,3] u8, or NULL to stop after `packed` (the bokeh stage sits between the two);  depth_out [H,W] fp32 or NULL (filled
+ *   depth plane, needed only by the bokeh stage). */
 CSB_API int csb_kenburns_frame(const float* points, const float* data, int N, int H, int W, double focal, double baseline,
                        const float* shift, const float* shift_dev, int pw, int ph, double cx, double cy,
                        int32_t* zkey, float* zee, float* acc, uint8_t* packed, uint8_t* out, float* depth_out, void* stream);

@@ -77,7 +77,13 @@ def _import_reference(rec):
     mu.launch_kernel = rec.launch_kernel
     cm = _load("refkb.common", os.path.join(REF, "anime_3dkenburns", "common.py"))
     cm.launch_kernel = rec.launch_kernel
-    return mu, cm
+    numba = types.ModuleType("numba")                      # utils/effects.py decorates its CPU variant with numba.njit; not needed here
+    numba.jit = numba.njit = lambda f=None, **kw: (f if callable(f) else (lambda g: g))
+    sys.modules.setdefault("numba", numba)
+    cupy.float32 = float
+    ef = _load("utils.effects", os.path.join(REF, "utils", "effects.py"))
+    ef.launch_kernel = rec.launch_kernel
+    return mu, cm, ef
 
 
 LAUNCHER = '''
@@ -88,13 +94,21 @@ extern "C" void launch_{entry}(int n, void** p, void* stream) {{
 '''
 
 
+BOKEH_LAUNCHER = '''
+extern "C" void launch_{entry}(int n, int h, int w, int nsamples, float dx, float dy, void** p, void* stream) {{
+    dim3 grid((n + 512 - 1) / 512, 1, 1), block(512, 1, 1);   // reference launch shape (utils/effects.py:74-76)
+    {entry}<<<grid, block, 0, (cudaStream_t) stream>>>(n, h, w, nsamples, dx, dy, (const float*) p[0], (const float*) p[1], (float*) p[2]);
+}}
+'''
+
+
 def main():
     if not os.path.isdir(REF):
         print("reference not present; keeping prebuilt oracle/_ref", file=sys.stderr)
         return 0
     os.makedirs(GEN, exist_ok=True)
     rec = _Recorder()
-    mu, cm = _import_reference(rec)
+    mu, cm, ef = _import_reference(rec)
     units = []
     for (H, W, N, C) in RENDER_SHAPES:
         rec.records.clear()
@@ -106,6 +120,9 @@ def main():
         cm.fill_disocclusion(torch.zeros(1, C, H, W), torch.zeros(1, 1, H, W))
         for name, src in rec.records:
             units.append((name, f"H{H}_W{W}_C{C}", src))
+    rec.records.clear()
+    ef.bokeh_filter_cupy(torch.zeros(1, 3, 16), torch.zeros(1, 1, 16), 0.0, 1.0, 4, 4, 32)      # utils/effects.py:12-84 (shape-independent source)
+    bokeh_units = [(name, src) for name, src in rec.records]
     nargs = {"kernel_pointrender_updateZee": 3, "kernel_pointrender_updateDegrid": 3,
              "kernel_pointrender_updateOutput": 4, "kernel_discfill_updateOutput": 3}
     objs = []
@@ -116,6 +133,14 @@ def main():
         cu = os.path.join(GEN, entry + ".cu")
         with open(cu, "w") as f:
             f.write("#include <assert.h>\n" + body + LAUNCHER.format(entry=entry, args=args))
+        obj = cu[:-3] + ".o"
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+                               "-Xcompiler", "-fPIC", "-c", cu, "-o", obj])
+        objs.append(obj)
+    for name, src in bokeh_units:                          # kernel_bokeh(n, h, w, nsamples, dx, dy, img, depth, blurred)
+        cu = os.path.join(GEN, name + ".cu")
+        with open(cu, "w") as f:
+            f.write(src + BOKEH_LAUNCHER.format(entry=name))
         obj = cu[:-3] + ".o"
         subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
                                "-Xcompiler", "-fPIC", "-c", cu, "-o", obj])

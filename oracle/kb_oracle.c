@@ -367,3 +367,30 @@ ORC_API void orc_resize_linear_u8c3(const uint8_t* src, int sh, int sw, int dh, 
     }
     free(xo); free(xa);
 }
+
+/* kernel_bokeh -- utils/effects.py:16-72, one directional gather pass of bokeh_filter_cupy (effects.py:12-84).  `img` and `blurred` are
+ * 3*n floats: the reference hands the kernel a channel-PLANAR buffer (np2flatten_tensor, effects.py:87-98) but the kernel addresses it as
+ * (y*w+x)*3+c (effects.py:36-38,58) -- restated as is.  `color += img*w_` is an FFMA in the NVRTC build (-fmad=true default): fmaf here.
+ * int(round(float)) = roundf (half away from zero) then float->int. */
+ORC_API void orc_bokeh_pass(int n, int h, int w, int nsamples, float dx, float dy, const float* img, const float* depth, float* blurred) {
+    const int im_size = h < w ? h : w, sample_offset = nsamples / 2;
+    for (long idx = 0; idx < (long) n * 3; ++idx) {
+        const int smp = (int) (idx / 3), c = (int) (idx % 3);
+        const int y = (smp / w) % h, x = smp % w;
+        const long fxy = (long) y * w + x, fid = fxy * 3 + c;
+        const float d = depth[fxy];
+        const float _dx = dx * d, _dy = dy * d;
+        float weight = 0.f, color = 0.f;
+        for (int s = 0; s < nsamples; ++s) {
+            const int sp = (s - sample_offset) * im_size;
+            const int x_ = x + f2i(roundf(_dx * (float) sp));
+            const int y_ = y + f2i(roundf(_dy * (float) sp));
+            if ((x_ >= w) | (y_ >= h) | (x_ < 0) | (y_ < 0)) continue;
+            const long f2 = (long) y_ * w + x_;
+            const float w_ = depth[f2];
+            weight += w_;
+            color = fmaf(img[f2 * 3 + c], w_, color);
+        }
+        blurred[fid] = (weight != 0.f) ? color / weight : img[fid];
+    }
+}

@@ -52,3 +52,16 @@ def fill_disocclusion(tenInput, tenDepth):
     tenOutput = tenInput.clone()
     _launch(f"kernel_discfill_updateOutput_H{H}_W{W}_C{Cc}", H * W, [tenInput, tenDepth, tenOutput])
     return tenOutput
+
+
+def bokeh_filter(img, depth, dx, dy, im_h, im_w, num_samples=32):
+    """utils/effects.py:12-84 (bokeh_filter_cupy) around the unmodified kernel_bokeh: img [1,3,HW], depth [1,1,HW] fp32 on the GPU."""
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_SO)
+    img, depth = img.contiguous(), depth.contiguous()
+    blurred = img.clone()
+    arr = (C.c_void_p * 3)(img.data_ptr(), depth.data_ptr(), blurred.data_ptr())
+    _lib.launch_kernel_bokeh(C.c_int(im_h * im_w), C.c_int(im_h), C.c_int(im_w), C.c_int(num_samples), C.c_float(dx), C.c_float(dy), arr,
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return blurred

@@ -115,3 +115,69 @@ def test_oracle_matches_reference_kernel_golden(name):
     assert bad.mean() < 5e-3
     filled = orc.fill_disocclusion(g['render'], g['render'][:, 3:4] * (g['existing'] > 0.0))
     assert np.array_equal(filled, g['filled'])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C8 bokeh oracle (oracle/bokeh_oracle.py + orc_bokeh_pass)
+# ---------------------------------------------------------------------------------------------------------------
+def test_bokeh_oracle_percentile_and_lut():
+    from oracle import bokeh_oracle as bo
+    rng = np.random.default_rng(0)
+    for n in (7, 1000, 20481):
+        a = (rng.standard_normal(n) * 7).astype(np.float32)
+        for q in (2, 85):
+            # numpy 2.x interpolates in float32, numpy 1.26 (the reference's pin) in float64: equal to float32 resolution
+            assert bo.percentile_linear(a, q) == pytest.approx(float(np.percentile(a.astype(np.float64), q)), rel=1e-6, abs=1e-6)
+    lut = bo.gray_r_bytes()
+    assert lut[0] == 255 and lut[-1] == 0 and (np.diff(lut.astype(int)) <= 0).all() and np.abs(lut.astype(int) + np.arange(256) - 255).max() <= 1
+    from cartoonsegmentation_b200.utils import effects as fx       # host tables of the product are built by the same expressions
+    assert np.array_equal(fx.gray_r_bytes(), lut)
+    x = np.arange(256).astype(np.float32) / np.float32(255)
+    assert np.array_equal(fx.highlight_table(13), bo.pow_f32(x, 13))
+    assert np.abs(fx.highlight_table(13) - np.power(x, 13)).max() <= np.spacing(np.float32(1.0))          # numpy's own float32 pow: within an ulp
+
+
+def test_bokeh_oracle_pass_matches_python_loops():
+    """orc_bokeh_pass (C) against a direct Python transcription of kernel_bokeh's index arithmetic (utils/effects.py:16-72) on a tiny image."""
+    import math
+    from oracle import bokeh_oracle as bo
+    h, w, ns = 9, 11, 8
+    rng = np.random.default_rng(3)
+    img = rng.random(3 * h * w).astype(np.float32)
+    dep = (rng.random(h * w) * 0.02).astype(np.float32)
+    dx, dy = np.float32(math.cos(-math.pi / 6)), np.float32(math.sin(-math.pi / 6))
+    got = bo.bokeh_pass(img, dep, dx, dy, h, w, ns)
+    exp = np.empty_like(img)
+    rnd = lambda v: int(math.floor(abs(float(v)) + 0.5)) * (1 if v >= 0 else -1)          # roundf: half away from zero
+    for idx in range(3 * h * w):
+        smp, c = idx // 3, idx % 3
+        y, x = (smp // w) % h, smp % w
+        d = dep[y * w + x]
+        _dx, _dy = np.float32(dx * d), np.float32(dy * d)
+        weight, color = np.float32(0), np.float32(0)
+        for s_ in range(ns):
+            sp = (s_ - ns // 2) * min(h, w)
+            x_, y_ = x + rnd(np.float32(_dx * np.float32(sp))), y + rnd(np.float32(_dy * np.float32(sp)))
+            if x_ >= w or y_ >= h or x_ < 0 or y_ < 0:
+                continue
+            w_ = dep[y_ * w + x_]
+            weight = np.float32(weight + w_)
+            color = np.float32(float(img[(y_ * w + x_) * 3 + c]) * float(w_) + float(color))           # fma: one rounding
+        exp[idx] = np.float32(color / weight) if weight != 0 else img[idx]
+    assert np.array_equal(got, exp)
+
+
+def test_bokeh_oracle_chain_runs():
+    from oracle import bokeh_oracle as bo
+    rng = np.random.default_rng(1)
+    d = (rng.random((40, 56)) * 30 + 5).astype(np.float32)
+    d8 = bo.colorize_gray_r(d)
+    assert d8.dtype == np.uint8 and d8.min() == 0 and d8.max() == 255
+    masks = np.zeros((2, 40, 56), bool)
+    masks[0, 5:20, 5:30] = True
+    start, end = bo.focal_plane_range(d8, masks)
+    assert start in (0.0, 255.0) and end == float(np.median(d8[masks[0]]))
+    assert bo.focal_plane_range(d8, None) == (0.0, 255.0)
+    img = rng.integers(0, 256, (40, 56, 3), dtype=np.uint8)
+    out = bo.bokeh_blur(img, d8, 32, 13, 1, bo.focal_plane(0.5, 50.0, start, end))
+    assert out.shape == img.shape and out.dtype == np.uint8
