@@ -130,6 +130,27 @@ CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, in
 /* cv2.resize(src, (Wo,Ho), interpolation=INTER_LINEAR) on uint8 HWC images, bit-exact (used for scaledown_maxsize, utils/io_utils.py:254-274). */
 CSB_API int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream);
 
+/* ZoeDepth / MiDaS DPT-BEiT-L encoder pieces (the encoder is torch.hub `intel-isl/MiDaS` `DPT_BEiT_L_384`, loaded at
+ * depth_modules/zoedepth/models/base_models/midas.py:341 and NOT vendored in the reference: restated from timm's BEiT + MiDaS v3.1's DPT).
+ * Every Linear / Conv runs on csb_conv2d_nhwc; these are the remaining ops (csrc/zoe_attn.cu, csrc/zoe_io.cu).
+ *   csb_attention_bias   out[b,q,h*64+:] = softmax_k(Q.K/sqrt(64)*... + bias[h,q,k]) V; qkv [B,T,3*heads*64] fp16 (q|k|v), bias [heads,Tp,Tp] fp16 with
+ *                        Tp a multiple of 64 and the columns k >= T set to a large negative number; out [B,T,heads*64] fp16.
+ *   csb_tokens_assemble  tokens [B,1+P,C] = cat(cls [C], patches [B,P,C])            (BeitEmbeddings)
+ *   csb_readout_concat   out [B,P,2C] = [tokens[b,1+p] | tokens[b,0]]                (DPT 'project' readout before its Linear + GELU)
+ *   csb_pixel_shuffle_nhwc  x [B,h,w,k*k*C] -> y [B,h*k,w*k,C]: the tail of ConvTranspose2d(kernel=stride=k) computed as a 1x1 conv
+ *   csb_zoe_prep         img [H,W,3] u8 -> patch rows [1|2][Hn/16][Wn/16][768] fp16 (channel (r*16+s)*3+c): /255, reflect pad (pad_h, pad_w), bilinear
+ *                        align_corners=True resize to Hn x Wn, (x-0.5)/0.5; with flip_aug a second, horizontally flipped entry
+ *                        (depth_model.py:57-112, midas.py:164-186)
+ *   csb_zoe_finish       net depth [1|2][Hn][Wn] fp32 -> out [H][W]: bicubic (A=-0.75, align_corners=False) to the padded size, crop, un-flip, mean
+ *   csb_zoe_disparity    depth -> disparity (kenburns_effect.py:812-818); scratch: one uint32 */
+CSB_API int csb_attention_bias(const void* qkv, int B, int T, int heads, int head_dim, const void* bias, int Tp, float scale, void* out, void* stream);
+CSB_API int csb_tokens_assemble(const void* patches, const void* cls, int B, int P, int C, void* tokens, void* stream);
+CSB_API int csb_readout_concat(const void* tokens, int B, int P, int C, void* out, void* stream);
+CSB_API int csb_pixel_shuffle_nhwc(const void* x, int B, int h, int w, int k, int C, void* y, void* stream);
+CSB_API int csb_zoe_prep(const uint8_t* img, int H, int W, int pad_h, int pad_w, int Hn, int Wn, int flip_aug, void* patches, void* stream);
+CSB_API int csb_zoe_finish(const float* depth_net, int flip_aug, int Hn, int Wn, int H, int W, int pad_h, int pad_w, float* out, void* stream);
+CSB_API int csb_zoe_disparity(const float* depth, long long n, double focal, double baseline, float* disparity, unsigned* scratch, void* stream);
+
 /* Bokeh depth-of-field of the frame loop -- kenburns_effect.py:1042-1067, utils/effects.py:12-84,143-182,
  * depth_modules/zoedepth/utils/misc.py:97-150 -- on the device; the reference does all but the three gathers in numpy on the host.
  *   ws: csb_bokeh_workspace_bytes(H, W, K) bytes of device memory, shared by the three calls of a frame.

@@ -1,0 +1,110 @@
+"""ZoeDepth rows B1-B3 on the B200: the attention kernel vs a torch fp32 reference, the DPT-BEiT-L encoder vs goldens from transformers' independent
+port of the same network (tests/golden/make_zoe_dpt_golden.py; the hub code the reference loads is not vendored), and the inference wrapper
+(reflect pad + align-corners resize + flip twin; bicubic back-resize + crop + un-flip + mean; depth -> disparity) vs the torch calls the reference
+makes (depth_model.py:57-129, midas.py:164-186, kenburns_effect.py:812-818)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean() / ((b ** 2).mean() + 1e-30)))
+
+
+@pytest.mark.parametrize("B,T", [(2, 577), (1, 321), (3, 64), (1, 65)])
+def test_attention_vs_torch(built_lib, B, T):
+    import ctypes as C
+    from cartoonsegmentation_b200._lib import check, lib, ptr, stream
+    heads, d = 16, 64
+    g = torch.Generator(device='cuda').manual_seed(T)
+    qkv = (torch.randn(B, T, 3 * heads * d, generator=g, device='cuda') * 1.5).half()
+    Tp = (T + 63) // 64 * 64
+    bias = torch.full((heads, Tp, Tp), -60000.0, device='cuda', dtype=torch.float16)
+    bias[:, :T, :T] = (torch.randn(heads, T, T, generator=g, device='cuda') * 2).half()
+    out = torch.empty(B, T, heads * d, device='cuda', dtype=torch.float16)
+    check(lib().csb_attention_bias(ptr(qkv), B, T, heads, d, ptr(bias), Tp, C.c_float(d ** -0.5), ptr(out), stream()), "csb_attention_bias")
+    q, k, v = qkv.float().view(B, T, 3, heads, d).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-2, -1) * d ** -0.5 + bias[:, :T, :T].float()[None]).softmax(-1) @ v).transpose(1, 2).reshape(B, T, heads * d)
+    assert torch.isfinite(out).all()
+    assert _rr(out.float().cpu(), ref.cpu()) < 2e-3          # fp16 probabilities / output rounding
+
+
+@pytest.fixture(scope="module")
+def hf_weights():
+    sys.path.insert(0, GOLD)
+    import make_zoe_dpt_golden as mk
+    return mk, mk.hf_to_midas(mk.build_hf_model().state_dict())
+
+
+@pytest.mark.parametrize("Hn,Wn", [(384, 384), (256, 320)])
+def test_dpt_beit_vs_transformers_golden(built_lib, hf_weights, Hn, Wn):
+    from cartoonsegmentation_b200.depth_modules.zoedepth import BeitDPT
+    mk, sd = hf_weights
+    net = BeitDPT(sd, 'cuda')
+    x = mk.net_input(Hn, Wn)                                                              # [1,3,Hn,Wn] fp32, already normalised
+    patches = x[0].permute(1, 2, 0).reshape(Hn // 16, 16, Wn // 16, 16, 3).permute(0, 2, 1, 3, 4).reshape(1, Hn // 16, Wn // 16, 768).half().cuda().contiguous()
+    rel, outconv, btl, blocks = net.forward(patches)
+    g = np.load(os.path.join(GOLD, f"zoe_dpt_ref_{Hn}x{Wn}.npz"))
+    errs = dict(rel=_rr(rel[0].cpu(), g['rel']), outconv=_rr(outconv[0, ::4, ::4].float().cpu(), g['outconv'].astype(np.float32)),
+                btl=_rr(btl[0].float().cpu(), g['btl'].astype(np.float32)))
+    for k, t in enumerate(blocks):
+        st = max(1, t.shape[1] // 24)
+        errs[f"fused{k}"] = _rr(t[0, ::st, ::st].float().cpu(), g[f"fused{k}"].astype(np.float32))
+    print("DPT-BEiT-L rel RMS vs transformers fp32:", {k: round(v, 5) for k, v in errs.items()})
+    assert max(errs.values()) < 1e-2, errs                                                  # fp16 storage through 24 blocks + decoder
+
+
+def test_wrapper_prep_and_finish_vs_torch(built_lib):
+    import ctypes as C
+    from cartoonsegmentation_b200._lib import check, lib, ptr, stream
+    from cartoonsegmentation_b200.depth_modules.zoedepth import midas_net_size
+    from cartoonsegmentation_b200.utils.synthetic import smooth_image
+    for (H, W) in ((300, 420), (512, 512)):
+        img = torch.from_numpy(smooth_image(H, W, seed=3)).cuda()
+        ph, pw = int(np.sqrt(H / 2) * 3), int(np.sqrt(W / 2) * 3)
+        Hn, Wn = midas_net_size(H + 2 * ph, W + 2 * pw)
+        patches = torch.empty((2, Hn // 16, Wn // 16, 768), device='cuda', dtype=torch.float16)
+        check(lib().csb_zoe_prep(ptr(img), H, W, ph, pw, Hn, Wn, 1, ptr(patches), stream()), "csb_zoe_prep")
+        x = (img.float() / 255).permute(2, 0, 1)[None]                                       # what the reference feeds: [1,3,H,W] in [0,1]
+        for f, xin in enumerate((x, torch.flip(x, dims=[3]))):
+            xp = F.pad(xin, [pw, pw, ph, ph], mode='reflect')
+            xr = (F.interpolate(xp, (Hn, Wn), mode='bilinear', align_corners=True) - 0.5) / 0.5
+            got = patches[f].float().view(Hn // 16, Wn // 16, 16, 16, 3).permute(4, 0, 2, 1, 3).reshape(3, Hn, Wn)
+            assert (got - xr[0]).abs().max() < 2e-3                                          # fp16 storage of values in [-1, 1]
+        d = torch.rand(2, Hn, Wn, device='cuda') * 5 + 0.5
+        out = torch.empty((H, W), device='cuda')
+        check(lib().csb_zoe_finish(ptr(d), 1, Hn, Wn, H, W, ph, pw, ptr(out), stream()), "csb_zoe_finish")
+        up = F.interpolate(d[:, None], size=(H + 2 * ph, W + 2 * pw), mode='bicubic', align_corners=False)[:, 0, ph:ph + H, pw:pw + W]
+        ref = (up[0] + torch.flip(up[1], dims=[1])) / 2
+        assert (out - ref).abs().max() < 2e-5 * float(ref.abs().max())
+    depth = torch.rand(64, 80, device='cuda') * 3
+    depth[3, 4] = 0.0
+    depth[5, 6] = float('nan')
+    disp = torch.empty_like(depth)
+    scr = torch.zeros(1, device='cuda', dtype=torch.int32)
+    check(lib().csb_zoe_disparity(ptr(depth), C.c_longlong(depth.numel()), C.c_double(512.0), C.c_double(40.0), ptr(disp), ptr(scr), stream()), "csb_zoe_disparity")
+    dd = depth.clone()
+    dd[dd == 0] = dd[dd > 0].min()
+    ref = ((512.0 * 40.0) / (dd + 0.00001)).nan_to_num_(0, 0, 0)
+    assert torch.allclose(disp, ref, rtol=1e-6, atol=0)
+
+
+def test_zoedepth_infer_end_to_end(built_lib):
+    from cartoonsegmentation_b200.depth_modules.zoedepth import ZoeDepth
+    from cartoonsegmentation_b200.utils.synthetic import smooth_image
+    net = ZoeDepth(None, 'cuda')
+    img = torch.from_numpy(smooth_image(480, 640, seed=11)).cuda()
+    depth = net.infer(img)
+    assert depth.shape == (480, 640) and torch.isfinite(depth).all() and float(depth.min()) > 0
+    d2 = net.infer(torch.flip(img, dims=[1]))                                                # flip augmentation makes the estimator flip-equivariant
+    assert _rr(torch.flip(d2, dims=[1]).cpu(), depth.cpu()) < 5e-3
+    disp = net.disparity(depth, 512.0, 40.0)
+    assert torch.isfinite(disp).all() and float(disp.max()) > 0
