@@ -287,8 +287,9 @@ class KenBurnsPipeline:
             self.animeinsseg = AnimeInsSeg(ck, default_det_size=self.cfg.det_size, device=self.device, refine_kwargs={'refine_method': 'none'})
 
     def set_depth_estimation(self, depth_est: str, ckpt=None):
-        """reference :529-560.  'leres' is built (ResNeXt-101 32x8d + decoder on the tcgen05 engine); 'zoe' (BEiT-L DPT encoder), 'marigold'
-        and 'default' are not -- they raise at use time unless `depth_model` is set by the caller ('external')."""
+        """reference :529-560.  'leres' (ResNeXt-101 32x8d + decoder) and 'zoe' (DPT-BEiT-L + metric bins head, flip + pad augmentation) run on
+        the tcgen05 engine; 'marigold' (a diffusion model, SURVEY.md §2 out of scope) and 'default' raise at use time unless `depth_model` is
+        set by the caller ('external')."""
         self.cfg.depth_est = depth_est
         if depth_est not in ('zoe', 'leres', 'marigold', 'default', 'external'):
             raise NotImplementedError(depth_est)
@@ -302,6 +303,22 @@ class KenBurnsPipeline:
                     sd = {('depth_model.' + k if not k.startswith('depth_model.') else k): v for k, v in sd.items()}
                 self.leres = LeReS(sd, self.device)
             self.depth_model = lambda img, img_tensor: self._depth_est_leres(img_tensor, img)
+        elif depth_est == 'zoe':
+            from ..depth_modules.zoedepth import ZoeDepth
+            if getattr(self, 'depth_zoe', None) is None:
+                sd = None
+                if ckpt is not None:                                         # ZoeD_M12_N.pt: {'model': state_dict} (model_io.py:49-58)
+                    obj = torch.load(ckpt, map_location='cpu')
+                    sd = obj.get('model', obj)
+                self.depth_zoe = ZoeDepth(sd, self.device)
+            self.depth_model = lambda img, img_tensor: self._depth_est_zoe(img_tensor, img)
+
+    def _depth_est_zoe(self, img_tensor, img, *args, **kwargs):
+        """reference :812-818: `depth_zoe.infer(img_tensor, with_flip_aug=True, pad_input=True)` -> disparity [1,1,H,W].  `img` is the BGR uint8
+        frame whose /255 the reference passes as `img_tensor` (without the RGB reorder ZoeDepth expects -- kept)."""
+        u8 = img if torch.is_tensor(img) else torch.from_numpy(np.ascontiguousarray(img)).to(self.device)
+        depth = self.depth_zoe.infer(u8, pad_input=True, with_flip_aug=True)
+        return self.depth_zoe.disparity(depth, self.cfg.focal, self.cfg.baseline)[None, None]
 
     # ---- reference :563-581
     def _leres_post(self, depth_logits: np.ndarray, ori_hw):

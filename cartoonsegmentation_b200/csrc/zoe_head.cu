@@ -49,33 +49,52 @@ __global__ void __launch_bounds__(256) k_attractor(const float* __restrict__ A, 
     }
 }
 
+// One thread writes 8 consecutive output channels (one 16 B store; a warp covers consecutive channel groups of the same pixels, so the corner
+// reads of the 128-channel embedding are contiguous across lanes even though the +33 channel offset leaves them unaligned).
 __global__ void __launch_bounds__(256) k_zoe_cond_input(const __half* __restrict__ feat, const float* __restrict__ rel, int hr, int wr,
                                                         const __half* __restrict__ emb, int he, int we, int N, int H, int W, __half* __restrict__ out) {
-    const long long total = (long long) N * H * W;
-    for (long long pix = blockIdx.x * (long long) blockDim.x + threadIdx.x; pix < total; pix += (long long) gridDim.x * blockDim.x) {
+    const long long total = (long long) N * H * W * 22;
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int g = (int) (i % 22);
+        const long long pix = i / 22;
+        uint4* o4 = reinterpret_cast<uint4*>(out + pix * 176) + g;
+        if (g < 4) {                                                          // outconv_activation, copied
+            *o4 = reinterpret_cast<const uint4*>(feat + pix * 32)[g];
+            continue;
+        }
         const int x = (int) (pix % W), y = (int) ((pix / W) % H);
         const long long n = pix / ((long long) W * H);
-        __half* o = out + pix * 176;
-        const uint4* f = reinterpret_cast<const uint4*>(feat + pix * 32);
-        uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o4[j] = f[j];
         int y0, y1, x0, x1;
         float ly, lx;
-        ac_coord(y, hr, H, y0, y1, ly);
-        ac_coord(x, wr, W, x0, x1, lx);
-        const float* R = rel + n * hr * wr;
-        o[32] = __float2half_rn((1.f - ly) * ((1.f - lx) * R[(size_t) y0 * wr + x0] + lx * R[(size_t) y0 * wr + x1]) +
-                                ly * ((1.f - lx) * R[(size_t) y1 * wr + x0] + lx * R[(size_t) y1 * wr + x1]));
         ac_coord(y, he, H, y0, y1, ly);
         ac_coord(x, we, W, x0, x1, lx);
         const __half* E = emb + n * he * we * 128;
-        for (int c = 0; c < 128; ++c) {
-            const float v = (1.f - ly) * ((1.f - lx) * __half2float(E[((size_t) y0 * we + x0) * 128 + c]) + lx * __half2float(E[((size_t) y0 * we + x1) * 128 + c])) +
-                            ly * ((1.f - lx) * __half2float(E[((size_t) y1 * we + x0) * 128 + c]) + lx * __half2float(E[((size_t) y1 * we + x1) * 128 + c]));
-            o[33 + c] = __float2half_rn(v);
+        const __half* e00 = E + ((size_t) y0 * we + x0) * 128;
+        const __half* e01 = E + ((size_t) y0 * we + x1) * 128;
+        const __half* e10 = E + ((size_t) y1 * we + x0) * 128;
+        const __half* e11 = E + ((size_t) y1 * we + x1) * 128;
+        __align__(16) __half v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            float val = 0.f;                                                  // channels 161..175: zero padding
+            if (c == 32) {                                                    // interpolate(rel_depth), align_corners=True
+                int ry0, ry1, rx0, rx1;
+                float rly, rlx;
+                ac_coord(y, hr, H, ry0, ry1, rly);
+                ac_coord(x, wr, W, rx0, rx1, rlx);
+                const float* R = rel + n * hr * wr;
+                val = (1.f - rly) * ((1.f - rlx) * R[(size_t) ry0 * wr + rx0] + rlx * R[(size_t) ry0 * wr + rx1]) +
+                      rly * ((1.f - rlx) * R[(size_t) ry1 * wr + rx0] + rlx * R[(size_t) ry1 * wr + rx1]);
+            } else if (c < 161) {
+                const int ce = c - 33;
+                // same association as the per-pixel form: (1-ly)*((1-lx)*a + lx*b) + ly*((1-lx)*c + lx*d)
+                val = (1.f - ly) * ((1.f - lx) * __half2float(e00[ce]) + lx * __half2float(e01[ce])) +
+                      ly * ((1.f - lx) * __half2float(e10[ce]) + lx * __half2float(e11[ce]));
+            }
+            v[j] = __float2half_rn(val);
         }
-        for (int c = 161; c < 176; ++c) o[c] = __float2half_rn(0.f);
+        *o4 = *reinterpret_cast<const uint4*>(v);
     }
 }
 
@@ -133,7 +152,7 @@ extern "C" int csb_zoe_attractor(const float* A, int na, const float* b_prev, in
 extern "C" int csb_zoe_cond_input(const void* feat32, const float* rel, int hr, int wr, const void* emb128, int he, int we, int N, int H, int W, void* out176,
                                   void* stream) {
     CSB_REQUIRE(feat32 && rel && emb128 && out176 && N > 0 && H > 0 && W > 0, "bad arguments");
-    k_zoe_cond_input<<<csb::wave_grid((long long) N * H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) feat32, rel, hr, wr, (const __half*) emb128, he, we,
+    k_zoe_cond_input<<<csb::wave_grid((long long) N * H * W * 22, 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) feat32, rel, hr, wr, (const __half*) emb128, he, we,
                                                                                                        N, H, W, (__half*) out176);
     return csb::launched("k_zoe_cond_input", (cudaStream_t) stream);
 }

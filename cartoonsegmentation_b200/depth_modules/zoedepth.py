@@ -370,6 +370,25 @@ class ZoeDepth:
         check(lib().csb_zoe_finish(ptr(metric), int(with_flip_aug), Hn, Wn, H, W, ph, pw, ptr(out), stream()), "csb_zoe_finish")
         return out
 
+    def infer_batch(self, imgs_u8, pad_input=True, with_flip_aug=True):
+        """Same as `infer` for a stack [B,H,W,3] of equally sized images: one encoder / head pass over all 2B net inputs -> [B,H,W] fp32.
+        (The reference is strictly batch 1; results per image are identical to `infer`.)"""
+        Bn, H, W = imgs_u8.shape[:3]
+        ph = int(np.sqrt(H / 2) * 3) if pad_input else 0
+        pw = int(np.sqrt(W / 2) * 3) if pad_input else 0
+        Hn, Wn = midas_net_size(H + 2 * ph, W + 2 * pw)
+        nb = 2 if with_flip_aug else 1
+        imgs_u8 = imgs_u8.contiguous()
+        patches = torch.empty((Bn * nb, Hn // 16, Wn // 16, 768), device=self.dev, dtype=torch.float16)
+        for i in range(Bn):
+            check(lib().csb_zoe_prep(ptr(imgs_u8[i]), H, W, ph, pw, Hn, Wn, int(with_flip_aug), ptr(patches[i * nb:]), stream()), "csb_zoe_prep")
+        rel, outconv, btl, blocks = self.core.forward(patches)
+        metric = self.head.forward(rel, outconv, btl, blocks)
+        out = torch.empty((Bn, H, W), device=self.dev, dtype=torch.float32)
+        for i in range(Bn):
+            check(lib().csb_zoe_finish(ptr(metric[i * nb:]), int(with_flip_aug), Hn, Wn, H, W, ph, pw, ptr(out[i]), stream()), "csb_zoe_finish")
+        return out
+
     def disparity(self, depth, focal, baseline):
         """`_depth_est_zoe` tail (kenburns_effect.py:815-817)"""
         out = torch.empty_like(depth)

@@ -108,3 +108,18 @@ def test_zoedepth_infer_end_to_end(built_lib):
     assert _rr(torch.flip(d2, dims=[1]).cpu(), depth.cpu()) < 5e-3
     disp = net.disparity(depth, 512.0, 40.0)
     assert torch.isfinite(disp).all() and float(disp.max()) > 0
+
+
+def test_pipeline_depth_est_zoe(built_lib):
+    """KenBurnsPipeline(depth_est='zoe') -- the reference's default estimator (kenburns_effect.py:218) -- end to end on the device."""
+    from cartoonsegmentation_b200.animeinsseg import AnimeInstances
+    from cartoonsegmentation_b200.anime_3dkenburns.kenburns_effect import KenBurnsConfig, KenBurnsPipeline
+    from cartoonsegmentation_b200.utils.synthetic import smooth_image
+    pipe = KenBurnsPipeline(KenBurnsConfig(det_size=320, max_size=320, num_frame=3, depth_est='zoe'))
+    img = smooth_image(288, 320, seed=21)
+    kcfg = pipe.generate_kenburns_config(img, instances=AnimeInstances())
+    disp = kcfg['tenRawDisparity']
+    assert disp.shape == (1, 1, 288, 320) and torch.isfinite(disp).all()
+    assert float(disp.max()) == pytest.approx(kcfg.baseline, rel=1e-6)                         # :928 normalisation
+    frames = pipe.autozoom(kcfg, inpaint=False)
+    assert len(frames) == 3 and frames[0].shape == (288, 320, 3)
