@@ -18,6 +18,7 @@ import math
 import torch
 
 from .. import engine as E
+from .._lib import check, lib, ptr, stream
 
 MEAN_BGR, STD_BGR = (103.53, 116.28, 123.675), (57.375, 57.12, 58.395)      # rtmdet base cfg, SURVEY Appendix A.1
 DEPTHS, DIMS = (3, 3, 27, 3), (128, 256, 512, 1024)
@@ -43,9 +44,34 @@ def _csplayer(specs, name, cin, cout, n):
         _convmodule(specs, f"{name}.blocks.{b}.conv2.pointwise_conv", mid, mid, 1)
 
 
-def param_specs():
-    """[(name, shape, kind)] of the ConvNeXt-B RTMDet-Ins detector, mmdet parameter names."""
+CSPNEXT_L = dict(stem=(32, 32, 64), stages=((64, 128, 3, True, False), (128, 256, 6, True, False), (256, 512, 6, True, False), (512, 1024, 3, False, True)))
+
+
+def _cspnext_specs(s):
+    """mmdet `CSPNeXt(arch='P5', deepen_factor=1, widen_factor=1, expand_ratio=.5, channel_attention=True)` -- the backbone of the shipped
+    rtmdetl_e60.ckpt: stem + stage1..4 = [conv 3x3 s2, (SPPBottleneck), CSPLayer + ChannelAttention]."""
+    c0, c1, c2 = CSPNEXT_L['stem']
+    _convmodule(s, "backbone.stem.0", 3, c0, 3)
+    _convmodule(s, "backbone.stem.1", c0, c1, 3)
+    _convmodule(s, "backbone.stem.2", c1, c2, 3)
+    for i, (cin, cout, n, _identity, spp) in enumerate(CSPNEXT_L['stages'], 1):
+        _convmodule(s, f"backbone.stage{i}.0", cin, cout, 3)
+        j = 1
+        if spp:
+            _convmodule(s, f"backbone.stage{i}.1.conv1", cout, cout // 2, 1)
+            _convmodule(s, f"backbone.stage{i}.1.conv2", cout * 2, cout, 1)
+            j = 2
+        _csplayer(s, f"backbone.stage{i}.{j}", cout, cout, n)
+        s += [(f"backbone.stage{i}.{j}.attention.fc.weight", (cout, cout, 1, 1), 'conv_lin'), (f"backbone.stage{i}.{j}.attention.fc.bias", (cout,), 'bias')]
+
+
+def param_specs(backbone='convnext_b'):
+    """[(name, shape, kind)] of the RTMDet-Ins detector (ConvNeXt-B or CSPNeXt-L backbone), mmdet parameter names."""
     s = []
+    if backbone == 'cspnext_l':
+        _cspnext_specs(s)
+        return s + _neck_head_specs()
+    assert backbone == 'convnext_b', backbone
     s += [("backbone.downsample_layers.0.0.weight", (DIMS[0], 3, 4, 4), 'conv_lin'), ("backbone.downsample_layers.0.0.bias", (DIMS[0],), 'bias'),
           ("backbone.downsample_layers.0.1.weight", (DIMS[0],), 'ln_w'), ("backbone.downsample_layers.0.1.bias", (DIMS[0],), 'ln_b')]
     for i in range(1, 4):
@@ -62,6 +88,11 @@ def param_specs():
                   (f"{p}.gamma", (d,), 'gamma')]
     for i in (1, 2, 3):
         s += [(f"backbone.norm{i}.weight", (DIMS[i],), 'ln_w'), (f"backbone.norm{i}.bias", (DIMS[i],), 'ln_b')]
+    return s + _neck_head_specs()
+
+
+def _neck_head_specs():
+    s = []
     c = DIMS[1:]
     _convmodule(s, "neck.reduce_layers.0", c[2], c[1], 1)
     _convmodule(s, "neck.reduce_layers.1", c[1], c[0], 1)
@@ -88,7 +119,7 @@ def param_specs():
     return s
 
 
-def synthetic_state_dict(seed=0, cls_bias=-5.0):
+def synthetic_state_dict(seed=0, cls_bias=-5.0, backbone='convnext_b'):
     """Seeded variance-preserving weights: conv std sqrt(2/fan_in) before SiLU/GELU/ReLU, 1/sqrt(fan_in) before linear
     outputs, biases U(-0.1,0.1), BN gamma U(0.8,1.2) beta U(-0.1,0.1) mean N(0,0.1) var U(0.8,1.2), LN gamma U(0.8,1.2), layer-scale 1.0.
     (The reference's 'random init' is PyTorch's default because init_weights() is never called, animeinsseg/__init__.py:204-209; that
@@ -98,7 +129,7 @@ def synthetic_state_dict(seed=0, cls_bias=-5.0):
 
     def u(shape, lo, hi):
         return torch.rand(shape, generator=g) * (hi - lo) + lo
-    for name, shape, kind in param_specs():
+    for name, shape, kind in param_specs(backbone):
         gain = 1.0
         if ':' in kind:                       # 'conv_lin:25' -> output gain, so that scores / mask logits are well spread (not clustered at 0)
             kind, gain = kind.split(':')[0], float(kind.split(':')[1])
@@ -150,12 +181,18 @@ class _Conv:
 
 
 class _CSP:
-    def __init__(self, sd, name, dev, eps):
+    """mmdet CSPLayer (CSPNeXtBlocks): add_identity=False / no attention in the neck, add_identity per stage + ChannelAttention in the backbone."""
+
+    def __init__(self, sd, name, dev, eps, add_identity=False):
         wm, bm = _fold_bn(sd, f"{name}.main_conv", eps)
         ws, bs = _fold_bn(sd, f"{name}.short_conv", eps)
         self.mid = wm.shape[0]
+        self.add_identity = add_identity
         self.ms = _Conv(torch.cat([wm, ws], 0), torch.cat([bm, bs], 0), dev, act='silu')          # main + short fused along Cout
         self.final = _Conv(*_fold_bn(sd, f"{name}.final_conv", eps), dev, act='silu')
+        self.att = None
+        if f"{name}.attention.fc.weight" in sd:                                                    # x * hardsigmoid(fc(GAP(x)))
+            self.att = _Conv(sd[f"{name}.attention.fc.weight"], sd[f"{name}.attention.fc.bias"], dev, act='hardsigmoid')
         self.blocks = []
         b = 0
         while f"{name}.blocks.{b}.conv1.conv.weight" in sd:
@@ -168,11 +205,57 @@ class _CSP:
 
     def __call__(self, x, out=None, out_coff=0):
         y = self.ms(x)                                        # [.., 2*mid] = [main | short]
-        for c1, dw, pw in self.blocks:                        # CSPNeXtBlock (add_identity=False in the neck)
+        for c1, dw, pw in self.blocks:                        # CSPNeXtBlock
             a = E.conv2d_nhwc(y, c1.w, c1.b, pad=1, act='silu', in_coff=0)
             d = E.dwconv_nhwc(a, dw[0], dw[1], act='silu')
-            E.conv2d_nhwc(d, pw.w, pw.b, act='silu', out=y, out_coff=0)      # back into the main half
+            if self.add_identity:                             # out + identity: the block input is the main half itself (read, then overwritten per element)
+                E.conv2d_nhwc(d, pw.w, pw.b, act='silu', out=y, out_coff=0, residual=y, res_mode=2, res_coff=0)
+            else:
+                E.conv2d_nhwc(d, pw.w, pw.b, act='silu', out=y, out_coff=0)      # back into the main half
+        if self.att is not None:
+            N, H, W, Cc = y.shape
+            acc = torch.empty((N, Cc), device=y.device, dtype=torch.float32)
+            pooled = torch.empty((N, 1, 1, Cc), device=y.device, dtype=y.dtype)
+            check(lib().csb_gap_nhwc(ptr(y), Cc, 0, N, H, W, Cc, ptr(acc), ptr(pooled), stream()), "csb_gap_nhwc")
+            gate = self.att(pooled)
+            check(lib().csb_scale_channels_nhwc(ptr(y), Cc, 0, N, H, W, Cc, ptr(gate), stream()), "csb_scale_channels_nhwc")
         return E.conv2d_nhwc(y, self.final.w, self.final.b, act='silu', out=out, out_coff=out_coff)
+
+
+class _CSPNeXt:
+    """CSPNeXt-L backbone on the engine.  __call__(x16 [N,H,W,16], cat_slices {stage index 2|3|4: (buffer, channel offset)})."""
+
+    def __init__(self, sd, dev, eps):
+        cm = lambda n, **kw: _Conv(*_fold_bn(sd, n, eps), dev, act='silu', **kw)
+        w0, b0 = _fold_bn(sd, "backbone.stem.0", eps)
+        self.stem = [_Conv(w0, b0, dev, stride=2, pad=1, act='silu', cin_pad=16), cm("backbone.stem.1", pad=1), cm("backbone.stem.2", pad=1)]
+        self.stages = []
+        for i, (_cin, cout, _n, identity, spp) in enumerate(CSPNEXT_L['stages'], 1):
+            st = dict(down=cm(f"backbone.stage{i}.0", stride=2, pad=1), spp=None)
+            j = 1
+            if spp:
+                st['spp'] = (cm(f"backbone.stage{i}.1.conv1"), cm(f"backbone.stage{i}.1.conv2"), cout // 2)
+                j = 2
+            st['csp'] = _CSP(sd, f"backbone.stage{i}.{j}", dev, eps, add_identity=identity)
+            self.stages.append(st)
+
+    def __call__(self, x16, cat_slices):
+        t, toff = x16, 0
+        for c in self.stem:
+            t = c(t)
+        for i, st in enumerate(self.stages, 1):
+            t = st['down'](t, in_coff=toff)                    # the previous stage may have written into a slice of a concat buffer
+            if st['spp'] is not None:                          # SPPBottleneck: cat(x, pool5, pool9, pool13); pool9 = pool5 o pool5, pool13 = pool5^3 (exact for max)
+                c1, c2, mid = st['spp']
+                N, H, W, _ = t.shape
+                cat = torch.empty((N, H, W, 4 * mid), device=t.device, dtype=t.dtype)
+                c1(t, out=cat, out_coff=0)
+                for k in range(3):
+                    E.maxpool2d_nhwc(cat, 5, 1, 2, False, xoff=k * mid, channels=mid, out=cat, yoff=(k + 1) * mid)
+                t = c2(cat)
+            buf, toff = cat_slices.get(i, (None, 0))
+            t = st['csp'](t, out=buf, out_coff=toff)
+        return t
 
 
 class RTMDetIns:
@@ -182,6 +265,12 @@ class RTMDetIns:
         sd, dev = state_dict, torch.device(device)
         self.dev = dev
         f32 = lambda t: t.float().contiguous().to(dev)
+        self.cspnext = _CSPNeXt(sd, dev, bn_eps) if "backbone.stem.0.conv.weight" in sd else None          # rtmdetl_e60.ckpt layout (Appendix A.3)
+        if self.cspnext is None:
+            self._init_convnext(sd, dev, f32)
+        self._init_neck_head(sd, dev, bn_eps)
+
+    def _init_convnext(self, sd, dev, f32):
         # ---- backbone (Appendix A.4)
         self.stem = _Conv(sd["backbone.downsample_layers.0.0.weight"], sd["backbone.downsample_layers.0.0.bias"], dev, stride=4, cin_pad=16)
         self.stem_ln = (f32(sd["backbone.downsample_layers.0.1.weight"]), f32(sd["backbone.downsample_layers.0.1.bias"]))
@@ -202,6 +291,8 @@ class RTMDetIns:
                                fc2=_Conv(sd[f"{p}.pointwise_conv2.weight"][:, :, None, None] * gamma.view(-1, 1, 1, 1), sd[f"{p}.pointwise_conv2.bias"] * gamma, dev)))
             self.blocks.append(st)
         self.out_ln = {i: (f32(sd[f"backbone.norm{i}.weight"]), f32(sd[f"backbone.norm{i}.bias"])) for i in (1, 2, 3)}
+
+    def _init_neck_head(self, sd, dev, bn_eps):
         # ---- neck (Appendix A.5)
         cm = lambda n, **kw: _Conv(*_fold_bn(sd, n, bn_eps), dev, act='silu', **kw)
         self.reduce = [cm("neck.reduce_layers.0"), cm("neck.reduce_layers.1")]
@@ -255,7 +346,10 @@ class RTMDetIns:
         catB4 = torch.empty((N, h4, w4, 512), device=dev, dtype=f16)     # [down(o3) | p4]
         catB5 = torch.empty((N, h5, w5, 1024), device=dev, dtype=f16)    # [down(o4) | p5]
         catM = torch.empty((N, h3, w3, 768), device=dev, dtype=f16)      # [P3 | up(P4) | up(P5)]
-        self.backbone(x16, {1: (cat3, 256), 2: (cat4, 512), 3: (c5, 0)})
+        if self.cspnext is not None:
+            self.cspnext(x16, {2: (cat3, 256), 3: (cat4, 512), 4: (c5, 0)})
+        else:
+            self.backbone(x16, {1: (cat3, 256), 2: (cat4, 512), 3: (c5, 0)})
         # ---- neck
         self.reduce[0](c5, out=catB5, out_coff=512)                                           # p5
         E.resample_nhwc(catB5, h4, w4, 'nearest', out=cat4, xoff=512, yoff=0, channels=512)

@@ -370,6 +370,75 @@ extern "C" int csb_maxpool_nhwc(const void* x, int N, int H, int W, int C, void*
     return csb_maxpool2d_nhwc(x, C, 0, N, H, W, C, 3, 2, 1, 0, y, C, 0, stream);
 }
 
+// ---- mmdet ChannelAttention (CSPNeXt CSPLayer): x * hardsigmoid(fc(global_avg_pool(x))) -- GAP and the per-(image, channel) scaling; the fc is a conv launch
+namespace {
+// partial sums: grid (chunks, N); thread t owns channel octets t, t+blockDim, ...; fp32 atomics into acc[N][C]
+__global__ void k_gap_partial(const __half* __restrict__ x, int ldx, int xoff, int HW, int C, float* __restrict__ acc) {
+    const int n = blockIdx.y, c8n = C / 8;
+    const long long per = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long) blockIdx.x * per, p1 = min(p0 + per, (long long) HW);
+    for (int c8 = threadIdx.x; c8 < c8n; c8 += blockDim.x) {
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const __half* base = x + ((long long) n * HW) * ldx + xoff + c8 * 8;
+        for (long long p = p0; p < p1; ++p) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + p * ldx);
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(h[j]);
+                s[2 * j] += f.x;
+                s[2 * j + 1] += f.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&acc[(long long) n * C + c8 * 8 + j], s[j]);
+    }
+}
+__global__ void k_gap_finish(const float* __restrict__ acc, long long n, float inv, __half* __restrict__ out) {
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) out[i] = __float2half_rn(acc[i] * inv);
+}
+__global__ void k_scale_channels(__half* __restrict__ x, int ldx, int xoff, long long HW, int C, long long total8, const __half* __restrict__ s) {
+    const int c8n = C / 8;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long) gridDim.x * blockDim.x) {
+        const int c8 = (int) (i % c8n);
+        const long long pix = i / c8n;
+        const long long n = pix / HW;
+        uint4* px = reinterpret_cast<uint4*>(x + pix * ldx + xoff + c8 * 8);
+        uint4 v = *px;
+        const uint4 w = *reinterpret_cast<const uint4*>(s + n * C + c8 * 8);
+        __half2* a = reinterpret_cast<__half2*>(&v);
+        const __half2* b = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = __half22float2(a[j]), fb = __half22float2(b[j]);
+            a[j] = __floats2half2_rn(fa.x * fb.x, fa.y * fb.y);
+        }
+        *px = v;
+    }
+}
+}  // namespace
+
+extern "C" int csb_gap_nhwc(const void* x, int ldx, int xoff, int N, int H, int W, int C, float* acc, void* y, void* stream) {
+    CSB_REQUIRE(x && acc && y && N > 0 && H > 0 && W > 0 && C % 8 == 0 && (ldx | xoff) % 8 == 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t) stream;
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t) N * C, st), "memset"));
+    csb::memset_done(st);
+    int chunks = (4 * csb::num_sms() + N - 1) / N;
+    chunks = chunks > H * W ? H * W : (chunks < 1 ? 1 : chunks);
+    k_gap_partial<<<dim3(chunks, N), 128, 0, st>>>((const __half*) x, ldx, xoff, H * W, C, acc);
+    CSB_TRY(csb::launched("k_gap_partial", st));
+    k_gap_finish<<<csb::wave_grid((long long) N * C, 256, 1), 256, 0, st>>>(acc, (long long) N * C, 1.0f / (float) (H * W), (__half*) y);
+    return csb::launched("k_gap_finish", st);
+}
+
+extern "C" int csb_scale_channels_nhwc(void* x, int ldx, int xoff, int N, int H, int W, int C, const void* scale, void* stream) {
+    CSB_REQUIRE(x && scale && N > 0 && H > 0 && W > 0 && C % 8 == 0 && (ldx | xoff) % 8 == 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t) stream;
+    const long long total8 = (long long) N * H * W * (C / 8);
+    k_scale_channels<<<csb::wave_grid(total8, 256, 8), 256, 0, st>>>((__half*) x, ldx, xoff, (long long) H * W, C, total8, (const __half*) scale);
+    return csb::launched("k_scale_channels", st);
+}
+
 extern "C" int csb_add_nhwc(const void* a, int lda, int aoff, const void* b, int ldb, int boff, long long npix, int C, void* y, int ldy, int yoff, void* stream) {
     CSB_REQUIRE(a && b && y && C % 8 == 0 && (lda | aoff | ldb | boff | ldy | yoff) % 8 == 0, "bad arguments");
     k_add<<<csb::wave_grid(npix * (C / 8), 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) a, lda, aoff, (const __half*) b, ldb, boff, npix, C, (__half*) y, ldy, yoff);

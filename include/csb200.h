@@ -242,6 +242,10 @@ CSB_API int csb_maxpool_nhwc(const void* x, int N, int H, int W, int C, void* y,
 /*   csb_maxpool2d_nhwc  general MaxPool2d(K, stride, pad, ceil_mode) on channel slices (ISNet's 2x2 ceil-mode pools, isnet.py:130). */
 CSB_API int csb_maxpool2d_nhwc(const void* x, int ldx, int xoff, int N, int H, int W, int C, int K, int stride, int pad, int ceil_mode, void* y, int ldy,
                        int yoff, void* stream);
+/*   csb_gap_nhwc / csb_scale_channels_nhwc  mmdet ChannelAttention of the CSPNeXt CSPLayer: y[n,c] = mean_hw x (fp32
+ *                       accumulation in acc [N,C], fp16 result), and x[n,h,w,c] *= s[n,c] in place; the fc + Hardsigmoid between them is a conv launch. */
+CSB_API int csb_gap_nhwc(const void* x, int ldx, int xoff, int N, int H, int W, int C, float* acc, void* y, void* stream);
+CSB_API int csb_scale_channels_nhwc(void* x, int ldx, int xoff, int N, int H, int W, int C, const void* scale, void* stream);
 CSB_API int csb_add_nhwc(const void* a, int lda, int aoff, const void* b, int ldb, int boff, long long npix, int C, void* y, int ldy, int yoff, void* stream);
 /*   csb_prelu_nhwc      y = PReLU(x), per-channel slopes (pre-activations of the Inpaint GridNet, pointcloud_inpainting.py:10-13). */
 CSB_API int csb_prelu_nhwc(const void* x, int ldx, int xoff, const float* slope, long long npix, int C, void* y, int ldy, int yoff, void* stream);

@@ -77,17 +77,73 @@ class CSPNeXtBlock(nn.Module):
         return out + x if self.add_identity else out
 
 
+class ChannelAttention(nn.Module):
+    """mmdet `ChannelAttention` ‡ (layers/se_layer.py): x * Hardsigmoid(Conv2d(C, C, 1, bias=True)(AdaptiveAvgPool2d(1)(x)))."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.fc = nn.Conv2d(channels, channels, 1, 1, 0, bias=True)
+
+    def forward(self, x):
+        return x * F.hardsigmoid(self.fc(x.mean((2, 3), keepdim=True)))
+
+
 class CSPLayer(nn.Module):
-    def __init__(self, cin, cout, num_blocks, add_identity, expand_ratio=0.5, act='silu'):
+    def __init__(self, cin, cout, num_blocks, add_identity, expand_ratio=0.5, act='silu', channel_attention=False):
         super().__init__()
         mid = int(cout * expand_ratio)
         self.main_conv = ConvModule(cin, mid, 1, act=act)
         self.short_conv = ConvModule(cin, mid, 1, act=act)
         self.final_conv = ConvModule(2 * mid, cout, 1, act=act)
         self.blocks = nn.Sequential(*[CSPNeXtBlock(mid, mid, add_identity, act) for _ in range(num_blocks)])
+        if channel_attention:
+            self.attention = ChannelAttention(2 * mid)
 
     def forward(self, x):
-        return self.final_conv(torch.cat((self.blocks(self.main_conv(x)), self.short_conv(x)), dim=1))
+        x = torch.cat((self.blocks(self.main_conv(x)), self.short_conv(x)), dim=1)
+        if hasattr(self, 'attention'):
+            x = self.attention(x)
+        return self.final_conv(x)
+
+
+class SPPBottleneck(nn.Module):
+    """mmdet `SPPBottleneck` ‡ (backbones/csp_darknet.py): 1x1 (C -> C/2), cat(x, MaxPool 5/9/13, stride 1, pad k//2), 1x1 (2C -> C)."""
+
+    def __init__(self, cin, cout, kernel_sizes=(5, 9, 13), act='silu'):
+        super().__init__()
+        mid = cin // 2
+        self.conv1 = ConvModule(cin, mid, 1, act=act)
+        self.poolings = nn.ModuleList([nn.MaxPool2d(k, 1, k // 2) for k in kernel_sizes])
+        self.conv2 = ConvModule(mid * (len(kernel_sizes) + 1), cout, 1, act=act)
+
+    def forward(self, x):
+        x = self.conv1(x)
+        return self.conv2(torch.cat([x] + [p(x) for p in self.poolings], dim=1))
+
+
+class CSPNeXt(nn.Module):
+    """mmdet `CSPNeXt(arch='P5', deepen_factor=1, widen_factor=1, expand_ratio=.5, channel_attention=True, out_indices=(2,3,4))` ‡
+    -- the backbone of the shipped rtmdetl_e60.ckpt."""
+    ARCH = ((64, 128, 3, True, False), (128, 256, 6, True, False), (256, 512, 6, True, False), (512, 1024, 3, False, True))
+
+    def __init__(self, act='silu'):
+        super().__init__()
+        self.stem = nn.Sequential(ConvModule(3, 32, 3, 2, 1, act=act), ConvModule(32, 32, 3, 1, 1, act=act), ConvModule(32, 64, 3, 1, 1, act=act))
+        for i, (cin, cout, n, identity, spp) in enumerate(self.ARCH, 1):
+            stage = [ConvModule(cin, cout, 3, 2, 1, act=act)]
+            if spp:
+                stage.append(SPPBottleneck(cout, cout, act=act))
+            stage.append(CSPLayer(cout, cout, n, identity, 0.5, act, channel_attention=True))
+            setattr(self, f'stage{i}', nn.Sequential(*stage))
+
+    def forward(self, x):
+        outs = []
+        x = self.stem(x)
+        for i in range(1, 5):
+            x = getattr(self, f'stage{i}')(x)
+            if i >= 2:
+                outs.append(x)
+        return outs
 
 
 # ----------------------------------------------------------------------------------------------- backbone (A.4)
@@ -208,8 +264,8 @@ class RTMDetInsSepBNHead(nn.Module):
 class RTMDetIns(nn.Module):
     def __init__(self, backbone='convnext_b'):
         super().__init__()
-        assert backbone == 'convnext_b'
-        self.backbone = ConvNeXt()
+        assert backbone in ('convnext_b', 'cspnext_l')
+        self.backbone = ConvNeXt() if backbone == 'convnext_b' else CSPNeXt()
         self.neck = CSPNeXtPAFPN()
         self.bbox_head = RTMDetInsSepBNHead()
 

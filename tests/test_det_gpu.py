@@ -155,3 +155,35 @@ def test_animeinsseg_infer_end_to_end(env):
     seg.set_max_instance(5)
     assert seg.model.bbox_head.test_cfg['max_per_img'] == 5
     assert len(seg.infer(img, det_size=size, max_instances=5)) <= 5
+
+
+@pytest.mark.parametrize("size", [256, 320])
+def test_cspnext_l_forward_vs_oracle(built_lib, size):
+    """Row A2's second backbone -- mmdet CSPNeXt-L (stem, SPPBottleneck, CSPLayers with identity + channel attention), the layout of the shipped
+    rtmdetl_e60.ckpt -- through the same neck/head, against the fp32 oracle with the same seeded state_dict."""
+    from cartoonsegmentation_b200.animeinsseg import rtmdet as R
+    sd = R.synthetic_state_dict(0, backbone='cspnext_l')
+    oracle = D.RTMDetIns('cspnext_l').eval()
+    missing, unexpected = oracle.load_state_dict(sd, strict=False)
+    assert not unexpected and all('num_batches_tracked' in k for k in missing)
+    img = smooth_image(size, size + 64, seed=size + 1)
+    net = R.RTMDetIns(sd)
+    assert net.cspnext is not None
+    cls, reg, ker, mf = net.forward(torch.from_numpy(img).cuda())
+    with torch.no_grad():
+        o_cls, o_reg, o_ker, o_mf = oracle(D.preprocess(img))
+    nchw = lambda t: t.permute(0, 3, 1, 2).cpu()
+    errs = {}
+    for l in range(3):
+        errs[f'cls{l}'] = rel_rms(nchw(cls[l]), o_cls[l]); errs[f'reg{l}'] = rel_rms(nchw(reg[l]), o_reg[l]); errs[f'ker{l}'] = rel_rms(nchw(ker[l]), o_ker[l])
+    errs['mask_feat'] = rel_rms(nchw(mf), o_mf)
+    print("CSPNeXt-L: relative RMS error of the fp16 network vs the fp32 oracle:", {k: round(v, 5) for k, v in errs.items()})
+    assert max(errs.values()) < 2e-2, errs
+
+
+def test_cspnext_l_infer_surface(built_lib):
+    """AnimeInsSeg built from a CSPNeXt-L state_dict (what loading rtmdetl_e60.ckpt produces) runs `infer` end to end."""
+    from cartoonsegmentation_b200.animeinsseg import AnimeInsSeg, rtmdet as R
+    seg = AnimeInsSeg(R.synthetic_state_dict(0, backbone='cspnext_l'), default_det_size=320)
+    inst = seg.infer(smooth_image(300, 280, seed=2), output_type='tensor', pred_score_thr=0.0)
+    assert inst.masks is None or inst.masks.shape[1:] == (300, 280)
