@@ -275,6 +275,8 @@ class KenBurnsPipeline:
         self._frame_scratch = None
         self.set_detector(cfg.detector)
         self.set_depth_estimation(cfg.depth_est)
+        if self.cfg.default_depth_refine:                                     # reference :421-422
+            self.set_depth_refinement(cfg.depth_refinement)
         self.set_inpainting(cfg.inpaint_type)
 
     # ---- component selection (reference :427-560)
@@ -393,8 +395,19 @@ class KenBurnsPipeline:
             sd = torch.load(ckpt, map_location='cpu') if ckpt is not None else None
             self.kenburns_inpaintnet = Inpaint(sd, self.device)
 
-    def set_depth_refinement(self, depth_refinement: str):
-        raise NotImplementedError("Refine disparity net (SURVEY.md §8f rank 2) is not built yet")
+    def set_depth_refinement(self, depth_refinement: str, ckpt=None):
+        """reference :820-826: only 'default' (the `Refine` net, `models/disparity_refinement.py`) exists upstream."""
+        if depth_refinement != 'default':
+            raise NotImplementedError(f'Invalid depth refinement: {depth_refinement}')
+        if getattr(self, 'depth_refinenet', None) is None:
+            from .models.disparity_refinement import Refine
+            sd = torch.load(ckpt, map_location='cpu') if ckpt is not None else None
+            self.depth_refinenet = Refine(sd, self.device)
+        self._refine_depth = lambda img, disparity: self.depth_refinenet.forward(img, disparity)
+
+    def refine_depth(self, img: torch.Tensor, disparity: torch.Tensor):
+        """reference :828-829"""
+        return self._refine_depth(img, disparity)
 
     def set_config(self, cfg: KenBurnsConfig):
         self.cfg = cfg
@@ -420,7 +433,9 @@ class KenBurnsPipeline:
                                       "to a callable or pass disparity= to generate_kenburns_config")
         disparity = self.depth_model(img, img_tensor)
         disparity = depth_adjustment_animesseg(instances, disparity, img_tensor, use_medium=self.cfg.depthest_use_medium)      # :604
-        return disparity
+        if self.cfg.default_depth_refine:                                                                                       # :619-620
+            disparity = self.refine_depth(img_tensor, disparity)
+        return disparity                   # refine_crf (:621-622) is out of scope
 
     # ---- reference :898-951
     def generate_kenburns_config(self, img: np.ndarray, instances: Optional[AnimeInstances] = None, verbose: bool = False, savep=None, disparity=None):
