@@ -228,7 +228,8 @@ def depth_adjustment_animesseg(instances: AnimeInstances, tenDisparity, tenImage
 def depth_adjust_batch(disparity, masks, num):
     """csb_depth_adjust_batch: disparity [N,H,W] fp32 (in place), masks [N,Kmax,H,W] bool, num [N] int32 on the device -- one cooperative launch."""
     N, Kmax, H, W = masks.shape
-    state = torch.empty(5 * N * Kmax + N, device=disparity.device, dtype=torch.int32)
+    lib().csb_depth_adjust_state_words.restype = C.c_longlong
+    state = torch.empty(int(lib().csb_depth_adjust_state_words(N, Kmax, H, W)), device=disparity.device, dtype=torch.int32)
     check(lib().csb_depth_adjust_batch(ptr(disparity), ptr(masks.view(torch.uint8)), ptr(num), N, Kmax, H, W, ptr(state), stream()), "csb_depth_adjust_batch")
     return disparity
 
@@ -355,19 +356,32 @@ class KenBurnsPipeline:
         else:
             small = torch.from_numpy(np.stack([scaledown_maxsize(im, self.cfg.depth_est_size, 32) for im in imgs])).to(self.device)
         logits = self.leres.forward(small)                                     # [N,h,w] fp32
+        n, h, w = logits.shape
+        if ori_h >= h and ori_w >= w and not getattr(self, 'leres_host_tail', False):
+            # the reference's numpy/OpenCV tail (16 -> 8 bit quantisation, INTER_AREA resize back) on the device, bit-exact (csrc/leres_tail.cu):
+            # no D2H, no host work, the stream never waits for the CPU
+            mm = torch.empty(2 * n, device=self.device, dtype=torch.int32)
+            q8 = torch.empty((n, h, w), device=self.device, dtype=torch.uint8)
+            out = torch.empty((n, 1, ori_h, ori_w), device=self.device, dtype=torch.float32)
+            check(lib().csb_leres_depth_tail(ptr(logits), n, h, w, ori_h, ori_w, ptr(mm), ptr(q8), ptr(out), stream()), "csb_leres_depth_tail")
+            pos_min = torch.where(out > 0, out, torch.full_like(out, float('inf'))).amin(dim=(1, 2, 3), keepdim=True)       # :577, per image
+            out = torch.where(out == 0, pos_min, out)
+            return (None, (ori_h, ori_w), n, out)
         key = tuple(logits.shape)
         if getattr(self, '_leres_pin', None) is None or tuple(self._leres_pin.shape) != key:
             self._leres_pin = torch.empty(key, dtype=torch.float32).pin_memory()
         self._leres_pin.copy_(logits, non_blocking=True)                       # one D2H for the batch
         ev = torch.cuda.Event()
         ev.record()
-        return (ev, (ori_h, ori_w), logits.shape[0])
+        return (ev, (ori_h, ori_w), logits.shape[0], None)
 
     def leres_finish(self, handle):
         """Phase 2: wait for the logits, run the reference's host-side tail (16->8 bit quantisation, OpenCV resize; a thread pool -- OpenCV and
         numpy release the GIL), upload the disparities."""
         from concurrent.futures import ThreadPoolExecutor
-        ev, (ori_h, ori_w), n = handle
+        if handle[0] is None:                                                  # finished on the device by leres_enqueue
+            return [handle[3][i:i + 1] for i in range(handle[2])]
+        ev, (ori_h, ori_w), n = handle[:3]
         ev.synchronize()
         logits = self._leres_pin.numpy()
         if getattr(self, '_pool', None) is None:

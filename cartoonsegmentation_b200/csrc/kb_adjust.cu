@@ -100,7 +100,9 @@ __device__ __forceinline__ void group_barrier(unsigned* counter, unsigned target
 
 __global__ void __launch_bounds__(512) k_adj_batch(float* __restrict__ disp, const uint8_t* __restrict__ masks, const int* __restrict__ num, int Kmax, int H, int W,
                                                    int G, int* __restrict__ tops, int* __restrict__ bottoms, int* __restrict__ mtops,
-                                                   int* __restrict__ mbottoms, unsigned* __restrict__ vbits, unsigned* __restrict__ bars) {
+                                                   int* __restrict__ mbottoms, unsigned* __restrict__ vbits, unsigned* __restrict__ bars,
+                                                   const int* __restrict__ need) {
+    if (need && *need == 0) return;                                 // the order-free path (below) already produced the result
     const int img = blockIdx.x / G, g = blockIdx.x % G;
     const int K = min(num[img], Kmax);
     float* D = disp + (size_t) img * H * W;
@@ -151,7 +153,187 @@ __global__ void __launch_bounds__(512) k_adj_batch(float* __restrict__ disp, con
     }
 }
 
+// ---- order-free formulation (the common case: every disparity under a mask is > 0, which the depth estimators guarantee) -------------------
+// With positive disparities the sequential recurrence has a closed dependency structure:
+//   * top_k / bottom_k / cut_k depend on the mask only (plane.sum(row) > 0  <=>  the row intersects the mask);
+//   * after the loop a pixel holds v_last, `last` = the highest instance index covering it;
+//   * v_k = max over the pixels q of mask_k in rows >= cut_k of the value q holds just before step k, i.e. of v_pred(q,k) (pred = highest covering
+//     index below k) or of the original disparity if there is none (masked-out pixels contribute plane = 0 < v_k).
+// So: one pass packs the K masks into a K-bit cover word per pixel and finds top/bottom; one pass derives base_k = max of original disparities
+// and the relation R[k] = {pred(q,k)}; K scalar steps resolve v_k = max(base_k, max_{j in R[k]} v_j); one pass writes v_last.  Every step is a
+// max or a select -- bit-identical to the reference's arithmetic ((1-m)*d + m*v is exactly v or d for finite d).  The first pass also raises a
+// flag if any masked disparity is not > 0; then nothing is written and the sequential kernel above runs instead.
+constexpr int kParMaxK = 128;
+
+__global__ void __launch_bounds__(256) k_adjp_cover(const float* __restrict__ disp, const uint8_t* __restrict__ masks, const int* __restrict__ num, int Kmax, int H,
+                                                    int W, int Kw, int* __restrict__ tops, int* __restrict__ bottoms, unsigned* __restrict__ cover,
+                                                    int* __restrict__ need) {
+    __shared__ int s_top[kParMaxK], s_bot[kParMaxK];
+    __shared__ int s_fail;
+    const int img = blockIdx.y, K = min(num[img], Kmax);
+    for (int i = threadIdx.x; i < kParMaxK; i += blockDim.x) { s_top[i] = 0x7fffffff; s_bot[i] = -1; }
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int segs = (W + 127) / 128;
+    const long long HW = (long long) H * W;
+    const float* D = disp + (long long) img * HW;
+    const uint8_t* M = masks + (long long) img * Kmax * HW;
+    unsigned* C = cover + (long long) img * HW * Kw;
+    bool fail = false;
+    for (long long sgm = (long long) blockIdx.x * nwarp + warp; sgm < (long long) H * segs; sgm += (long long) gridDim.x * nwarp) {
+        const int y = (int) (sgm / segs), x = (int) (sgm % segs) * 128 + lane * 4;
+        const bool valid = x < W;                                      // W % 4 == 0
+        const long long p = (long long) y * W + x;
+        unsigned c[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0u;
+        for (int k = 0; k < K; ++k) {
+            uchar4 m = make_uchar4(0, 0, 0, 0);
+            if (valid) m = *reinterpret_cast<const uchar4*>(M + (long long) k * HW + p);
+            const unsigned bit = 1u << (k & 31);
+            const int wi = k >> 5;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {                                  // static register indexing
+                if (w == wi) {
+                    if (m.x) c[0][w] |= bit;
+                    if (m.y) c[1][w] |= bit;
+                    if (m.z) c[2][w] |= bit;
+                    if (m.w) c[3][w] |= bit;
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, (m.x | m.y | m.z | m.w) != 0);
+            if (lane == 0 && b) {
+                if (y < s_top[k]) atomicMin(&s_top[k], y);
+                if (y > s_bot[k]) atomicMax(&s_bot[k], y);
+            }
+        }
+        if (valid) {
+            const float4 d = *reinterpret_cast<const float4*>(D + p);
+            const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned any = c[j][0] | c[j][1] | c[j][2] | c[j][3];
+                if (any && !(dv[j] > 0.f)) fail = true;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if (w < Kw) C[(p + j) * Kw + w] = c[j][w];
+            }
+        }
+    }
+    if (fail) s_fail = 1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        if (s_bot[k] >= 0) {
+            atomicMin(tops + img * Kmax + k, s_top[k]);
+            atomicMax(bottoms + img * Kmax + k, s_bot[k]);
+        }
+    }
+    if (threadIdx.x == 0 && s_fail) atomicOr(need, 1);
+}
+
+__global__ void __launch_bounds__(256) k_adjp_rel(const float* __restrict__ disp, const int* __restrict__ num, int Kmax, int H, int W, int Kw,
+                                                  const int* __restrict__ tops, const int* __restrict__ bottoms, const unsigned* __restrict__ cover,
+                                                  unsigned* __restrict__ base, unsigned* __restrict__ rel, const int* __restrict__ need) {
+    if (*need) return;
+    __shared__ int s_cut[kParMaxK];
+    __shared__ unsigned s_base[kParMaxK];
+    __shared__ unsigned s_rel[kParMaxK * 4];
+    const int img = blockIdx.y, K = min(num[img], Kmax);
+    for (int k = threadIdx.x; k < kParMaxK; k += blockDim.x) {
+        int cut = 0x7fffffff;
+        if (k < K) {
+            const int top = tops[img * Kmax + k], bottom = bottoms[img * Kmax + k];
+            if (bottom >= 0) cut = py_round_to_int((double) top + (0.97 * (double) (bottom - top)));
+        }
+        s_cut[k] = cut;
+        s_base[k] = 0u;
+    }
+    for (int i = threadIdx.x; i < kParMaxK * 4; i += blockDim.x) s_rel[i] = 0u;
+    __syncthreads();
+    const long long HW = (long long) H * W;
+    const float* D = disp + (long long) img * HW;
+    const unsigned* C = cover + (long long) img * HW * Kw;
+    for (long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long) gridDim.x * blockDim.x) {
+        const int y = (int) (p / W);
+        int prev = -1;
+        for (int wi = 0; wi < Kw; ++wi) {
+            unsigned w = C[p * Kw + wi];
+            while (w) {
+                const int k = wi * 32 + (__ffs(w) - 1);
+                w &= w - 1;
+                if (y >= s_cut[k]) {
+                    if (prev < 0) {
+                        const unsigned u = __float_as_uint(D[p]);             // > 0: bit patterns order like the values
+                        if (u > s_base[k]) atomicMax(&s_base[k], u);
+                    } else {
+                        const unsigned bit = 1u << (prev & 31);
+                        const int idx = k * 4 + (prev >> 5);
+                        if (!(s_rel[idx] & bit)) atomicOr(&s_rel[idx], bit);
+                    }
+                }
+                prev = k;
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (s_base[k]) atomicMax(base + img * Kmax + k, s_base[k]);
+    for (int i = threadIdx.x; i < K * 4; i += blockDim.x)
+        if (s_rel[i]) atomicOr(rel + (long long) img * Kmax * 4 + i, s_rel[i]);
+}
+
+// one warp per image: v_k = max(base_k, max_{j in R[k]} v_j), k ascending (R[k] only holds j < k)
+__global__ void k_adjp_resolve(const int* __restrict__ num, int Kmax, const unsigned* __restrict__ base, const unsigned* __restrict__ rel,
+                               unsigned* __restrict__ vbits, const int* __restrict__ need) {
+    if (*need) return;
+    __shared__ unsigned v[kParMaxK];
+    const int img = blockIdx.x, K = min(num[img], Kmax), lane = threadIdx.x;
+    for (int k = 0; k < K; ++k) {
+        unsigned m = 0u;
+        if (lane < 4) {
+            unsigned w = rel[((long long) img * Kmax + k) * 4 + lane];
+            while (w) {
+                const int j = lane * 32 + (__ffs(w) - 1);
+                w &= w - 1;
+                m = max(m, v[j]);
+            }
+        }
+        for (int o = 2; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) v[k] = max(m, base[img * Kmax + k]);
+        __syncwarp();
+    }
+    for (int k = lane; k < K; k += 32) vbits[img * Kmax + k] = v[k];
+}
+
+__global__ void __launch_bounds__(256) k_adjp_apply(float* __restrict__ disp, int Kmax, int H, int W, int Kw, const unsigned* __restrict__ cover,
+                                                    const unsigned* __restrict__ vbits, const int* __restrict__ need) {
+    if (*need) return;
+    const int img = blockIdx.y;
+    const long long HW = (long long) H * W;
+    float* D = disp + (long long) img * HW;
+    const unsigned* C = cover + (long long) img * HW * Kw;
+    for (long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long) gridDim.x * blockDim.x) {
+        for (int wi = Kw - 1; wi >= 0; --wi) {
+            const unsigned w = C[p * Kw + wi];
+            if (w) {
+                D[p] = __uint_as_float(vbits[img * Kmax + wi * 32 + 31 - __clz(w)]);
+                break;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+// state (int32 words): [tops | mtops | bottoms | mbottoms | vbits] x (N*Kmax), bars [N], need [4], base [N*Kmax], rel [N*Kmax*4], cover [N*H*W*Kw]
+extern "C" long long csb_depth_adjust_state_words(int N, int Kmax, int H, int W) {
+    const long long slots = (long long) N * Kmax;
+    const long long Kw = (Kmax + 31) / 32;
+    long long words = 5 * slots + N + 4 + slots + slots * 4;
+    if (Kmax <= kParMaxK && W % 4 == 0) words += (long long) N * H * W * Kw;
+    return words;
+}
 
 extern "C" int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, const int* num, int N, int Kmax, int H, int W, int32_t* state, void* stream) {
     CSB_REQUIRE(disparity && masks && num && state, "null pointer");
@@ -161,17 +343,37 @@ extern "C" int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, co
     CSB_REQUIRE(G >= 1, "at most one image per SM (N <= SM count): split the batch");
     G = G > 16 ? 16 : G;
     const size_t slots = (size_t) N * Kmax;
-    int* tops = state;                       // [tops | mtops] initialised to 0x7f7f7f7f, [bottoms | mbottoms] to -1, [vbits | bars] to 0
+    int* tops = state;                       // [tops | mtops] initialised to 0x7f7f7f7f, [bottoms | mbottoms] to -1, everything after to 0
     int* mtops = state + slots;
     int* bottoms = state + 2 * slots;
     int* mbottoms = state + 3 * slots;
     unsigned* vbits = reinterpret_cast<unsigned*>(state + 4 * slots);
     unsigned* bars = reinterpret_cast<unsigned*>(state + 5 * slots);
+    int* need = state + 5 * slots + N;
+    unsigned* base = reinterpret_cast<unsigned*>(need + 4);
+    unsigned* rel = base + slots;
+    unsigned* cover = rel + slots * 4;
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(tops, 0x7f, sizeof(int) * 2 * slots, st), "memset"));
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(bottoms, 0xff, sizeof(int) * 2 * slots, st), "memset"));
-    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(vbits, 0, sizeof(int) * (slots + N), st), "memset"));
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(vbits, 0, sizeof(int) * (slots + N + 4 + slots + slots * 4), st), "memset"));
     csb::memset_done(st);
-    void* args[] = {&disparity, &masks, &num, &Kmax, &H, &W, &G, &tops, &bottoms, &mtops, &mbottoms, &vbits, &bars};
+    const int* need_arg = nullptr;
+    if (Kmax <= kParMaxK && W % 4 == 0) {                            // order-free path; falls through to the sequential kernel if `need` gets raised
+        const int Kw = (Kmax + 31) / 32;
+        int gx = (4 * csb::num_sms() + N - 1) / N;
+        gx = gx < 1 ? 1 : gx;
+        k_adjp_cover<<<dim3(gx, N), 256, 0, st>>>(disparity, masks, num, Kmax, H, W, Kw, mtops, mbottoms, cover, need);      // mask-row extents: the
+        // sequential kernel computes the same values into the same slots, so a fallback run is not disturbed
+        CSB_TRY(csb::launched("k_adjp_cover", st));
+        k_adjp_rel<<<dim3(gx, N), 256, 0, st>>>(disparity, num, Kmax, H, W, Kw, mtops, mbottoms, cover, base, rel, need);
+        CSB_TRY(csb::launched("k_adjp_rel", st));
+        k_adjp_resolve<<<N, 32, 0, st>>>(num, Kmax, base, rel, vbits, need);
+        CSB_TRY(csb::launched("k_adjp_resolve", st));
+        k_adjp_apply<<<dim3(gx, N), 256, 0, st>>>(disparity, Kmax, H, W, Kw, cover, vbits, need);
+        CSB_TRY(csb::launched("k_adjp_apply", st));
+        need_arg = need;
+    }
+    void* args[] = {&disparity, &masks, &num, &Kmax, &H, &W, &G, &tops, &bottoms, &mtops, &mbottoms, &vbits, &bars, &need_arg};
     // cooperative launch: the runtime verifies that all N*G CTAs are co-resident, which the software barriers rely on
     CSB_TRY(csb::cuda_ok(cudaLaunchCooperativeKernel((void*) k_adj_batch, dim3(N * G), dim3(512), args, 0, st), "cudaLaunchCooperativeKernel(k_adj_batch)"));
     return csb::launched("k_adj_batch", st);

@@ -90,8 +90,12 @@ CSB_API int csb_disocclusion_fill(const float* input, const float* depth, int B,
  * on the device without host syncs.  disparity [H,W] fp32 in place; masks [K,H,W] uint8 0/1 (torch.bool); state: 16 bytes of device scratch.
  * (The reference's `.sum() == 0` skip and row tests are evaluated as "any plane > 0", identical for non-negative disparities.) */
 CSB_API int csb_depth_adjust_instances(float* disparity, const uint8_t* masks, int K, int H, int W, void* state, void* stream);
-/* The same for a batch in ONE cooperative launch: disparity [N,H,W] in place, masks [N,Kmax,H,W], num [N] device int32 (instances per image,
- * e.g. straight from csb_rtmdet_select), state: (5*N*Kmax + N) int32 of device scratch.  N <= number of SMs. */
+/* The same for a batch without host synchronisation: disparity [N,H,W] in place, masks [N,Kmax,H,W], num [N] device int32 (instances per image,
+ * e.g. straight from csb_rtmdet_select), state: csb_depth_adjust_state_words(N, Kmax, H, W) int32 of device scratch.  N <= number of SMs.
+ * When every disparity under a mask is > 0 (what the depth estimators produce) the recurrence is evaluated order-free in four parallel passes
+ * (K-bit cover word per pixel, predecessor relation, K scalar max steps, write-back: csrc/kb_adjust.cu); otherwise -- decided on the device -- one
+ * cooperative launch walks the instances in order.  Both are bit-identical to the reference's torch formulation. */
+CSB_API long long csb_depth_adjust_state_words(int N, int Kmax, int H, int W);
 CSB_API int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, const int* num, int N, int Kmax, int H, int W, int32_t* state, void* stream);
 
 /* process_shift scalar part -- anime_3dkenburns/common.py:60-72, evaluated on the device in double precision from the
@@ -129,6 +133,11 @@ CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, in
 
 /* cv2.resize(src, (Wo,Ho), interpolation=INTER_LINEAR) on uint8 HWC images, bit-exact (used for scaledown_maxsize, utils/io_utils.py:254-274). */
 CSB_API int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream);
+
+/* LeReS post-processing -- depth_modules/leres/__init__.py:117-140 (min/max normalise to 16 bit, cv2.convertScaleAbs to 8 bit,
+ * bitwise_not) + kenburns_effect.py:572-577 (cv2.resize INTER_AREA back to the frame size, astype(float32)), bit-exact against numpy + OpenCV, for
+ * the upscaling / same-size branch.  logits [N,h,w] fp32 -> out [N,H,W] fp32 (8-bit values); minmax: 2*N uint32, q8: N*h*w bytes of scratch. */
+CSB_API int csb_leres_depth_tail(const float* logits, int N, int h, int w, int H, int W, unsigned* minmax, uint8_t* q8, float* out, void* stream);
 
 /* ZoeDepth / MiDaS DPT-BEiT-L encoder pieces (the encoder is torch.hub `intel-isl/MiDaS` `DPT_BEiT_L_384`, loaded at
  * depth_modules/zoedepth/models/base_models/midas.py:341 and NOT vendored in the reference: restated from timm's BEiT + MiDaS v3.1's DPT).

@@ -394,3 +394,37 @@ ORC_API void orc_bokeh_pass(int n, int h, int w, int nsamples, float dx, float d
         blurred[fid] = (weight != 0.f) ? color / weight : img[fid];
     }
 }
+
+/* cv2.resize(src 8UC1, (dw, dh), interpolation=INTER_AREA) when UPSCALING (dw >= sw and dh >= sh) -- the LeReS tail, kenburns_effect.py:572-577.
+ * OpenCV imgproc/src/resize.cpp: "true area interpolation is only implemented for scale >= 1; otherwise it is emulated using some variant of
+ * bilinear": INTER_LINEAR's fixed-point kernel (11-bit coefficients) with area-mode source positions
+ *     sx = floor(dx * scale);  fx = (dx + 1) - (sx + 1) * inv_scale;  fx = fx <= 0 ? 0 : fx - floor(fx). */
+ORC_API void orc_resize_area_up_u8c1(const uint8_t* src, int sh, int sw, int dh, int dw, uint8_t* dst) {
+    const double inv_x = (double) dw / sw, inv_y = (double) dh / sh;
+    const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
+    int* xo = (int*) malloc(sizeof(int) * dw); short* xa = (short*) malloc(sizeof(short) * dw * 2);
+    for (int dx = 0; dx < dw; ++dx) {
+        int sx = (int) floor(dx * scale_x);
+        float fx = (float) ((dx + 1) - (sx + 1) * inv_x);
+        fx = fx <= 0 ? 0.f : fx - floorf(fx);
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xo[dx] = sx;
+        xa[dx * 2] = (short) lrintf((1.f - fx) * 2048.f); xa[dx * 2 + 1] = (short) lrintf(fx * 2048.f);
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+        int sy = (int) floor(dy * scale_y);
+        float fy = (float) ((dy + 1) - (sy + 1) * inv_y);
+        fy = fy <= 0 ? 0.f : fy - floorf(fy);
+        const int y0 = clampi(sy, 0, sh - 1), y1 = clampi(sy + 1, 0, sh - 1);
+        const short b0 = (short) lrintf((1.f - fy) * 2048.f), b1 = (short) lrintf(fy * 2048.f);
+        for (int dx = 0; dx < dw; ++dx) {
+            const int x0 = xo[dx], x1 = x0 + 1 < sw ? x0 + 1 : x0;
+            const int s0 = src[(long) y0 * sw + x0] * xa[dx * 2] + src[(long) y0 * sw + x1] * xa[dx * 2 + 1];
+            const int s1 = src[(long) y1 * sw + x0] * xa[dx * 2] + src[(long) y1 * sw + x1] * xa[dx * 2 + 1];
+            const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+            dst[(long) dy * dw + dx] = (uint8_t) (v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+    }
+    free(xo); free(xa);
+}

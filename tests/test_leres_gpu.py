@@ -66,3 +66,39 @@ def test_leres_forward_vs_reference_golden(eng, name):
     d = np.abs(qa.astype(int) - qb.astype(int))
     print(f"   8-bit depth image: max |diff| {d.max()} levels, mean {d.mean():.3f}")
     assert d.mean() < 2.0 and np.percentile(d, 99) <= 6
+
+
+@pytest.mark.parametrize("hw,HW", [((640, 640), (1024, 1024)), ((480, 640), (720, 960)), ((96, 128), (100, 131)), ((64, 96), (64, 96))])
+def test_device_tail_equals_host_numpy_opencv(built_lib, hw, HW):
+    """csb_leres_depth_tail == the reference's host tail (apply_leres :117-140 + kenburns_effect.py:572-577) run with numpy + OpenCV, exactly."""
+    import cv2
+    from cartoonsegmentation_b200._lib import check, lib, ptr, stream
+    from cartoonsegmentation_b200.depth_modules.leres import quantise_depth
+    (h, w), (H, W) = hw, HW
+    n = 3
+    rng = np.random.default_rng(h + W)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    logits = np.stack([(3 + np.sin(xx / (7.0 + i)) * np.cos(yy / 11.0) * 2 + rng.standard_normal((h, w)) * 0.05).astype(np.float32) for i in range(n)])
+    logits[2] = 1.5                                                             # constant map: max - min <= eps -> zeros -> 255 everywhere
+    dev = torch.from_numpy(logits).cuda()
+    mm = torch.empty(2 * n, device='cuda', dtype=torch.int32)
+    q8 = torch.empty((n, h, w), device='cuda', dtype=torch.uint8)
+    out = torch.empty((n, H, W), device='cuda', dtype=torch.float32)
+    check(lib().csb_leres_depth_tail(ptr(dev), n, h, w, H, W, ptr(mm), ptr(q8), ptr(out), stream()), "csb_leres_depth_tail")
+    for i in range(n):
+        d8 = quantise_depth(logits[i])
+        assert np.array_equal(q8[i].cpu().numpy(), d8)
+        ref = cv2.resize(d8, (W, H), interpolation=cv2.INTER_AREA).astype(np.float32)
+        assert np.array_equal(out[i].cpu().numpy(), ref)
+
+
+def test_pipeline_leres_device_tail_matches_host_tail(built_lib):
+    from cartoonsegmentation_b200.anime_3dkenburns.kenburns_effect import KenBurnsConfig, KenBurnsPipeline
+    from cartoonsegmentation_b200.utils.synthetic import smooth_image
+    pipe = KenBurnsPipeline(KenBurnsConfig(det_size=320, max_size=1024, num_frame=3, depth_est='leres', depth_est_size=320))
+    imgs = [smooth_image(512, 640, seed=31 + i) for i in range(2)]
+    a = pipe._depth_est_leres_batch(imgs)
+    pipe.leres_host_tail = True
+    b = pipe._depth_est_leres_batch(imgs)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

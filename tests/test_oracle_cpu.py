@@ -181,3 +181,17 @@ def test_bokeh_oracle_chain_runs():
     img = rng.integers(0, 256, (40, 56, 3), dtype=np.uint8)
     out = bo.bokeh_blur(img, d8, 32, 13, 1, bo.focal_plane(0.5, 50.0, start, end))
     assert out.shape == img.shape and out.dtype == np.uint8
+
+
+def test_area_upscale_restatement_matches_opencv():
+    """orc_resize_area_up_u8c1 (cv2.resize INTER_AREA when upscaling = fixed-point bilinear with area-mode source positions) == cv2, bit for bit."""
+    import ctypes as C
+    import cv2
+    from oracle import kb_oracle
+    L = kb_oracle.lib()
+    rng = np.random.default_rng(0)
+    for (sh, sw, dh, dw) in [(640, 640, 1024, 1024), (480, 640, 720, 960), (96, 128, 100, 131), (33, 47, 97, 50), (64, 64, 64, 64)]:
+        src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        dst = np.empty((dh, dw), np.uint8)
+        L.orc_resize_area_up_u8c1(src.ctypes.data_as(C.c_void_p), sh, sw, dh, dw, dst.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(dst, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA))

@@ -119,3 +119,34 @@ def test_inpaint_net_vs_reference_golden(built_lib):
         rel = np.sqrt(((a - b) ** 2).mean()) / np.sqrt((b ** 2).mean())
         print(f"{k}: relative RMS error {rel:.5f}, max abs {np.abs(a - b).max():.4f}")
         assert a.shape == b.shape and rel < 2e-2
+
+
+@pytest.mark.parametrize("H,W,K,mode", [(200, 260, 9, 'positive'), (200, 260, 9, 'zeros'), (96, 130, 5, 'positive'), (256, 512, 100, 'positive'), (128, 256, 40, 'negative')])
+def test_depth_adjust_batch_paths_match_reference_formulation(built_lib, H, W, K, mode):
+    """csb_depth_adjust_batch: the order-free path (positive disparities, W % 4 == 0, K <= 128) and the device-selected sequential fallback
+    (zeros / negatives under a mask, other widths) are both bit-identical to the reference's torch loop (kenburns_effect.py:39-91), with heavily
+    overlapping masks, empty instances and different instance counts per image."""
+    from cartoonsegmentation_b200.animeinsseg import AnimeInstances
+    from cartoonsegmentation_b200.anime_3dkenburns import kenburns_effect as kb
+    rng = np.random.default_rng(H + K)
+    disp = torch.from_numpy(smooth_disparity(H, W, seed=3)).cuda().reshape(1, 1, H, W).clone()
+    if mode == 'zeros':
+        disp[0, 0, 40:90, 30:200] = 0.0
+    if mode == 'negative':
+        disp[0, 0, 10:60, 100:180] *= -1.0
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = np.zeros((K, H, W), bool)
+    for k in range(K):                                   # big overlapping ellipses + a few thin / empty ones
+        cy, cx, ry, rx = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(4, H / 1.5), rng.uniform(4, W / 1.5)
+        masks[k] = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1.0
+    masks[K // 2] = False
+    masks[K - 1, H - 1, :] = True
+    m = torch.from_numpy(masks).cuda()
+    img = torch.zeros(1, 3, H, W, device='cuda')
+    counts = [K, 0, max(1, K // 3)]
+    d3 = disp[0].repeat(3, 1, 1).contiguous()
+    kb.depth_adjust_batch(d3, m[None].repeat(3, 1, 1, 1).contiguous(), torch.tensor(counts, device='cuda', dtype=torch.int32))
+    for i, c in enumerate(counts):
+        inst = AnimeInstances(m[:c], torch.zeros(c, 4, dtype=torch.int32, device='cuda'), torch.ones(c, device='cuda')) if c else AnimeInstances()
+        ref = kb.depth_adjustment_animesseg_torch(inst, disp.clone(), img)
+        assert torch.equal(d3[i], ref[0, 0]), (mode, i, float((d3[i] - ref[0, 0]).abs().max()))
