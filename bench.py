@@ -224,7 +224,7 @@ def main():
     stage_img = torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8)
     cd = ctypes.c_double
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    seg_sub = 8                                                      # detector sub-batch (activations of 8 x 1024^2 ~ 3 GB)
+    seg_sub = int(os.environ.get("CSB_SEG_SUB", "32"))              # detector sub-batch (activations of 32 x 1024^2 ~ 12 GB of the 180 GB)
     stats = {"instances": 0}
 
     def warp(img_u8, raw, out, slot):

@@ -272,7 +272,9 @@ class RTMDetIns:
 
     def _init_convnext(self, sd, dev, f32):
         # ---- backbone (Appendix A.4)
-        self.stem = _Conv(sd["backbone.downsample_layers.0.0.weight"], sd["backbone.downsample_layers.0.0.bias"], dev, stride=4, cin_pad=16)
+        # 4x4 stride-4 patchify as a 1x1 GEMM over the space-to-depth input written by csb_image_prep_s2d_nhwc: weight [Cout, (r*4+s)*3+c] padded to 64
+        w0 = sd["backbone.downsample_layers.0.0.weight"].float()
+        self.stem = _Conv(w0.permute(0, 2, 3, 1).reshape(w0.shape[0], 48, 1, 1), sd["backbone.downsample_layers.0.0.bias"], dev, cin_pad=64)
         self.stem_ln = (f32(sd["backbone.downsample_layers.0.1.weight"]), f32(sd["backbone.downsample_layers.0.1.bias"]))
         self.down = [None]
         for i in range(1, 4):
@@ -339,7 +341,10 @@ class RTMDetIns:
         assert H % 32 == 0 and W % 32 == 0, "detector input must be padded to a multiple of 32 (Pad to det_size)"
         dev, f16 = img_u8.device, torch.float16
         h3, w3, h4, w4, h5, w5 = H // 8, W // 8, H // 16, W // 16, H // 32, W // 32
-        x16 = E.image_prep_nhwc(img_u8, MEAN_BGR, STD_BGR, swap_rb=False, CP=16)
+        if self.cspnext is not None:
+            x16 = E.image_prep_nhwc(img_u8, MEAN_BGR, STD_BGR, swap_rb=False, CP=16)
+        else:
+            x16 = E.image_prep_s2d_nhwc(img_u8, MEAN_BGR, STD_BGR, 4, 64)                  # [N,H/4,W/4,64]: the ConvNeXt stem's GEMM input
         cat3 = torch.empty((N, h3, w3, 512), device=dev, dtype=f16)      # [up(p4) | c3]
         cat4 = torch.empty((N, h4, w4, 1024), device=dev, dtype=f16)     # [up(p5) | c4]
         c5 = torch.empty((N, h5, w5, 1024), device=dev, dtype=f16)

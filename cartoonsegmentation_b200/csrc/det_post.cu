@@ -361,6 +361,64 @@ __global__ void __launch_bounds__(256) k_mask_tail_up8(const float* __restrict__
     }
 }
 
+// 16 output pixels per thread, one aligned 16 B store.  Pixels 16t .. 16t+15 of a row interpolate between the logit columns 2t-1 .. 2t+2
+// (clamped at the borders, which is exactly what the align_corners=False source-index clamp does): [second half of cell 2t-1 | cell 2t | first half of
+// cell 2t+1].  The interpolant is linear inside a cell, so if its six segment end points all lie on one side of the threshold (by more than the 1e-3
+// margin) the whole 16-pixel run is constant -- the common case away from mask boundaries costs ~2 instructions per pixel; otherwise the pixels
+// are walked individually, with the reference's exact expression inside the margin.
+__global__ void __launch_bounds__(256) k_mask_tail_up8x16(const float* __restrict__ logits, const int* __restrict__ num, int max_per_img, int h, int w, int H, int W,
+                                                          float thr, float thr_logit, unsigned char* __restrict__ masks) {
+    const int inst = blockIdx.y, img = blockIdx.z;
+    if (inst >= num[img]) return;
+    const float* lg = logits + ((size_t) img * max_per_img + inst) * h * w;
+    unsigned char* out = masks + ((size_t) img * max_per_img + inst) * H * W;
+    const int runs = W / 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * runs; i += gridDim.x * blockDim.x) {
+        const int t = i % runs, y = i / runs;
+        int y0, y1;
+        float ly0, ly1;
+        src_index(0.125f, y, h, y0, y1, ly0, ly1);
+        const float* r0 = lg + y0 * w;
+        const float* r1 = lg + y1 * w;
+        float A[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = min(max(2 * t - 1 + k, 0), w - 1);
+            A[k] = ly0 * __ldg(r0 + c) + ly1 * __ldg(r1 + c);
+        }
+        const float d0 = A[1] - A[0], d1 = A[2] - A[1], d2 = A[3] - A[2];
+        // segment end points: cell 2t-1 at j = 4, 7; cell 2t at j = 0, 7; cell 2t+1 at j = 0, 3   (weight (2j+1)/16)
+        const float e0 = fmaf(d0, 0.5625f, A[0]), e1 = fmaf(d0, 0.9375f, A[0]), e2 = fmaf(d1, 0.0625f, A[1]), e3 = fmaf(d1, 0.9375f, A[1]),
+                    e4 = fmaf(d2, 0.0625f, A[2]), e5 = fmaf(d2, 0.4375f, A[2]);
+        const float lo = fminf(fminf(fminf(e0, e1), fminf(e2, e3)), fminf(e4, e5)), hi = fmaxf(fmaxf(fmaxf(e0, e1), fmaxf(e2, e3)), fmaxf(e4, e5));
+        uint4 r;
+        if (lo - thr_logit > 1e-3f) r = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+        else if (thr_logit - hi > 1e-3f) r = make_uint4(0u, 0u, 0u, 0u);
+        else {
+            auto exact = [&](int x) {
+                int x0, x1;
+                float lx0, lx1;
+                src_index(0.125f, x, w, x0, x1, lx0, lx1);
+                return ly0 * (lx0 * __ldg(r0 + x0) + lx1 * __ldg(r0 + x1)) + ly1 * (lx0 * __ldg(r1 + x0) + lx1 * __ldg(r1 + x1));
+            };
+            unsigned wds[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const int seg = p < 4 ? 0 : (p < 12 ? 1 : 2), j = p < 4 ? p + 4 : (p < 12 ? p - 4 : p - 12);
+                const float a = seg == 0 ? A[0] : (seg == 1 ? A[1] : A[2]), dd = seg == 0 ? d0 : (seg == 1 ? d1 : d2);
+                const float v = fmaf(dd, (float) (2 * j + 1) * 0.0625f, a);
+                const float m = v - thr_logit;
+                unsigned bit;
+                if (fabsf(m) > 1e-3f) bit = m > 0.f ? 1u : 0u;
+                else bit = mask_decide(exact(16 * t + p), thr, thr_logit);
+                wds[p >> 2] |= bit << (8 * (p & 3));
+            }
+            r = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+        *reinterpret_cast<uint4*>(out + (size_t) y * W + 16 * t) = r;
+    }
+}
+
 }  // namespace
 
 extern "C" int csb_rtmdet_select(const float* const* cls, const float* const* reg, const float* const* ker, const int* hs, const int* ws, const int* strides,
@@ -413,6 +471,12 @@ extern "C" int csb_rtmdet_masks(const float* mask_feat, const float* kernels, co
         const float tl = (mask_thr > 0.f && mask_thr < 1.f) ? logf(mask_thr / (1.0f - mask_thr)) : (mask_thr <= 0.f ? -INFINITY : INFINITY);
         int g8 = (out_h * (w + 1) + 255) / 256;
         g8 = g8 > 128 ? 128 : g8;
+        if (out_w % 16 == 0 && (((uintptr_t) masks | (size_t) out_h * out_w) & 15) == 0) {
+            int g16 = (out_h * (out_w / 16) + 255) / 256;
+            g16 = g16 > 64 ? 64 : g16;
+            k_mask_tail_up8x16<<<dim3(g16, max_per_img, N), 256, 0, st>>>(logits, num, max_per_img, h, w, out_h, out_w, mask_thr, tl, masks);
+            return csb::launched("k_mask_tail", st);
+        }
         k_mask_tail_up8<<<dim3(g8, max_per_img, N), 256, 0, st>>>(logits, num, max_per_img, h, w, out_h, out_w, mask_thr, tl, masks);
         return csb::launched("k_mask_tail", st);
     }

@@ -274,6 +274,31 @@ __global__ void __launch_bounds__(256) k_image_prep(const uint8_t* __restrict__ 
     }
 }
 
+// Space-to-depth variant for a P x P stride-P stem conv (ConvNeXt's 4x4 s4 patchify): y [N, H/P, W/P, CP] with channel (r*P + s)*3 + c holding the
+// normalised pixel (P*oy + r, P*ox + s), zero padded to CP -- the stem becomes a dense 1x1 GEMM with K = CP instead of P*P taps of 16 padded
+// channels, and this kernel writes 2*CP/(P*P) B per input pixel instead of 32.  One thread per (output cell, row r of the patch).
+__global__ void __launch_bounds__(256) k_image_prep_s2d(const uint8_t* __restrict__ img, int N, int H, int W, int P, float m0, float m1, float m2, float s0,
+                                                        float s1, float s2, int swap_rb, int CP, __half* __restrict__ y) {
+    const int Ho = H / P, Wo = W / P;
+    const long long total = (long long) N * Ho * Wo * P;
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
+        const int r = (int) (i % P);
+        const long long cell = i / P;
+        const int ox = (int) (cell % Wo), oy = (int) ((cell / Wo) % Ho);
+        const long long n = cell / ((long long) Wo * Ho);
+        const uint8_t* src = img + ((n * H + (long long) oy * P + r) * W + (long long) ox * P) * 3;
+        __half* dst = y + cell * CP + r * P * 3;
+        for (int e = 0; e < P * 3; ++e) {
+            const int c = e % 3;
+            const int cs = swap_rb ? 2 - c : c;
+            dst[e] = __float2half_rn(((float) src[e - c + cs] - mean[c]) / sd[c]);
+        }
+        if (r == P - 1)
+            for (int e = P * P * 3; e < CP; ++e) y[cell * CP + e] = __float2half_rn(0.f);
+    }
+}
+
 // MaxPool2d(K, stride, pad[, ceil_mode]) NHWC fp16 on channel slices: one thread per (output pixel, 8-channel vector).
 __global__ void __launch_bounds__(256) k_maxpool(const __half* __restrict__ x, int ldx, int xoff, int N, int H, int W, int C, int K, int stride, int pad,
                                                  int Ho, int Wo, __half* __restrict__ y, int ldy, int yoff) {
@@ -355,6 +380,15 @@ static int pool_out(int H, int K, int stride, int pad, int ceil_mode) {
     int o = ceil_mode ? (H + 2 * pad - K + stride - 1) / stride + 1 : (H + 2 * pad - K) / stride + 1;
     if (ceil_mode && (o - 1) * stride >= H + pad) --o;      // PyTorch: the last window must start inside the (left-padded) input
     return o;
+}
+
+extern "C" int csb_image_prep_s2d_nhwc(const uint8_t* img, int N, int H, int W, int P, const float* mean3, const float* std3, int swap_rb, int CP, void* y,
+                                       void* stream) {
+    CSB_REQUIRE(img && mean3 && std3 && y, "null pointer");
+    CSB_REQUIRE(N > 0 && P > 0 && H % P == 0 && W % P == 0 && CP >= P * P * 3 && CP % 8 == 0, "H and W must be multiples of P, CP >= 3 P^2");
+    k_image_prep_s2d<<<csb::wave_grid((long long) N * (H / P) * (W / P) * P, 256, 8), 256, 0, (cudaStream_t) stream>>>(
+        img, N, H, W, P, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], swap_rb, CP, (__half*) y);
+    return csb::launched("k_image_prep", (cudaStream_t) stream);
 }
 
 extern "C" int csb_maxpool2d_nhwc(const void* x, int ldx, int xoff, int N, int H, int W, int C, int K, int stride, int pad, int ceil_mode, void* y, int ldy,

@@ -115,6 +115,17 @@ def image_prep_nhwc(img_u8, mean, std, swap_rb=False, CP=16):
     return out
 
 
+def image_prep_s2d_nhwc(img_u8, mean, std, P, CP, swap_rb=False):
+    """uint8 [N,H,W,3] -> fp16 [N,H/P,W/P,CP] space-to-depth (channel (r*P+s)*3+c), (x-mean)/std, zero padded: input of a patchify stem as a 1x1 GEMM."""
+    if img_u8.dim() == 3:
+        img_u8 = img_u8[None]
+    N, H, W, _ = img_u8.shape
+    out = torch.empty((N, H // P, W // P, CP), device=img_u8.device, dtype=torch.float16)
+    m = (C.c_float * 3)(*[float(v) for v in mean]); s = (C.c_float * 3)(*[float(v) for v in std])
+    check(lib().csb_image_prep_s2d_nhwc(ptr(img_u8), N, H, W, P, m, s, int(swap_rb), CP, ptr(out), stream()), "csb_image_prep_s2d_nhwc")
+    return out
+
+
 def maxpool3s2_nhwc(x):
     N, H, W, Cc = x.shape
     out = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), device=x.device, dtype=x.dtype)

@@ -244,6 +244,10 @@ CSB_API int csb_layernorm_nhwc(const void* x, int ldx, int xoff, const float* ga
 CSB_API int csb_resample_nhwc(const void* x, int ldx, int xoff, int N, int Hi, int Wi, int C, int Ho, int Wo, int mode, void* y, int ldy, int yoff,
                       void* stream);
 CSB_API int csb_image_prep_nhwc(const uint8_t* img, long long npix, const float* mean3, const float* std3, int swap_rb, int CP, void* y, void* stream);
+/*   csb_image_prep_s2d_nhwc  the same normalisation written space-to-depth for a P x P stride-P patchify stem (ConvNeXt 4x4 s4): y [N,H/P,W/P,CP],
+ *                       channel (r*P+s)*3+c = pixel (P*oy+r, P*ox+s), zero padded to CP; the stem conv then is a 1x1 GEMM over CP channels. */
+CSB_API int csb_image_prep_s2d_nhwc(const uint8_t* img, int N, int H, int W, int P, const float* mean3, const float* std3, int swap_rb, int CP, void* y,
+                            void* stream);
 /*   csb_maxpool_nhwc    MaxPool2d(kernel 3, stride 2, padding 1) (ResNeXt stem, Resnext_torch.py:160).
  *   csb_add_nhwc        y = a + b on channel slices (FFM skip add, network_auxi.py:207).
  *   csb_resample_f32    single-channel fp32 bilinear resize, align_corners selectable (AO output upsample, network_auxi.py:251). */
