@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -58,6 +59,8 @@ struct ConvKernelParams {
     float* out_f32;
     int out_ld, out_coff;
     int is_bf16;
+    int tma_store;               // 0: per-lane 16 B global stores; 1 / 2: smem-staged TMA tile stores (64 B-swizzled / linear staging)
+    uint32_t stage_off;          // byte offset of the epilogue staging area (8 warps x 2 KiB) from the 1 KiB-aligned smem base
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -91,6 +94,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -194,8 +207,11 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 // One 32-column chunk of one accumulator row.  The fast path (full chunk, 16 B-aligned slices) is straight-line code: 8 float4 bias
 // loads (warp-uniform -> broadcast), 4 x 16 B residual loads, activation on 32 independent values, 4 x 16 B stores.
 template <class T, int ACT>
-__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[32], size_t pix, int n0, bool row_ok, bool fast) {
-    if (!row_ok) return;
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[32], size_t pix, int n0, bool row_ok, bool fast, uint32_t stage,
+                                               const CUtensorMap* tmC, int cw, int chh, int cimg) {
+    // stage != 0: this full chunk leaves through shared memory and one TMA tile store per warp (rows outside the image are clipped by the TMA unit;
+    // their arithmetic runs on in-bounds addresses because `pix` is clamped by the caller)
+    if (!row_ok && !(stage && fast && !p.out_f32)) return;
     if (fast && !p.out_f32) {
         float y[32];
 #pragma unroll
@@ -239,6 +255,26 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
 #pragma unroll
             for (int j = 0; j < 32; j += 2) upk2(fadd2(pk2(y[j], y[j + 1]), pk2(r[j], r[j + 1])), y[j], y[j + 1]);
         }
+        if (stage) {
+            // Each lane owns one 64 B row of the warp's 32 x 32 staging tile.  A 16 B-per-lane global store touches 32 different lines per
+            // instruction (the C -> 4C layers were bound by exactly that); the TMA engine writes whole rows and takes the work off the LSU.
+            const int lane = threadIdx.x & 31;
+            if (lane == 0) tma_store_wait_read();                 // the previous tile of this warp has left shared memory
+            __syncwarp();
+            const uint32_t row = stage + (uint32_t) lane * 64u;
+            const uint32_t sw = p.tma_store == 1 ? (uint32_t) ((lane >> 1) & 3) : 0u;      // CU_TENSOR_MAP_SWIZZLE_64B: 16 B chunk ^= (row >> 1) & 3
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                st_shared_v4(row + (((uint32_t) g ^ sw) << 4), make_uint4(pack2<T>(y[8 * g], y[8 * g + 1]), pack2<T>(y[8 * g + 2], y[8 * g + 3]),
+                                                                         pack2<T>(y[8 * g + 4], y[8 * g + 5]), pack2<T>(y[8 * g + 6], y[8 * g + 7])));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_4d(tmC, stage, n0, cw, chh, cimg);
+                tma_store_commit();
+            }
+            return;
+        }
         uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.out) + pix * p.out_ld + p.out_coff + n0);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -247,6 +283,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
         return;
     }
     // generic path: channel tails, unaligned slices, fp32 outputs (head predictions)
+    if (!row_ok) return;
     const T* res = p.res_mode ? reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0 : nullptr;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -264,7 +301,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
 
 // Epilogue role: 8 warps; warp w owns TMEM lane quarter (w & 3) and the 32-column chunks with (chunk & 1) == (w - 4) / 4.
 template <class T, int ACT>
-__device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles) {
+__device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
+                                              const CUtensorMap* tmC) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, half = (warp - 4) >> 2;
     const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && (!p.bias || ((uintptr_t) p.bias % 16 == 0));
@@ -276,7 +314,11 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
         const int m = q * 32 + lane;
         const int oh = th * p.bh + m / p.bw, ow = tw * p.bw + m % p.bw;
         const bool row_ok = oh < p.H && ow < p.W;
-        const size_t pix = ((size_t) img * p.H + oh) * p.W + ow;
+        // rows outside the image still run the arithmetic on the TMA-store path (the store clips them): keep their residual address in bounds
+        const size_t pix = ((size_t) img * p.H + (oh < p.H ? oh : p.H - 1)) * p.W + (ow < p.W ? ow : p.W - 1);
+        const uint32_t stage = p.tma_store ? stage_base + (uint32_t) (warp - 4) * 2048u : 0u;
+        const int row0 = q * 32;
+        const int cw = tw * p.bw + row0 % p.bw, chh = th * p.bh + row0 / p.bw;
         mbar_wait(tfull0 + 8u * as, aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) as * 256u;
@@ -298,28 +340,30 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
                 if (lane == 0) mbar_arrive(tempty0 + 8u * as);
             }
             const int n0 = nt * p.block_n + ch * 32;
-            epilogue_chunk<T, ACT>(p, acc, pix, n0, row_ok, aligned && n0 + 32 <= p.Cout);
+            epilogue_chunk<T, ACT>(p, acc, pix, n0, row_ok, aligned && n0 + 32 <= p.Cout, stage, tmC, cw, chh, img);
         }
         if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();           // every tile store of this warp has completed before the CTA may exit
 }
 
 template <class T>
-__device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles) {
+__device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
+                                                  const CUtensorMap* tmC) {
     switch (p.act) {      // hoisted out of every loop: each instantiation is straight-line code
-        case CSB_ACT_RELU: epilogue_role<T, CSB_ACT_RELU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
-        case CSB_ACT_SILU: epilogue_role<T, CSB_ACT_SILU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
-        case CSB_ACT_GELU: epilogue_role<T, CSB_ACT_GELU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
-        case CSB_ACT_PRELU: epilogue_role<T, CSB_ACT_PRELU>(p, tmem_base, tfull0, tempty0, total_tiles); break;
-        case CSB_ACT_SIGMOID: epilogue_role<T, CSB_ACT_SIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles); break;
-        case CSB_ACT_SOFTPLUS: epilogue_role<T, CSB_ACT_SOFTPLUS>(p, tmem_base, tfull0, tempty0, total_tiles); break;
-        case CSB_ACT_HARDSIGMOID: epilogue_role<T, CSB_ACT_HARDSIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles); break;
-        default: epilogue_role<T, CSB_ACT_NONE>(p, tmem_base, tfull0, tempty0, total_tiles); break;
+        case CSB_ACT_RELU: epilogue_role<T, CSB_ACT_RELU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_SILU: epilogue_role<T, CSB_ACT_SILU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_GELU: epilogue_role<T, CSB_ACT_GELU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_PRELU: epilogue_role<T, CSB_ACT_PRELU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_SIGMOID: epilogue_role<T, CSB_ACT_SIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_SOFTPLUS: epilogue_role<T, CSB_ACT_SOFTPLUS>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_HARDSIGMOID: epilogue_role<T, CSB_ACT_HARDSIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        default: epilogue_role<T, CSB_ACT_NONE>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
     }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                         const ConvKernelParams p) {
+                                                         const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t row_bytes = (uint32_t) p.bk * 2u;
@@ -338,6 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -408,8 +453,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
         }
     } else if (warp >= 4) {
         // ===================================================== epilogue (TMEM -> registers -> global), 8 warps
-        if (p.is_bf16) epilogue_dispatch<__nv_bfloat16>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles);
-        else epilogue_dispatch<__half>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles);
+        if (p.is_bf16) epilogue_dispatch<__nv_bfloat16>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
+        else epilogue_dispatch<__half>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
     }
     tc_fence_before();
     __syncthreads();
@@ -505,19 +550,36 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
 
     const uint32_t row_bytes = p.bk * 2, stage_bytes = ((kBlockM + p.block_n) * row_bytes + 1023u) & ~1023u;
     const int kblocks = p.R * p.S * p.kchunks;
-    int stages = (int) ((200u * 1024u) / stage_bytes);
+    int stages = (int) ((208u * 1024u) / stage_bytes);
     stages = stages > kMaxStages ? kMaxStages : stages;
     stages = stages > kblocks * 2 ? (kblocks * 2 < 2 ? 2 : kblocks * 2) : stages;
     p.stages = stages < 2 ? 2 : stages;
-    const size_t smem = (size_t) p.stages * stage_bytes + 1024 /*align*/ + 8 * (2 * kMaxStages + 2 * kAccStages) + 16;
+    // [stages | barriers + tmem slot | pad to 1 KiB | epilogue staging 8 x 2 KiB]
+    p.stage_off = (uint32_t) (((size_t) p.stages * stage_bytes + 8 * (2 * kMaxStages + 2 * kAccStages) + 16 + 1023) & ~(size_t) 1023);
+    const size_t smem = (size_t) p.stage_off + 8 * 2048 + 1024 /*align*/;
     p.bias = bias; p.act = d->act; p.act_param = act_param;
     p.residual = residual; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.res_mode = d->res_mode;
     p.out = y; p.out_f32 = y_f32; p.out_ld = d->out_ld; p.out_coff = d->out_coff; p.is_bf16 = d->dtype == 1;
+    // Output tensor map for the epilogue's TMA tile stores: the channel slice [out_coff, out_coff + Cout) of the NHWC output, box = 32 channels x
+    // the 32 rows one epilogue warp owns ({32, 32, 1, 1} or {32, bw, 32 / bw, 1}); channels >= Cout and rows outside the image are clipped.
+    static const int store_mode = [] { const char* e = getenv("CSB_TMA_STORE"); return e ? atoi(e) : 1; }();
+    CUtensorMap tmC = tmA;
+    p.tma_store = 0;
+    if (store_mode && y && !y_f32 && d->out_ld % 8 == 0 && d->out_coff % 8 == 0 && ((uintptr_t) y & 15) == 0 && d->Cout >= 32) {
+        const int cbw = p.bw < 32 ? p.bw : 32, cbh = 32 / cbw;
+        cuuint64_t cdim[4] = {(cuuint64_t) d->Cout, (cuuint64_t) p.W, (cuuint64_t) p.H, (cuuint64_t) p.N};
+        cuuint64_t cstr[3] = {(cuuint64_t) d->out_ld * esz, (cuuint64_t) d->out_ld * esz * p.W, (cuuint64_t) d->out_ld * esz * p.W * p.H};
+        cuuint32_t cbox[4] = {32, (cuuint32_t) cbw, (cuuint32_t) cbh, 1}, cestr[4] = {1, 1, 1, 1};
+        char* cbase = reinterpret_cast<char*>(y) + (size_t) d->out_coff * esz;
+        r = enc(&tmC, dt, 4, cbase, cdim, cstr, cbox, cestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                store_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) p.tma_store = store_mode == 1 ? 1 : 2;
+    }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     const int total = p.tiles_m * p.tiles_n;
     const int grid = total < csb::num_sms() ? total : csb::num_sms();
-    k_conv_tc<<<grid, kThreads, smem, (cudaStream_t) stream>>>(tmA, tmB, p);
+    k_conv_tc<<<grid, kThreads, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {           // detailed profile: one key per layer shape
         char label[160];
         snprintf(label, sizeof label, "k_conv_tc[%dx%dx%dx%d->%d k%dx%d s%d d%d g%d act%d res%d]", d->N, d->Hin, d->Win, d->Cin, d->Cout, d->R, d->S, d->stride,
