@@ -4,11 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference ...                     # CPU arm: the oracle port of the same path on the host cores
 
-A "step" is one pass of the hot path over one batch of `--batch` synthetic 1024x1024 input frames.
-Round-1 workload (`config.workload`): the Ken-Burns *warp* leg of BASELINE.json's metric -- per input frame:
-disparity -> point cloud (kenburns_effect.py:928-937), camera shift, z-buffered splat render, disocclusion fill,
-uint8 pack, centre crop + bilinear resize (kenburns_effect.py:1028-1040,1069-1070).  The seg and depth forwards are not on
-the path yet (`config.stages_missing`); raw disparity is a synthetic input until the depth net lands.
+A "step" is one pass of the hot path over one batch of `--batch` synthetic 1024x1024 input frames.  Workload of the headline line
+(`config.workload`, BASELINE.json metric "seg+depth+warp"): per input frame the AnimeInsSeg.infer body (ConvNeXt-B RTMDet-Ins forward,
+decode / NMS / dynamic mask head / x8 mask tail), the depth forward (`--depth leres` default: ResNeXt-101 32x8d + decoder and the
+reference's 16->8 bit tail; `--depth zoe`: DPT-BEiT-L + metric bins head with pad + flip augmentation), instance-guided depth
+flattening, disparity -> point cloud (kenburns_effect.py:928-937), camera shift, z-buffered splat render, disocclusion fill, uint8
+pack, centre crop + bilinear resize (kenburns_effect.py:1028-1040,1069-1070).
+
+The same JSON line carries `other_workloads` (skipped with --no-other), each measured through the reference-facing Python API with
+host buffers on both sides:
+  infer_batch32    BASELINE configs[1]: AnimeInsSeg.infer(list of 32 numpy images), refine off; and with the default-on ISNet refine
+  kenburns_full    BASELINE configs[3]: KenBurnsPipeline.generate_kenburns_config(img) + .autozoom(cfg): seg + depth + 256-candidate
+                   autozoom + 2 inpaint passes + 75 output frames per input image
 
 Timing: W >= 3 warm-up steps, then exactly K steps between barrier + cuda.synchronize; device time from CUDA events on
 the launching stream, max over ranks.  Inputs cycle over `--scenes` distinct scenes whose footprint exceeds the 126 MB L2.
@@ -104,70 +111,148 @@ def cpu_arm(imgs, disp, n_frames, threads):
     return n_frames / (time.perf_counter() - t0)
 
 
+class CpuPath:
+    """The CPU arm: the oracle port of every stage of the workload for ONE input frame (PyTorch fp32 on all host threads for the networks,
+    oracle/kb_oracle.c for the Ken-Burns kernels).  The real reference package cannot run on a CPU at all (mmdet / mmcv / cupy absent in the
+    image; its Ken-Burns kernels are GPU-only cupy strings and anime_3dkenburns/common.py:74 hard-codes .cuda()), so its CPU implementation of
+    this path *is* the port."""
+
+    def __init__(self, stages, depth='leres'):
+        import torch
+        from cartoonsegmentation_b200.animeinsseg import rtmdet
+        from cartoonsegmentation_b200.depth_modules import leres as L
+        from oracle import det_oracle as D, kb_oracle as orc, leres_oracle as LO
+        self.torch, self.D, self.orc, self.LO = torch, D, orc, LO
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.stages = stages
+        self.depth = depth if 'depth' in stages else None
+        self.det = self.ler = None
+        if 'seg' in stages:
+            self.det = D.RTMDetIns().eval(); self.det.load_state_dict(rtmdet.synthetic_state_dict(0))
+        if self.depth == 'leres':
+            self.ler = LO.RelDepthModel().eval(); self.ler.load_state_dict(L.synthetic_state_dict(0), strict=False)
+        elif self.depth == 'zoe':
+            raise SystemExit("--impl reference --depth zoe: the CPU oracle of DPT-BEiT-L @672^2 x 2 flips needs minutes per frame; time the LeReS workload")
+        orc.lib()
+
+    def frame(self, img, raw_synth):
+        torch = self.torch
+        masks = None
+        with torch.no_grad():
+            if self.det is not None:
+                masks = self.D.infer(self.det, img)['masks']
+            raw = self.LO.depth_est_leres(self.ler, img) if self.ler is not None else raw_synth
+            if masks is not None and len(masks):                       # depth_adjustment_animesseg (kenburns_effect.py:39-91)
+                d = torch.from_numpy(raw)[None, None].clone()
+                for m in masks.float():
+                    plane = d * m
+                    if plane.sum().item() == 0:
+                        continue
+                    rows = (plane.sum([3], True) > 0.0).flatten().nonzero()
+                    top, bottom = rows[0].item(), rows[-1].item()
+                    d = ((1.0 - m) * d) + (m * plane[:, :, int(round(top + (0.97 * (bottom - top)))):, :].max())
+                raw = d[0, 0].numpy()
+        if 'warp' in self.stages:
+            return cpu_frame(self.orc, img, np.ascontiguousarray(raw))
+        return None
+
+    def time(self, imgs, disp, steps, warm):
+        for i in range(warm):
+            self.frame(imgs[i % len(imgs)], disp[i % len(disp)])
+        t0 = time.perf_counter()
+        for i in range(steps):
+            self.frame(imgs[i % len(imgs)], disp[i % len(disp)])
+        return (time.perf_counter() - t0) / steps
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the same path on the host cores.  The real package cannot run here (mmdet /
-    mmcv / cupy absent, its Ken-Burns kernels are GPU-only cupy strings, anime_3dkenburns/common.py:74 hard-codes .cuda()), so this is the
-    oracle port: oracle/det_oracle.py (PyTorch fp32, all host threads) -> oracle/leres_oracle.py -> oracle/kb_oracle.c, one image per step."""
+    """--impl reference: CpuPath, one image per step, on all host threads; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import torch
-    from cartoonsegmentation_b200.animeinsseg import rtmdet
-    from cartoonsegmentation_b200.depth_modules import leres as L
-    from oracle import det_oracle as D, kb_oracle as orc, leres_oracle as LO
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     stages = [s_ for s_ in args.stages.split(",") if s_]
     imgs, disp = make_inputs(2)
-    det = D.RTMDetIns().eval(); det.load_state_dict(rtmdet.synthetic_state_dict(0))
-    ler = LO.RelDepthModel().eval(); ler.load_state_dict(L.synthetic_state_dict(0), strict=False)
-
-    def one(i):
-        img = imgs[i % 2]
-        masks = None
-        if 'seg' in stages:
-            masks = D.infer(det, img)['masks']
-        raw = LO.depth_est_leres(ler, img) if 'depth' in stages else disp[i % 2]
-        if masks is not None and len(masks):                       # depth_adjustment_animesseg (kenburns_effect.py:39-91)
-            d = torch.from_numpy(raw)[None, None].clone()
-            for m in masks.float():
-                plane = d * m
-                if plane.sum().item() == 0:
-                    continue
-                rows = (plane.sum([3], True) > 0.0).flatten().nonzero()
-                top, bottom = rows[0].item(), rows[-1].item()
-                d = ((1.0 - m) * d) + (m * plane[:, :, int(round(top + (0.97 * (bottom - top)))):, :].max())
-            raw = d[0, 0].numpy()
-        if 'warp' in stages:
-            cpu_frame(orc, img, np.ascontiguousarray(raw))
-    steps, warm = max(1, min(args.steps, 2)), min(args.warmup, 1)
-    for i in range(warm):
-        one(i)
-    t0 = time.perf_counter()
-    for i in range(steps):
-        one(i)
-    dt = time.perf_counter() - t0
-    fps = steps / dt
+    cpu = CpuPath(stages, args.depth)
+    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    sec = cpu.time(imgs, disp, steps, warm)
+    fps = 1.0 / sec
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": 1000.0 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(1, 2, stages),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} step(s) x 1 frame of 1024x1024 through the oracle port of every stage (PyTorch fp32 on {cores} threads + C)"},
+        "ms_per_step": 1000.0 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, 2, stages, args.depth),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
+                         "sample": f"{steps} step(s) x 1 frame of 1024x1024 through the oracle port of every stage (PyTorch fp32 on {cpu.cores} threads + C)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
 
 
-def workload_config(batch, scenes, stages=("seg", "depth", "warp")):
+def workload_config(batch, scenes, stages=("seg", "depth", "warp"), depth="leres"):
     names = {"seg": "AnimeInsSeg.infer body (ConvNeXt-B RTMDet-Ins forward @1024^2, det_size=1024, random-init seeded weights, decode/NMS/mask head/mask tail, "
                     "max_instances=100, refine off)",
-             "depth": "LeReS depth (ResNeXt-101 32x8d + decoder @640^2) + reference host-side 16->8 bit quantisation + instance-guided depth flattening",
+             "depth": ("LeReS depth (ResNeXt-101 32x8d + decoder @640^2) + the reference's 16->8 bit quantisation tail" if depth == "leres" else
+                       "ZoeDepth (DPT-BEiT-L @672^2, reflect pad + flip augmentation = 2 net inputs per frame, metric bins head, depth->disparity)")
+                      + " + instance-guided depth flattening",
              "warp": "disparity->cloud + camera shift + z-buffered render (C=4) + disocclusion fill + u8 pack + centre crop/resize: one Ken-Burns frame"}
     missing = [v for k, v in {"seg": "seg", "depth": "depth (raw disparity is then a synthetic input)", "warp": "warp"}.items() if k not in stages]
-    missing += ["ISNet mask refine (A10)", "Inpaint net + autozoom (C4-C6: per-image, not per-frame)"]
+    missing += ["ISNet mask refine (A10) and Inpaint net + autozoom (C4-C6) are per-image, not per-frame: measured in other_workloads"]
     return {"workload": "per input frame @1024x1024: " + " -> ".join(names[s_] for s_ in ("seg", "depth", "warp") if s_ in stages),
-            "stages": list(stages), "stages_missing": missing, "frame": [H, W], "batch_frames_per_step": batch, "focal": FOCAL, "baseline": BASELINE,
+            "stages": list(stages), "depth": depth if "depth" in stages else None, "stages_missing": missing, "frame": [H, W], "batch_frames_per_step": batch, "focal": FOCAL, "baseline": BASELINE,
             "l2_policy": f"inputs cycle over {scenes} distinct scenes; every frame streams > 126 MB of intermediates, so no input survives in L2 between uses"}
+
+
+# ------------------------------------------------------------------------------------------------ API-level workloads (BASELINE configs[1], [3])
+def run_other(pipe, imgs_np, args):
+    """Workloads measured through the reference-facing Python API, host numpy in / host numpy (or AnimeInstances) out, CUDA events around the
+    calls (the host gaps between launches are inside the timed region)."""
+    import torch
+    seg = pipe.animeinsseg
+    S = len(imgs_np)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), r
+
+    res = {}
+    # ---- BASELINE configs[1]: AnimeInsSeg.infer on a batch (python list) of 32 images of 1024x1024, det_size 1024
+    lst = [imgs_np[i % S] for i in range(32)]
+    off = {'refine_method': 'none'}
+    seg.infer(lst[:8], 0.3, off, 'tensor', det_size=H)
+    ms, inst = timed(lambda: seg.infer(lst, 0.3, off, 'tensor', det_size=H))
+    K = float(np.mean([len(i) for i in inst]))
+    res["infer_batch32"] = {"api": "AnimeInsSeg.infer(list of 32 ndarray 1024x1024x3, pred_score_thr=0.3, refine off, output_type='tensor', det_size=1024)",
+                            "frames_per_s": 32 / (ms * 1e-3), "ms": ms, "instances_per_image": K, "h2d_bytes": 32 * H * W * 3}
+    del inst
+    # ---- the same with the reference's default-on ISNet refinement (A10): 159.5 GFLOP per instance at 720^2
+    n_ref = 4
+    on = {'refine_method': 'refinenet_isnet'}
+    seg.infer(lst[:1], 0.3, on, 'tensor', det_size=H)
+    ms, inst = timed(lambda: seg.infer(lst[:n_ref], 0.3, on, 'tensor', det_size=H))
+    K = float(np.mean([len(i) for i in inst]))
+    res["infer_refine_isnet"] = {"api": f"AnimeInsSeg.infer(list of {n_ref} ndarray 1024x1024x3, refine_method='refinenet_isnet' (reference default), det_size=1024)",
+                                 "frames_per_s": n_ref / (ms * 1e-3), "ms": ms, "instances_per_image": K,
+                                 "isnet_tflops": 159.5e-3 * K * n_ref / (ms * 1e-3)}
+    del inst
+    seg.set_refine_method('none')
+    # ---- BASELINE configs[3]: full 3D Ken Burns per input image: seg + depth + adjust + cloud + autozoom (256 candidate renders) + 2 inpaint passes
+    #      + num_frame (75) output frames, uint8 frames returned on the host (run_kenburns.py:19-33)
+    n_img = max(1, args.other_images)
+
+    def kb_image(i):
+        kcfg = pipe.generate_kenburns_config(imgs_np[i % S])
+        return pipe.autozoom(kcfg)
+    kb_image(0)
+    ms, frames = timed(lambda: [len(kb_image(1 + i)) for i in range(n_img)])
+    res["kenburns_full"] = {"api": "KenBurnsPipeline.generate_kenburns_config(img) + .autozoom(cfg): seg + depth(%s) + autozoom + 2 x inpaint + %d frames, "
+                                   "host ndarray in, list of host uint8 frames out" % (pipe.cfg.depth_est, pipe.cfg.num_frame),
+                            "input_images_per_s": n_img / (ms * 1e-3), "output_frames_per_s": sum(frames) / (ms * 1e-3), "ms_per_image": ms / n_img,
+                            "images": n_img, "h2d_bytes_per_image": H * W * 3, "d2h_bytes_per_image": pipe.cfg.num_frame * H * W * 3}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -180,7 +265,10 @@ def main():
     ap.add_argument("--scenes", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--stages", default="seg,depth,warp", help="comma list out of seg,depth,warp (default: the full metric)")
+    ap.add_argument("--depth", default="leres", choices=["leres", "zoe"], help="depth estimator of the depth stage (reference: KenBurnsConfig.depth_est)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip other_workloads (infer_batch32, kenburns_full)")
+    ap.add_argument("--other-images", type=int, default=3, help="input images of the kenburns_full workload")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -203,7 +291,7 @@ def main():
     B, S = args.batch, args.scenes
 
     # ---- the reference call surface: one pipeline object per rank, weights replicated from the same seed
-    cfg = kb.KenBurnsConfig(det_size=H, max_size=H, depth_est='leres' if 'depth' in stages else 'external', depth_est_size=640, pred_score_thr=0.3)
+    cfg = kb.KenBurnsConfig(det_size=H, max_size=H, depth_est=args.depth if 'depth' in stages else 'external', depth_est_size=640, pred_score_thr=0.3)
     pipe = kb.KenBurnsPipeline(cfg, device=dev)
     seg = pipe.animeinsseg
     seg.set_detect_size(H)
@@ -225,6 +313,7 @@ def main():
     cd = ctypes.c_double
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     seg_sub = int(os.environ.get("CSB_SEG_SUB", "32"))              # detector sub-batch (activations of 32 x 1024^2 ~ 12 GB of the 180 GB)
+    zoe_sub = int(os.environ.get("CSB_ZOE_SUB", "16"))              # ZoeDepth sub-batch (2 net inputs of 672^2 per frame)
     stats = {"instances": 0}
 
     def warp(img_u8, raw, out, slot):
@@ -248,8 +337,14 @@ def main():
             batch = imgs_dev[idx] if 'seg' in stages or 'depth' in stages else None
         masks = nums = nums_dev = None
         depth_handle = None
-        if 'depth' in stages:                                        # LeReS forward + D2H of its logits enqueued FIRST, so that the reference's
-            depth_handle = pipe.leres_enqueue(None, imgs_dev=batch)  # host-side tail (below) overlaps with the detector running on the GPU
+        disp = None
+        if 'depth' in stages and args.depth == 'leres':              # LeReS forward + the reference's quantisation tail, all on the device
+            depth_handle = pipe.leres_enqueue(None, imgs_dev=batch)
+        elif 'depth' in stages:                                      # ZoeDepth.infer(pad_input, with_flip_aug) + _depth_est_zoe's depth -> disparity
+            disp = []
+            for s0 in range(0, B, zoe_sub):
+                d = pipe.depth_zoe.infer_batch(batch[s0:s0 + zoe_sub])
+                disp += [pipe.depth_zoe.disparity(d[i], FOCAL, BASELINE) for i in range(d.shape[0])]
         if 'seg' in stages:                                          # AnimeInsSeg.infer body: detector forward + post-process (A1-A9)
             masks, nums_dev = [], []
             for s0 in range(0, B, seg_sub):
@@ -257,8 +352,7 @@ def main():
                 cls, reg, ker, mf = seg.model.net.forward(sub)
                 o = rtmdet_postprocess(cls, reg, ker, mf, (H, W), test_cfg)
                 masks.append(o['masks']); nums_dev.append(o['num'])
-        disp = None
-        if depth_handle is not None:                                 # the reference's host-side quantisation tail (B5) while the GPU runs the detector
+        if depth_handle is not None:
             disp = pipe.leres_finish(depth_handle)
         if 'seg' in stages:
             nums = torch.cat(nums_dev).cpu().tolist()                # the one host read of the seg stage (instance counts for the caller)
@@ -309,6 +403,8 @@ def main():
     lib.csb_profile_end(buf, len(buf))
     prof = json.loads(buf.value.decode())
 
+    other = run_other(pipe, imgs_np, args) if (world == 1 and not args.no_other) else None
+
     # throughput counters: ONE all-gather of a per-rank struct over NCCL/NVLink
     frames = args.steps * B
     gathered = gather_counters(torch.tensor([frames, ms, ms_e2e], device=dev, dtype=torch.float64))
@@ -327,7 +423,11 @@ def main():
         if dom == "k_conv_tc":
             # algorithmic FLOPs of the tensor-core launches of one step: detector 1011.9 GFLOP / image @1024^2 (ConvNeXt-B 641.7 + neck 132.2
             # + head 237.9), LeReS 591.9 GFLOP / image @640^2 input
-            gflop = (1011.9 if 'seg' in stages else 0.0) * B + (591.9 if 'depth' in stages else 0.0) * B
+            # ZoeDepth on k_conv_tc: per 672^2 net input, T = 1765 tokens, D = 1024: 24 blocks x 12 T D^2 MAC of Linear layers + ~291 GFLOP of DPT
+            # reassemble / fusion / head convs (the 4 T^2 D attention MACs run on k_attention and are NOT counted here); 2 net inputs per frame
+            zoe_gflop = 2 * (24 * 1765 * 12 * 1024 * 1024 * 2 / 1e9 + 291.0)
+            depth_gflop = 0.0 if 'depth' not in stages else (591.9 if args.depth == 'leres' else zoe_gflop)
+            gflop = (1011.9 if 'seg' in stages else 0.0) * B + depth_gflop * B
             ach = gflop / prof[dom]["ms"]                             # GFLOP / ms = TFLOP/s
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
                     "peak_source": "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback",
@@ -342,20 +442,28 @@ def main():
                     "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "algorithmic_bytes_per_launch": ab}
         if roof is not None:
             roof["per_kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-        h2d = B * H * W * 3 + (0 if 'depth' in stages else 0)
-        d2h = (B * H * W * 3 if 'warp' in stages else 0) + (B * 640 * 640 * 4 if 'depth' in stages else 0)
+        h2d = B * H * W * 3                                           # the uint8 BGR frames; every later stage stays on the device
+        d2h = (B * H * W * 3 if 'warp' in stages else 0) + (4 * B if 'seg' in stages else 0)     # rendered uint8 frames + instance counts
         out = {"metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate) / f32 render",
-               "data": "synthetic", "config": workload_config(B, S, stages), "clocks": clocks,
-               "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d + (B * H * W * 4 if 'depth' in stages else 0),
-                       "d2h_bytes_per_step": d2h},
+               "data": "synthetic", "config": workload_config(B, S, stages, args.depth), "clocks": clocks,
+               "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": launches, "roofline": roof,
                "instances_per_image": stats["instances"] / max(1, (args.warmup + 1 + 2 * args.steps + 1) * B) if 'seg' in stages else None}
+        if world == 1 and not args.no_other:
+            out["other_workloads"] = other
         if world == 1 and not args.no_cpu_baseline:
-            n = 4
-            out["cpu_baseline"] = {"value": cpu_arm(imgs_np[:2], disp_np[:2], n, 1), "unit": "frames/s", "cores": 1, "kind": "port",
-                                   "sample": f"{n} frames of 1024x1024 on 1 thread through the WARP stage only (oracle/kb_oracle.c, scalar C port); the seg/depth "
-                                             "oracles are PyTorch fp32 and are timed by --impl reference"}
+            # the oracle port of the SAME workload (all stages) on the box's host cores, a bounded sample: 1 warm-up + 2 timed frames
+            if args.depth == 'leres':
+                cpu = CpuPath(stages, 'leres')
+                sec = cpu.time(imgs_np[:2], disp_np[:2], 2, 1)
+                out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
+                                       "sample": f"2 frames of 1024x1024 (after 1 warm-up) through every stage of the workload: oracle/det_oracle.py + oracle/leres_oracle.py "
+                                                 f"(PyTorch fp32, {cpu.cores} threads) + oracle/kb_oracle.c (scalar C)"}
+            else:
+                out["cpu_baseline"] = {"value": cpu_arm(imgs_np[:2], disp_np[:2], 4, 1), "unit": "frames/s", "cores": 1, "kind": "port",
+                                       "sample": "4 frames of 1024x1024 on 1 thread through the WARP stage only (oracle/kb_oracle.c); the DPT-BEiT-L CPU oracle @672^2 "
+                                                 "needs minutes per frame -- run the default --depth leres workload for an all-stage CPU baseline"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -313,7 +313,7 @@ class KenBurnsPipeline:
                 if ckpt is not None:                                         # ZoeD_M12_N.pt: {'model': state_dict} (model_io.py:49-58)
                     obj = torch.load(ckpt, map_location='cpu')
                     sd = obj.get('model', obj)
-                self.depth_zoe = ZoeDepth(sd, self.device)
+                self.depth_zoe = ZoeDepth(sd, self.device, img_size=[672, 672])               # reference :543
             self.depth_model = lambda img, img_tensor: self._depth_est_zoe(img_tensor, img)
 
     def _depth_est_zoe(self, img_tensor, img, *args, **kwargs):

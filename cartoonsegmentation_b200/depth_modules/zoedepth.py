@@ -332,8 +332,10 @@ class BeitDPT:
 
 
 def midas_net_size(h, w, net=384, multiple=32):
-    """`Resize(net, net, keep_aspect_ratio=True, ensure_multiple_of=32, resize_method='minimal').get_size` (midas.py:104-148)"""
-    sh, sw = net / h, net / w
+    """`Resize(net_w, net_h, keep_aspect_ratio=True, ensure_multiple_of=32, resize_method='minimal').get_size` (midas.py:104-148); `net` is the
+    config's `img_size` = int or (net_h, net_w) (midas.py:177-179)"""
+    net_h, net_w = (net, net) if isinstance(net, int) else (int(net[0]), int(net[1]))
+    sh, sw = net_h / h, net_w / w
     if abs(1 - sw) < abs(1 - sh):
         sh = sw
     else:
@@ -346,8 +348,11 @@ class ZoeDepth:
     """`ZoeDepth.infer(x, pad_input=True, with_flip_aug=True)` of the reference (depth_model.py:114-129) for one [H,W,3] uint8 image on the device
     (the reference passes BGR/255 without reordering, kenburns_effect.py:813 -- kept): -> metric depth [H,W] fp32."""
 
-    def __init__(self, state_dict=None, device='cuda'):
+    def __init__(self, state_dict=None, device='cuda', img_size=384):
+        """`img_size`: the MidasCore input resolution (midas.py:336-339; 384 when the config has none).  The reference's Ken-Burns pipeline
+        loads ZoeDepth with img_size=[672, 672] (kenburns_effect.py:543); `load_zoe` alone defaults to [512, 672] (depth_modules/__init__.py:40)."""
         dev = self.dev = torch.device(device)
+        self.img_size = img_size
         core = head = None
         if state_dict is not None:
             core = {k[len("core.core."):]: v for k, v in state_dict.items() if k.startswith("core.core.")}
@@ -360,7 +365,7 @@ class ZoeDepth:
         H, W = img_u8.shape[:2]
         ph = int(np.sqrt(H / 2) * 3) if pad_input else 0                                           # depth_model.py:81-82 (fh = fw = 3)
         pw = int(np.sqrt(W / 2) * 3) if pad_input else 0
-        Hn, Wn = midas_net_size(H + 2 * ph, W + 2 * pw)
+        Hn, Wn = midas_net_size(H + 2 * ph, W + 2 * pw, self.img_size)
         nb = 2 if with_flip_aug else 1
         patches = torch.empty((nb, Hn // 16, Wn // 16, 768), device=self.dev, dtype=torch.float16)
         check(lib().csb_zoe_prep(ptr(img_u8.contiguous()), H, W, ph, pw, Hn, Wn, int(with_flip_aug), ptr(patches), stream()), "csb_zoe_prep")
@@ -376,7 +381,7 @@ class ZoeDepth:
         Bn, H, W = imgs_u8.shape[:3]
         ph = int(np.sqrt(H / 2) * 3) if pad_input else 0
         pw = int(np.sqrt(W / 2) * 3) if pad_input else 0
-        Hn, Wn = midas_net_size(H + 2 * ph, W + 2 * pw)
+        Hn, Wn = midas_net_size(H + 2 * ph, W + 2 * pw, self.img_size)
         nb = 2 if with_flip_aug else 1
         imgs_u8 = imgs_u8.contiguous()
         patches = torch.empty((Bn * nb, Hn // 16, Wn // 16, 768), device=self.dev, dtype=torch.float16)
