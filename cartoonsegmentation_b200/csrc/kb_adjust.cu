@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) k_adjp_cover(const float* __restrict__ di
     const long long HW = (long long) H * W;
     const float* D = disp + (long long) img * HW;
     const uint8_t* M = masks + (long long) img * Kmax * HW;
-    unsigned* C = cover + (long long) img * HW * Kw;
+    unsigned* C = cover + (long long) img * HW * Kw;                      // word-planar: C[w * HW + pixel]
     bool fail = false;
     for (long long sgm = (long long) blockIdx.x * nwarp + warp; sgm < (long long) H * segs; sgm += (long long) gridDim.x * nwarp) {
         const int y = (int) (sgm / segs), x = (int) (sgm % segs) * 128 + lane * 4;
@@ -215,9 +215,99 @@ __global__ void __launch_bounds__(256) k_adjp_cover(const float* __restrict__ di
             for (int j = 0; j < 4; ++j) {
                 const unsigned any = c[j][0] | c[j][1] | c[j][2] | c[j][3];
                 if (any && !(dv[j] > 0.f)) fail = true;
+            }
 #pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    if (w < Kw) C[(p + j) * Kw + w] = c[j][w];
+            for (int w = 0; w < 4; ++w)
+                if (w < Kw) *reinterpret_cast<uint4*>(C + (long long) w * HW + p) = make_uint4(c[0][w], c[1][w], c[2][w], c[3][w]);
+        }
+    }
+    if (fail) s_fail = 1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        if (s_bot[k] >= 0) {
+            atomicMin(tops + img * Kmax + k, s_top[k]);
+            atomicMax(bottoms + img * Kmax + k, s_bot[k]);
+        }
+    }
+    if (threadIdx.x == 0 && s_fail) atomicOr(need, 1);
+}
+
+// W % 16 == 0: 16 pixels per thread.  The version above is latency-bound (one 4 B mask load in flight per thread: 0.8 TB/s of the 1 B/px x K mask
+// stream); here every thread issues eight independent 16 B loads (eight instances) before it touches them, and the byte -> bit transposition is
+// word-parallel: masks are 0/1 bytes, so `acc |= m << i` (i < 8) gathers eight instances of four pixels in one instruction without crossing bytes.
+__global__ void __launch_bounds__(256) k_adjp_cover16(const float* __restrict__ disp, const uint8_t* __restrict__ masks, const int* __restrict__ num, int Kmax, int H,
+                                                      int W, int Kw, int* __restrict__ tops, int* __restrict__ bottoms, unsigned* __restrict__ cover,
+                                                      int* __restrict__ need) {
+    __shared__ int s_top[kParMaxK], s_bot[kParMaxK];
+    __shared__ int s_fail;
+    const int img = blockIdx.y, K = min(num[img], Kmax);
+    for (int i = threadIdx.x; i < kParMaxK; i += blockDim.x) { s_top[i] = 0x7fffffff; s_bot[i] = -1; }
+    if (threadIdx.x == 0) s_fail = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int segs = (W + 511) / 512;
+    const long long HW = (long long) H * W;
+    const float* D = disp + (long long) img * HW;
+    const uint8_t* M = masks + (long long) img * Kmax * HW;
+    unsigned* C = cover + (long long) img * HW * Kw;
+    bool fail = false;
+    for (long long sgm = (long long) blockIdx.x * nwarp + warp; sgm < (long long) H * segs; sgm += (long long) gridDim.x * nwarp) {
+        const int y = (int) (sgm / segs), x = (int) (sgm % segs) * 512 + lane * 16;
+        const bool valid = x < W;                                      // W % 16 == 0
+        const long long p = (long long) y * W + x;
+        unsigned covered = 0u;                                         // bit j: pixel j is under some mask
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            if (wi * 32 >= K) break;                                   // warp-uniform
+            unsigned cw[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) cw[j] = 0u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int k0 = wi * 32 + g * 8;
+                if (k0 >= K) break;                                    // warp-uniform
+                uint4 m[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    m[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid && k0 + i < K) m[i] = __ldg(reinterpret_cast<const uint4*>(M + (long long) (k0 + i) * HW + p));
+                }
+                unsigned a[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned b = __ballot_sync(0xffffffffu, (m[i].x | m[i].y | m[i].z | m[i].w) != 0u);
+                    if (lane == 0 && b) {
+                        if (y < s_top[k0 + i]) atomicMin(&s_top[k0 + i], y);
+                        if (y > s_bot[k0 + i]) atomicMax(&s_bot[k0 + i], y);
+                    }
+                    a[0] |= m[i].x << i; a[1] |= m[i].y << i; a[2] |= m[i].z << i; a[3] |= m[i].w << i;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) cw[4 * q + jj] |= ((a[q] >> (8 * jj)) & 0xffu) << (8 * g);
+            }
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(C + (long long) wi * HW + p + 4 * q) = make_uint4(cw[4 * q], cw[4 * q + 1], cw[4 * q + 2], cw[4 * q + 3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) covered |= (cw[j] != 0u ? 1u : 0u) << j;
+        }
+        if (valid) {
+            for (int wi = (K + 31) / 32; wi < Kw; ++wi)                // words beyond this image's instance count
+#pragma unroll
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(C + (long long) wi * HW + p + 4 * q) = make_uint4(0u, 0u, 0u, 0u);
+            if (covered) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 d = *reinterpret_cast<const float4*>(D + p + 4 * q);
+                    if (((covered >> (4 * q)) & 1u) && !(d.x > 0.f)) fail = true;
+                    if (((covered >> (4 * q + 1)) & 1u) && !(d.y > 0.f)) fail = true;
+                    if (((covered >> (4 * q + 2)) & 1u) && !(d.z > 0.f)) fail = true;
+                    if (((covered >> (4 * q + 3)) & 1u) && !(d.w > 0.f)) fail = true;
+                }
             }
         }
     }
@@ -232,6 +322,10 @@ __global__ void __launch_bounds__(256) k_adjp_cover(const float* __restrict__ di
     if (threadIdx.x == 0 && s_fail) atomicOr(need, 1);
 }
 
+
+// One CTA walks whole rows.  Only instances whose bottom band (rows >= cut_k) contains the row matter, so the row's K-bit band mask is built first and
+// ANDed with the cover word: the vast majority of pixels leave after four coalesced loads (the previous version walked every set bit of every
+// pixel).  pred(q, k) = the highest covering index below k, from the FULL cover word.
 __global__ void __launch_bounds__(256) k_adjp_rel(const float* __restrict__ disp, const int* __restrict__ num, int Kmax, int H, int W, int Kw,
                                                   const int* __restrict__ tops, const int* __restrict__ bottoms, const unsigned* __restrict__ cover,
                                                   unsigned* __restrict__ base, unsigned* __restrict__ rel, const int* __restrict__ need) {
@@ -239,6 +333,7 @@ __global__ void __launch_bounds__(256) k_adjp_rel(const float* __restrict__ disp
     __shared__ int s_cut[kParMaxK];
     __shared__ unsigned s_base[kParMaxK];
     __shared__ unsigned s_rel[kParMaxK * 4];
+    __shared__ unsigned s_band[4];
     const int img = blockIdx.y, K = min(num[img], Kmax);
     for (int k = threadIdx.x; k < kParMaxK; k += blockDim.x) {
         int cut = 0x7fffffff;
@@ -253,30 +348,48 @@ __global__ void __launch_bounds__(256) k_adjp_rel(const float* __restrict__ disp
     __syncthreads();
     const long long HW = (long long) H * W;
     const float* D = disp + (long long) img * HW;
-    const unsigned* C = cover + (long long) img * HW * Kw;
-    for (long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long) gridDim.x * blockDim.x) {
-        const int y = (int) (p / W);
-        int prev = -1;
-        for (int wi = 0; wi < Kw; ++wi) {
-            unsigned w = C[p * Kw + wi];
-            while (w) {
-                const int k = wi * 32 + (__ffs(w) - 1);
-                w &= w - 1;
-                if (y >= s_cut[k]) {
-                    if (prev < 0) {
-                        const unsigned u = __float_as_uint(D[p]);             // > 0: bit patterns order like the values
-                        if (u > s_base[k]) atomicMax(&s_base[k], u);
-                    } else {
-                        const unsigned bit = 1u << (prev & 31);
-                        const int idx = k * 4 + (prev >> 5);
-                        if (!(s_rel[idx] & bit)) atomicOr(&s_rel[idx], bit);
+    const unsigned* C = cover + (long long) img * HW * Kw;                // word-planar
+    for (int y = blockIdx.x; y < H; y += gridDim.x) {
+        if (threadIdx.x < kParMaxK) {                                     // warps 0..3: band bit k = (y >= cut_k)
+            const unsigned b = __ballot_sync(0xffffffffu, y >= s_cut[threadIdx.x]);
+            if ((threadIdx.x & 31) == 0) s_band[threadIdx.x >> 5] = b;
+        }
+        __syncthreads();
+        const unsigned band[4] = {s_band[0], s_band[1], s_band[2], s_band[3]};
+        if (band[0] | band[1] | band[2] | band[3]) {
+            for (int x = threadIdx.x; x < W; x += blockDim.x) {
+                const long long p = (long long) y * W + x;
+                unsigned cw[4], lowprev[4];
+                int lp = -1;
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    cw[wi] = wi < Kw ? C[(long long) wi * HW + p] : 0u;
+                    lowprev[wi] = (unsigned) lp;                          // highest covering index in the words below wi (or -1)
+                    if (cw[wi]) lp = wi * 32 + 31 - __clz(cw[wi]);
+                }
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    unsigned r = cw[wi] & band[wi];
+                    while (r) {
+                        const int b = __ffs(r) - 1;
+                        r &= r - 1;
+                        const int k = wi * 32 + b;
+                        const unsigned lower = cw[wi] & ((1u << b) - 1u);
+                        const int prev = lower ? wi * 32 + 31 - __clz(lower) : (int) lowprev[wi];
+                        if (prev < 0) {
+                            const unsigned u = __float_as_uint(D[p]);             // > 0: bit patterns order like the values
+                            if (u > s_base[k]) atomicMax(&s_base[k], u);
+                        } else {
+                            const unsigned bit = 1u << (prev & 31);
+                            const int idx = k * 4 + (prev >> 5);
+                            if (!(s_rel[idx] & bit)) atomicOr(&s_rel[idx], bit);
+                        }
                     }
                 }
-                prev = k;
             }
         }
+        __syncthreads();                                                  // s_band is rewritten for the next row
     }
-    __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x)
         if (s_base[k]) atomicMax(base + img * Kmax + k, s_base[k]);
     for (int i = threadIdx.x; i < K * 4; i += blockDim.x)
@@ -315,7 +428,7 @@ __global__ void __launch_bounds__(256) k_adjp_apply(float* __restrict__ disp, in
     const unsigned* C = cover + (long long) img * HW * Kw;
     for (long long p = (long long) blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long) gridDim.x * blockDim.x) {
         for (int wi = Kw - 1; wi >= 0; --wi) {
-            const unsigned w = C[p * Kw + wi];
+            const unsigned w = C[(long long) wi * HW + p];
             if (w) {
                 D[p] = __uint_as_float(vbits[img * Kmax + wi * 32 + 31 - __clz(w)]);
                 break;
@@ -326,12 +439,12 @@ __global__ void __launch_bounds__(256) k_adjp_apply(float* __restrict__ disp, in
 
 }  // namespace
 
-// state (int32 words): [tops | mtops | bottoms | mbottoms | vbits] x (N*Kmax), bars [N], need [4], base [N*Kmax], rel [N*Kmax*4], cover [N*H*W*Kw]
+// state (int32 words): [tops | mtops | bottoms | mbottoms | vbits] x (N*Kmax), bars [N], need [4], base [N*Kmax], rel [N*Kmax*4], (pad to 16 B) cover [N][Kw][H*W]
 extern "C" long long csb_depth_adjust_state_words(int N, int Kmax, int H, int W) {
     const long long slots = (long long) N * Kmax;
     const long long Kw = (Kmax + 31) / 32;
     long long words = 5 * slots + N + 4 + slots + slots * 4;
-    if (Kmax <= kParMaxK && W % 4 == 0) words += (long long) N * H * W * Kw;
+    if (Kmax <= kParMaxK && W % 4 == 0) words += 3 + (long long) N * H * W * Kw;      // + alignment of the cover planes
     return words;
 }
 
@@ -352,7 +465,7 @@ extern "C" int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, co
     int* need = state + 5 * slots + N;
     unsigned* base = reinterpret_cast<unsigned*>(need + 4);
     unsigned* rel = base + slots;
-    unsigned* cover = rel + slots * 4;
+    unsigned* cover = reinterpret_cast<unsigned*>(state) + ((10 * slots + N + 4 + 3) & ~(size_t) 3);       // 16 B aligned (uint4 plane stores)
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(tops, 0x7f, sizeof(int) * 2 * slots, st), "memset"));
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(bottoms, 0xff, sizeof(int) * 2 * slots, st), "memset"));
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(vbits, 0, sizeof(int) * (slots + N + 4 + slots + slots * 4), st), "memset"));
@@ -362,8 +475,11 @@ extern "C" int csb_depth_adjust_batch(float* disparity, const uint8_t* masks, co
         const int Kw = (Kmax + 31) / 32;
         int gx = (4 * csb::num_sms() + N - 1) / N;
         gx = gx < 1 ? 1 : gx;
-        k_adjp_cover<<<dim3(gx, N), 256, 0, st>>>(disparity, masks, num, Kmax, H, W, Kw, mtops, mbottoms, cover, need);      // mask-row extents: the
-        // sequential kernel computes the same values into the same slots, so a fallback run is not disturbed
+        // mask-row extents: the sequential kernel computes the same values into the same slots, so a fallback run is not disturbed
+        if (W % 16 == 0 && ((uintptr_t) masks & 15) == 0 && ((long long) H * W) % 16 == 0)
+            k_adjp_cover16<<<dim3(gx, N), 256, 0, st>>>(disparity, masks, num, Kmax, H, W, Kw, mtops, mbottoms, cover, need);
+        else
+            k_adjp_cover<<<dim3(gx, N), 256, 0, st>>>(disparity, masks, num, Kmax, H, W, Kw, mtops, mbottoms, cover, need);
         CSB_TRY(csb::launched("k_adjp_cover", st));
         k_adjp_rel<<<dim3(gx, N), 256, 0, st>>>(disparity, num, Kmax, H, W, Kw, mtops, mbottoms, cover, base, rel, need);
         CSB_TRY(csb::launched("k_adjp_rel", st));
