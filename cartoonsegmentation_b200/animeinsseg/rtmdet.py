@@ -7,8 +7,9 @@ Everything runs NHWC fp16 with fp32 accumulation:
     of the regression branch folded into the packed weights, and bias + SiLU/GELU/ReLU + residual fused into its epilogue;
   * sibling convs that read the same tensor are fused along Cout (CSPLayer main+short, the three head towers' first conv);
   * concats never copy: producers write straight into channel slices of the concat buffer (out_coff), consumers read slices (in_coff);
-  * depthwise 7x7 + LayerNorm, depthwise 5x5 + BN + SiLU, LayerNorm2d, nearest / bilinear resampling are the HBM-bound kernels of
-    csrc/nn_elem.cu.
+  * depthwise 7x7 (+ LayerNorm), depthwise 5x5 + BN + SiLU, LayerNorm2d, nearest / bilinear resampling are the HBM-bound kernels of
+    csrc/nn_elem.cu; the LayerNorm of every ConvNeXt block is folded into the fc1 GEMM (the depthwise kernel emits per-pixel partial
+    statistics, the GEMM epilogue applies rstd * (acc - mean * colsum) + bias'), so no LayerNorm pass touches the activations.
 
 Parameters come in as a state_dict keyed by mmdet's parameter names (`backbone.*`, `neck.*`, `bbox_head.*`), so a real checkpoint
 drops in; `synthetic_state_dict` generates the seeded variance-preserving weights BASELINE.json asks for.
@@ -24,6 +25,8 @@ MEAN_BGR, STD_BGR = (103.53, 116.28, 123.675), (57.375, 57.12, 58.395)      # rt
 DEPTHS, DIMS = (3, 3, 27, 3), (128, 256, 512, 1024)
 STRIDES = (8, 16, 32)
 NUM_GEN_PARAMS = 169
+import os as _os
+FOLD_LN = _os.environ.get("CSB_FOLD_LN", "1") != "0"        # ConvNeXt block: LayerNorm applied in the fc1 GEMM epilogue (engine.fold_layernorm)
 
 
 # ------------------------------------------------------------------------------------------------ parameter inventory
@@ -287,7 +290,9 @@ class RTMDetIns:
                 p = f"backbone.stages.{i}.{b}"
                 gamma = sd[f"{p}.gamma"].float()
                 dw = f32(sd[f"{p}.depthwise_conv.weight"][:, 0].permute(1, 2, 0))                  # [7,7,C]
-                st.append(dict(dw=dw, dwb=f32(sd[f"{p}.depthwise_conv.bias"]), ln=(f32(sd[f"{p}.norm.weight"]), f32(sd[f"{p}.norm.bias"])),
+                # LayerNorm folded into fc1 (csb_conv2d_ln_nhwc): W' = W diag(gamma), b' = b + W beta, column sums of the rounded W'
+                wl, bl, cs = E.fold_layernorm(sd[f"{p}.pointwise_conv1.weight"], sd[f"{p}.pointwise_conv1.bias"], sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"])
+                st.append(dict(dw=dw, fc1_ln=(wl.to(dev), bl.to(dev), cs.to(dev)), dwb=f32(sd[f"{p}.depthwise_conv.bias"]), ln=(f32(sd[f"{p}.norm.weight"]), f32(sd[f"{p}.norm.bias"])),
                                fc1=_Conv(sd[f"{p}.pointwise_conv1.weight"][:, :, None, None], sd[f"{p}.pointwise_conv1.bias"], dev, act='gelu'),
                                # layer scale folded: gamma * (W2 h + b2)
                                fc2=_Conv(sd[f"{p}.pointwise_conv2.weight"][:, :, None, None] * gamma.view(-1, 1, 1, 1), sd[f"{p}.pointwise_conv2.bias"] * gamma, dev)))
@@ -326,8 +331,12 @@ class RTMDetIns:
                 ln, conv = self.down[i]
                 t = conv(E.layernorm_nhwc(t, *ln))
             for blk in self.blocks[i]:
-                u = E.dwconv_nhwc(t, blk['dw'], blk['dwb'], ln=blk['ln'], eps=1e-6)
-                h = blk['fc1'](u)
+                if FOLD_LN and t.shape[3] % 64 == 0:
+                    u, stats = E.dwconv_stats_nhwc(t, blk['dw'], blk['dwb'])
+                    h = E.conv2d_ln_nhwc(u, stats, *blk['fc1_ln'], eps=1e-6, act='gelu')
+                else:
+                    u = E.dwconv_nhwc(t, blk['dw'], blk['dwb'], ln=blk['ln'], eps=1e-6)
+                    h = blk['fc1'](u)
                 E.conv2d_nhwc(h, blk['fc2'].w, blk['fc2'].b, residual=t, res_mode=2, out=t)       # in place: t = t + gamma*(W2 h + b2)
             if i in cat_slices:
                 buf, off = cat_slices[i]

@@ -507,10 +507,13 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 }
 
 constexpr int kDwThreads = 128;
-template <int K, int ACT>       // ACT: the fused activation, compiled in (CSB_ACT_NONE / CSB_ACT_SILU), or -1 = decided at run time from `act`
+// STATS: also emit, per pixel and per 64-channel chunk, (sum, sum of squares) of the fp16-rounded outputs -> stats[pixel][C/64][2] fp32.  The
+// following C -> 4C GEMM applies the LayerNorm of the ConvNeXt block in its epilogue from these (csb_conv2d_ln_nhwc), so the separate
+// LayerNorm pass over the activations (read + write of 2 C B/px) disappears.
+template <int K, int ACT, bool STATS = false>       // ACT: the fused activation, compiled in (CSB_ACT_NONE / CSB_ACT_SILU), or -1 = decided at run time from `act`
 __global__ void __launch_bounds__(kDwThreads, 3) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
                                                         const float* __restrict__ bias, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy,
-                                                        int yoff) {
+                                                        int yoff, float* __restrict__ stats = nullptr) {
     constexpr int R = K / 2, TSY = 2, TSX = 8, INX = TSX + K - 1;
     __shared__ float2 wsm[K * K * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -589,11 +592,39 @@ __global__ void __launch_bounds__(kDwThreads, 3) k_dwconv_tile(const __half* __r
         }
         __half* yb = y + ((img * H + oy0) * W + ox0) * ldy + yoff + c0;
         const bool row1 = oy0 + 1 < H;
+        if constexpr (STATS) {
+            float v[32];                                                // [0,16): per-pixel sum over this lane's 2 channels, [16,32): sum of squares
 #pragma unroll
-        for (int j = 0; j < TSX; ++j) {
-            if (ox0 + j >= W) break;
-            *reinterpret_cast<__half2*>(yb + (size_t) j * ldy) = __floats2half2_rn(acc0[j].x, acc0[j].y);
-            if (row1) *reinterpret_cast<__half2*>(yb + ((size_t) W + j) * ldy) = __floats2half2_rn(acc1[j].x, acc1[j].y);
+            for (int j = 0; j < TSX; ++j) {
+                const __half2 h0 = __floats2half2_rn(acc0[j].x, acc0[j].y), h1 = __floats2half2_rn(acc1[j].x, acc1[j].y);
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                v[j] = f0.x + f0.y; v[16 + j] = fmaf(f0.x, f0.x, f0.y * f0.y);
+                v[8 + j] = f1.x + f1.y; v[24 + j] = fmaf(f1.x, f1.x, f1.y * f1.y);
+                if (ox0 + j < W) {
+                    *reinterpret_cast<__half2*>(yb + (size_t) j * ldy) = h0;
+                    if (row1) *reinterpret_cast<__half2*>(yb + ((size_t) W + j) * ldy) = h1;
+                }
+            }
+            // transposed butterfly: 32 values x 32 lanes -> lane l ends with the warp total of value l (31 shuffles instead of 160)
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const int m = 16 >> s;                                  // lane bit examined = number of values kept
+                const bool up = (lane & m) != 0;
+#pragma unroll
+                for (int i = 0; i < m; ++i) {
+                    const float send = up ? v[i] : v[i + m], keep = up ? v[i + m] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+            }
+            const int pl = lane & 15, py = oy0 + (pl >> 3), px = ox0 + (pl & 7);
+            if (py < H && px < W) stats[((((long long) img * H + py) * W + px) * (C >> 6) + chunk) * 2 + (lane >> 4)] = v[0];
+        } else {
+#pragma unroll
+            for (int j = 0; j < TSX; ++j) {
+                if (ox0 + j >= W) break;
+                *reinterpret_cast<__half2*>(yb + (size_t) j * ldy) = __floats2half2_rn(acc0[j].x, acc0[j].y);
+                if (row1) *reinterpret_cast<__half2*>(yb + ((size_t) W + j) * ldy) = __floats2half2_rn(acc1[j].x, acc1[j].y);
+            }
         }
     }
 }
@@ -647,6 +678,24 @@ extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w,
     if (K == 3) return launch_dwconv<3>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
     if (K == 5) return launch_dwconv<5>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
     return launch_dwconv<7>(xh, ldx, xoff, w, bias, ln_gamma, ln_beta, eps, act, N, H, W, C, yh, ldy, yoff, st);
+}
+
+extern "C" int csb_dwconv_stats_nhwc(const void* x, int ldx, int xoff, const float* w, const float* bias, int N, int H, int W, int C, int K, void* y, int ldy,
+                                     int yoff, float* stats, void* stream) {
+    CSB_REQUIRE(x && w && y && stats, "null pointer");
+    CSB_REQUIRE(K == 7 && C % 64 == 0 && C <= 2048, "K must be 7 and C a multiple of 64 (the ConvNeXt block)");
+    CSB_REQUIRE(ldx % 8 == 0 && xoff % 8 == 0 && ldy % 8 == 0 && yoff % 8 == 0, "channel strides/offsets must be multiples of 8");
+    cudaStream_t st = (cudaStream_t) stream;
+    static const int ctas = [] { const char* e = getenv("CSB_DW_CTAS"); return e ? atoi(e) : 3; }();
+    const long long ntiles = (long long) N * ((H + 1) / 2) * ((W + 7) / 8);
+    const int chunks = C / 64;
+    int gx = ctas * csb::num_sms() / chunks;
+    const long long need = (ntiles + kDwThreads / 32 - 1) / (kDwThreads / 32);
+    gx = gx > need ? (int) need : gx;
+    gx = gx < 1 ? 1 : gx;
+    k_dwconv_tile<7, CSB_ACT_NONE, true><<<dim3(gx, chunks), kDwThreads, 0, st>>>((const __half*) x, ldx, xoff, w, bias, CSB_ACT_NONE, N, H, W, C, (__half*) y, ldy,
+                                                                                  yoff, stats);
+    return csb::launched("k_dwconv_tile", st);
 }
 
 extern "C" int csb_layernorm_nhwc(const void* x, int ldx, int xoff, const float* gamma, const float* beta, float eps, long long npix, int C, void* y,

@@ -35,7 +35,11 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+// warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, then EG groups of 4 epilogue warps (EG = 2: 384 threads x 168 registers; EG = 3: 512 threads compiled
+// for 128 registers, where the first warpgroup shrinks to 40 with setmaxnreg.dec and the three epilogue warpgroups grow to 152).  The GELU / SiLU /
+// residual epilogues of the short-K layers are bound by dependency latency (issue slots 48 % busy, ncu): a third warp per scheduler with the
+// full register budget fills those gaps.
+constexpr int kMaxEpiGroups = 3;
 constexpr int kTmemCols = 512;
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 8;
@@ -61,6 +65,13 @@ struct ConvKernelParams {
     int is_bf16;
     int tma_store;               // 0: per-lane 16 B global stores; 1 / 2: smem-staged TMA tile stores (64 B-swizzled / linear staging)
     uint32_t stage_off;          // byte offset of the epilogue staging area (8 warps x 2 KiB) from the 1 KiB-aligned smem base
+    // LayerNorm folded into a 1x1 conv (csb_conv2d_ln_nhwc): x is UN-normalised, w = gamma (.) W, and the epilogue finishes
+    //   y = rstd[row] * (acc - mean[row] * colsum[col]) + bias'[col]      with colsum[col] = sum_k w[col][k], bias' = bias + W beta
+    // mean / rstd come from per-row partial (sum, sum of squares) pairs, one per 64-channel chunk, written by k_dwconv_tile<.., STATS>.
+    const float* ln_stats;
+    const float* ln_colsum;
+    int ln_nchunk;
+    float ln_inv_c, ln_eps;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -191,6 +202,37 @@ __device__ __forceinline__ void gelu2(float& a, float& b) {
     upk2(ffma2(h, fmul2(xc, q), h), a, b);                          // 0.5 x (1 + erf(x / sqrt2))
 }
 
+// Exact-erf GELU on two values in sigmoid form, on the MUFU pipe: gelu(x) = x * Phi(x) = x / (1 + exp(-2 g(x))), g(x) = atanh(erf(x / sqrt2)) fitted
+// by the odd polynomial x (c1 + c3 x^2 + c5 x^4) (x^2 clamped at 64, where Phi has saturated; weighted minimax fit, max |GELU error| 2.6e-5
+// over all x -- the same class as gelu2 above and 20x below the fp16 rounding of the output).  The constants carry the factor -2 log2(e), so
+// exp(-2 g) is one ex2.approx.  6 packed + 2 FMNMX + 4 MUFU per PAIR, against 15 packed + 4 FMNMX for gelu2: the epilogue of the C -> 4C
+// layers is bound by instruction issue / dependency latency, and a chunk that uses both forms (kGeluMufuPairs of its 16 pairs here, the rest
+// gelu2) spreads the work over the FMA and MUFU pipes (measured on B200, 512 -> 2048 @32x64x64 / 128 -> 512 @16x256x256: 0 pairs 348 / 548 us,
+// 8 pairs 322 / 489 us, 16 pairs 333 / 503 us).  ex2 overflow (x << 0) gives rcp(inf) = 0 -> 0, the correct limit.
+__device__ __forceinline__ void gelu2_mufu(float& a, float& b) {
+    const uint64_t x = pk2(a, b);
+    float s0, s1;
+    upk2(fmul2(x, x), s0, s1);
+    const uint64_t x2 = pk2(fminf(s0, 64.0f), fminf(s1, 64.0f));
+#define CSB_C2(v) pk2(v, v)
+    uint64_t q = ffma2(x2, CSB_C2(0.0010142643004655838f), CSB_C2(-0.10677573084831238f));
+    q = ffma2(q, x2, CSB_C2(-2.301121234893799f));
+    float u0, u1, e0, e1, r0, r1;
+    upk2(fmul2(q, x), u0, u1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(u0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(u1));
+    float d0, d1;
+    upk2(fadd2(pk2(e0, e1), CSB_C2(1.0f)), d0, d1);
+#undef CSB_C2
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+    upk2(fmul2(x, pk2(r0, r1)), a, b);
+}
+#ifndef CSB_GELU_MUFU_PAIRS
+#define CSB_GELU_MUFU_PAIRS 8
+#endif
+constexpr int kGeluMufuPairs = CSB_GELU_MUFU_PAIRS;      // of the 16 pairs of a 32-column chunk
+
 template <class T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
@@ -206,9 +248,9 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 
 // One 32-column chunk of one accumulator row.  The fast path (full chunk, 16 B-aligned slices) is straight-line code: 8 float4 bias
 // loads (warp-uniform -> broadcast), 4 x 16 B residual loads, activation on 32 independent values, 4 x 16 B stores.
-template <class T, int ACT>
+template <class T, int ACT, bool LN, int GM = kGeluMufuPairs>
 __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[32], size_t pix, int n0, bool row_ok, bool fast, uint32_t stage,
-                                               const CUtensorMap* tmC, int cw, int chh, int cimg) {
+                                               const CUtensorMap* tmC, int cw, int chh, int cimg, float neg_mean, float rstd) {
     // stage != 0: this full chunk leaves through shared memory and one TMA tile store per warp (rows outside the image are clipped by the TMA unit;
     // their arithmetic runs on in-bounds addresses because `pix` is clamped by the caller)
     if (!row_ok && !(stage && fast && !p.out_f32)) return;
@@ -216,7 +258,15 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(acc[j]);
-        if (p.bias) {                                       // packed adds: 16 FADD2 instead of 32 FADD
+        if constexpr (LN) {                                 // rstd * acc + (-mean * rstd * colsum + bias'): 32 FFMA2 (the plain path spends 16 FADD2)
+            const uint64_t nm = pk2(neg_mean, neg_mean), rs = pk2(rstd, rstd);      // neg_mean = -mean * rstd
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0) + g), b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + g);
+                upk2(ffma2(rs, pk2(y[4 * g], y[4 * g + 1]), ffma2(nm, pk2(c.x, c.y), pk2(b.x, b.y))), y[4 * g], y[4 * g + 1]);
+                upk2(ffma2(rs, pk2(y[4 * g + 2], y[4 * g + 3]), ffma2(nm, pk2(c.z, c.w), pk2(b.z, b.w))), y[4 * g + 2], y[4 * g + 3]);
+            }
+        } else if (p.bias) {                                // packed adds: 16 FADD2 instead of 32 FADD
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + g);
@@ -246,7 +296,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
             for (int j = 0; j < 32; ++j) y[j] = apply_act<ACT>(y[j], p.act_param ? __ldg(p.act_param + n0 + j) : 0.25f);
         } else if constexpr (ACT == CSB_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu2(y[j], y[j + 1]);
+            for (int j = 0; j < 32; j += 2) {                // interleaved, so that neighbouring pairs run on different pipes
+                if ((j >> 1) * GM / 16 != ((j >> 1) + 1) * GM / 16) gelu2_mufu(y[j], y[j + 1]);
+                else gelu2(y[j], y[j + 1]);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) y[j] = apply_act<ACT>(y[j], 0.f);
@@ -290,6 +343,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
         const int c = n0 + j;
         if (c >= p.Cout) continue;
         float v = __uint_as_float(acc[j]);
+        if constexpr (LN) v = fmaf(rstd, v, neg_mean * __ldg(p.ln_colsum + c));
         if (p.bias) v += __ldg(p.bias + c);
         if (p.res_mode == 1) v += to_f<T>(res[j]);
         v = apply_act<ACT>(v, p.act_param ? __ldg(p.act_param + c) : 0.25f);
@@ -299,11 +353,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
     }
 }
 
-// Epilogue role: 8 warps; warp w owns TMEM lane quarter (w & 3) and the 32-column chunks with (chunk & 1) == (w - 4) / 4.
-template <class T, int ACT>
+// Epilogue role: EG groups of 4 warps; warp w owns TMEM lane quarter (w & 3) and the 32-column chunks with chunk % EG == (w - 4) / 4.
+template <class T, int ACT, bool LN = false, int GM = kGeluMufuPairs>
 __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
                                               const CUtensorMap* tmC) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int EG = (int) (blockDim.x >> 7) - 1;
     const int q = warp & 3, half = (warp - 4) >> 2;
     const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && (!p.bias || ((uintptr_t) p.bias % 16 == 0));
     int as = 0;
@@ -319,19 +374,30 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
         const uint32_t stage = p.tma_store ? stage_base + (uint32_t) (warp - 4) * 2048u : 0u;
         const int row0 = q * 32;
         const int cw = tw * p.bw + row0 % p.bw, chh = th * p.bh + row0 / p.bw;
+        float neg_mean = 0.f, rstd = 1.f;
+        if constexpr (LN) {                                 // this row's LayerNorm statistics from the per-chunk partials (loaded before the wait)
+            const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + pix * p.ln_nchunk;
+            float s1 = 0.f, s2 = 0.f;
+            for (int c = 0; c < p.ln_nchunk; ++c) { const float2 t = __ldg(sp + c); s1 += t.x; s2 += t.y; }
+            const float mean = s1 * p.ln_inv_c;
+            rstd = rsqrtf(fmaxf(fmaf(s2, p.ln_inv_c, -mean * mean), 0.f) + p.ln_eps);
+            neg_mean = -mean * rstd;
+        }
         mbar_wait(tfull0 + 8u * as, aphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) as * 256u;
         const int ncols = min(p.block_n, p.Cout - nt * p.block_n);
         const int nchunks = (ncols + 31) / 32;
         int last = -1;                                     // last chunk this warp reads
-        for (int ch = half; ch < nchunks; ch += 2) last = ch;
+        for (int ch = half; ch < nchunks; ch += EG) last = ch;
         if (last < 0) {                                    // nothing to read for this warp in this tile: release immediately
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8u * as);
         }
-        for (int ch = half; ch < nchunks; ch += 2) {
+        for (int ch = half; ch < nchunks; ch += EG) {
+            const int n0 = nt * p.block_n + ch * 32;
+            const bool fast = aligned && n0 + 32 <= p.Cout;
             uint32_t acc[32];
             tmem_ld32(taddr + (uint32_t) ch * 32u, acc);
             if (ch == last) {                              // accumulator rows of this warp fully read: hand the TMEM stage back
@@ -339,8 +405,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty0 + 8u * as);
             }
-            const int n0 = nt * p.block_n + ch * 32;
-            epilogue_chunk<T, ACT>(p, acc, pix, n0, row_ok, aligned && n0 + 32 <= p.Cout, stage, tmC, cw, chh, img);
+            epilogue_chunk<T, ACT, LN, GM>(p, acc, pix, n0, row_ok, fast, stage, tmC, cw, chh, img, neg_mean, rstd);
         }
         if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
@@ -350,6 +415,11 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
 template <class T>
 __device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
                                                   const CUtensorMap* tmC) {
+    if (p.ln_stats) {     // LayerNorm-folded 1x1 conv: only the activations that follow a LayerNorm on this path
+        if (p.act == CSB_ACT_GELU) epilogue_role<T, CSB_ACT_GELU, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
+        else epilogue_role<T, CSB_ACT_NONE, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
+        return;
+    }
     switch (p.act) {      // hoisted out of every loop: each instantiation is straight-line code
         case CSB_ACT_RELU: epilogue_role<T, CSB_ACT_RELU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
         case CSB_ACT_SILU: epilogue_role<T, CSB_ACT_SILU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
@@ -362,8 +432,9 @@ __device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uin
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                         const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
+template <int EG>
+__global__ void __launch_bounds__(128 * (EG + 1), 1) k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t row_bytes = (uint32_t) p.bk * 2u;
@@ -386,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * EG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -402,6 +473,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
     const int total_tiles = p.tiles_m * p.tiles_n;
     const int kblocks = p.R * p.S * p.kchunks;
 
+    if constexpr (EG == 3) {
+        // 16 warps are compiled for 128 registers; the TMA / MMA / alloc warpgroup needs ~40, so it hands its share to the three epilogue
+        // warpgroups (4 x 32 x 40 + 12 x 32 x 152 = 63488 <= 65536): 12 epilogue warps run with the register budget of the 8-warp build.
+    }
+    if (warp < 4) {
+        if constexpr (EG == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
         // ===================================================== TMA producer
         if (elect_one()) {
@@ -451,8 +528,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc(const __grid_constant__
             }
             if (++as == kAccStages) { as = 0; aphase ^= 1u; }
         }
-    } else if (warp >= 4) {
-        // ===================================================== epilogue (TMEM -> registers -> global), 8 warps
+    }
+    } else {
+        // ===================================================== epilogue (TMEM -> registers -> global), 4 * EG warps
+        if constexpr (EG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         if (p.is_bf16) epilogue_dispatch<__nv_bfloat16>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
         else epilogue_dispatch<__half>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
     }
@@ -484,8 +563,8 @@ CUtensorMapSwizzle swizzle_of(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_
 
 }  // namespace
 
-extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void* w, const float* bias, const float* act_param,
-                               const void* residual, void* y, float* y_f32, void* stream) {
+static int conv_impl(const csb_conv_desc* d, const void* x, const void* w, const float* bias, const float* act_param, const void* residual, void* y,
+                     float* y_f32, const float* ln_stats, const float* ln_colsum, float ln_eps, void* stream) {
     CSB_REQUIRE(d && x && w && (y || y_f32), "null pointer");
     CSB_REQUIRE(d->N > 0 && d->Hin > 0 && d->Win > 0 && d->Cin > 0 && d->Cout > 0 && d->R > 0 && d->S > 0, "bad shape");
     CSB_REQUIRE(d->stride == 1 || d->stride == 2 || d->stride == 4, "stride must be 1, 2 or 4");
@@ -511,6 +590,13 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
     }
     p.in_coff = d->in_coff;
     const bool flat = d->R == 1 && d->S == 1 && d->stride == 1 && d->pad == 0 && !p.grouped;
+    if (ln_stats) {
+        CSB_REQUIRE(flat && ln_colsum && d->Cin % 64 == 0 && ((uintptr_t) ln_colsum & 15) == 0 && ((uintptr_t) ln_stats & 7) == 0,
+                    "LayerNorm folding needs a dense 1x1 stride-1 conv with Cin a multiple of 64");
+        CSB_REQUIRE(d->act == CSB_ACT_GELU || d->act == CSB_ACT_NONE, "LayerNorm folding supports act none / gelu");
+        CSB_REQUIRE(bias && ((uintptr_t) bias & 15) == 0, "LayerNorm folding needs the folded bias (bias + W beta), 16-byte aligned");
+        p.ln_stats = ln_stats; p.ln_colsum = ln_colsum; p.ln_nchunk = d->Cin / 64; p.ln_inv_c = 1.0f / (float) d->Cin; p.ln_eps = ln_eps;
+    }
     cuuint64_t gdim[4], gstr[3];
     cuuint32_t box[4], estr[4];
     const cuuint64_t esz = 2;
@@ -550,13 +636,13 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
 
     const uint32_t row_bytes = p.bk * 2, stage_bytes = ((kBlockM + p.block_n) * row_bytes + 1023u) & ~1023u;
     const int kblocks = p.R * p.S * p.kchunks;
-    int stages = (int) ((208u * 1024u) / stage_bytes);
+    int stages = (int) ((200u * 1024u) / stage_bytes);
     stages = stages > kMaxStages ? kMaxStages : stages;
     stages = stages > kblocks * 2 ? (kblocks * 2 < 2 ? 2 : kblocks * 2) : stages;
     p.stages = stages < 2 ? 2 : stages;
     // [stages | barriers + tmem slot | pad to 1 KiB | epilogue staging 8 x 2 KiB]
     p.stage_off = (uint32_t) (((size_t) p.stages * stage_bytes + 8 * (2 * kMaxStages + 2 * kAccStages) + 16 + 1023) & ~(size_t) 1023);
-    const size_t smem = (size_t) p.stage_off + 8 * 2048 + 1024 /*align*/;
+    const size_t smem = (size_t) p.stage_off + 4 * kMaxEpiGroups * 2048 + 1024 /*align*/;
     p.bias = bias; p.act = d->act; p.act_param = act_param;
     p.residual = residual; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.res_mode = d->res_mode;
     p.out = y; p.out_f32 = y_f32; p.out_ld = d->out_ld; p.out_coff = d->out_coff; p.is_bf16 = d->dtype == 1;
@@ -576,10 +662,17 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
         if (r == CUDA_SUCCESS) p.tma_store = store_mode == 1 ? 1 : 2;
     }
     static std::once_flag attr_once;
-    std::call_once(attr_once, [] { cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    std::call_once(attr_once, [] {
+        cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
     const int total = p.tiles_m * p.tiles_n;
     const int grid = total < csb::num_sms() ? total : csb::num_sms();
-    k_conv_tc<<<grid, kThreads, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
+    // 12 epilogue warps (EG = 3, registers re-balanced with setmaxnreg) by default: -1.1 ms on the detector's convs and -0.7 ms on LeReS' per 32
+    // frames against the 8-warp build, which stays selectable (CSB_EPI_GROUPS=2) for A/B runs
+    static const int eg = [] { const char* e = getenv("CSB_EPI_GROUPS"); return e && atoi(e) == 2 ? 2 : 3; }();
+    if (eg == 3) k_conv_tc<3><<<grid, 512, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
+    else k_conv_tc<2><<<grid, 384, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {           // detailed profile: one key per layer shape
         char label[160];
         snprintf(label, sizeof label, "k_conv_tc[%dx%dx%dx%d->%d k%dx%d s%d d%d g%d act%d res%d]", d->N, d->Hin, d->Win, d->Cin, d->Cout, d->R, d->S, d->stride,
@@ -587,4 +680,15 @@ extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void
         return csb::launched(csb::profile_intern(label), (cudaStream_t) stream);
     }
     return csb::launched("k_conv_tc", (cudaStream_t) stream);
+}
+
+extern "C" int csb_conv2d_nhwc(const csb_conv_desc* d, const void* x, const void* w, const float* bias, const float* act_param,
+                               const void* residual, void* y, float* y_f32, void* stream) {
+    return conv_impl(d, x, w, bias, act_param, residual, y, y_f32, nullptr, nullptr, 0.f, stream);
+}
+
+extern "C" int csb_conv2d_ln_nhwc(const csb_conv_desc* d, const void* x, const void* w, const float* bias, const float* colsum, const float* stats, float eps,
+                                  const void* residual, void* y, void* stream) {
+    CSB_REQUIRE(stats && colsum, "null pointer");
+    return conv_impl(d, x, w, bias, nullptr, residual, y, nullptr, stats, colsum, eps, stream);
 }

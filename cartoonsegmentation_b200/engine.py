@@ -67,6 +67,42 @@ def conv2d_nhwc(x, w, bias=None, stride=1, pad=0, dil=1, act=None, act_param=Non
     return out
 
 
+def fold_layernorm(w, b, gamma, beta, dtype=torch.float16):
+    """LayerNorm(gamma, beta) followed by Linear(w [Cout,Cin], b) == rstd * (x W'^T - mean * colsum) + b' on the un-normalised x:
+    -> (packed W' [Cout,1,1,Cin], b' fp32, colsum fp32 of the ROUNDED W' so that the mean term cancels exactly in the epilogue)."""
+    w, b, gamma, beta = w.float(), b.float(), gamma.float(), beta.float()
+    wp = (w * gamma[None, :]).to(dtype)
+    return wp.reshape(w.shape[0], 1, 1, w.shape[1]).contiguous(), (b + w @ beta).contiguous(), wp.float().sum(1).contiguous()
+
+
+def dwconv_stats_nhwc(x, w, bias=None, out=None, xoff=0, yoff=0, channels=None):
+    """Depthwise 7x7 + bias -> (y, stats [N*H*W, C/64, 2] fp32 partial (sum, sumsq) per pixel and 64-channel chunk) for conv2d_ln_nhwc."""
+    N, H, W, ldx = x.shape
+    Cc = w.shape[2] if channels is None else channels
+    if out is None:
+        out = torch.empty((N, H, W, Cc), device=x.device, dtype=x.dtype)
+    stats = torch.empty((N * H * W, Cc // 64, 2), device=x.device, dtype=torch.float32)
+    check(lib().csb_dwconv_stats_nhwc(ptr(x), ldx, xoff, ptr(w), ptr(bias), N, H, W, Cc, w.shape[0], ptr(out), out.shape[3], yoff, ptr(stats), stream()),
+          "csb_dwconv_stats_nhwc")
+    return out, stats
+
+
+def conv2d_ln_nhwc(x, stats, w, bias, colsum, eps=1e-6, act=None, residual=None, res_mode=0, out=None, out_coff=0):
+    """1x1 conv of LayerNorm(x) with the LayerNorm folded into the epilogue (see fold_layernorm); x is the un-normalised NHWC tensor."""
+    N, H, W, Cx = x.shape
+    Cout, R, S, Cin = w.shape
+    assert (R, S) == (1, 1) and Cin == Cx and x.dtype == w.dtype
+    if out is None:
+        out = torch.empty((N, H, W, Cout), device=x.device, dtype=x.dtype)
+    if residual is not None and res_mode == 0:
+        res_mode = 1
+    d = ConvDesc(N, H, W, Cin, Cx, 0, Cout, 1, 1, 1, 0, 1, out.shape[3], out_coff, ACT[act], res_mode,
+                 residual.shape[3] if residual is not None else 0, 0, 1 if x.dtype == torch.bfloat16 else 0, 1)
+    check(lib().csb_conv2d_ln_nhwc(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(colsum), ptr(stats), _cf(eps), ptr(residual), ptr(out), stream()),
+          "csb_conv2d_ln_nhwc")
+    return out
+
+
 def dwconv_nhwc(x, w, bias=None, ln=None, eps=1e-6, act=None, out=None, xoff=0, yoff=0, channels=None):
     """Depthwise KxK (stride 1, pad K/2) + bias [+ LayerNorm over C (ln=(gamma, beta))] [+ act].  x NHWC fp16, w [K,K,C] fp32."""
     N, H, W, ldx = x.shape

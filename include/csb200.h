@@ -228,6 +228,17 @@ typedef struct csb_conv_desc {
 CSB_API int csb_conv2d_nhwc(const csb_conv_desc* desc, const void* x, const void* w, const float* bias, const float* act_param,
                     const void* residual, void* y, float* y_f32, void* stream);
 
+/* LayerNorm folded into the 1x1 conv that consumes it (the ConvNeXt block: depthwise 7x7 -> LayerNorm -> Linear C->4C -> GELU, mmpretrain
+ * ConvNeXtBlock).  csb_dwconv_stats_nhwc is csb_dwconv_nhwc (K = 7, no activation) that also writes, per pixel and
+ * per 64-channel chunk, (sum, sum of squares) of its fp16 outputs: stats [N*H*W][C/64][2] fp32.  csb_conv2d_ln_nhwc then computes
+ *     y = act( rstd * (x W'^T - mean * colsum) + bias' ),   W' = W diag(gamma) (packed fp16),  colsum[co] = sum_ci W'[co][ci],
+ *     bias' = bias + W beta,   mean / rstd = LayerNorm statistics of the row from `stats` (biased variance, eps inside the sqrt)
+ * on the UN-normalised x (desc: dense 1x1, stride 1, Cin % 64 == 0, act none or gelu): the LayerNorm pass over the activations is gone. */
+CSB_API int csb_dwconv_stats_nhwc(const void* x, int ldx, int xoff, const float* w, const float* bias, int N, int H, int W, int C, int K, void* y, int ldy,
+                          int yoff, float* stats, void* stream);
+CSB_API int csb_conv2d_ln_nhwc(const csb_conv_desc* desc, const void* x, const void* w, const float* bias, const float* colsum, const float* stats,
+                       float eps, const void* residual, void* y, void* stream);
+
 /* HBM-bound NHWC fp16 layers between the tensor-core convs (csrc/nn_elem.cu).  Channel-slice addressing: ld = channels of the
  * buffer, off = first channel, so concats (CSPNeXtPAFPN, MaskFeatModule, CSPLayer -- SURVEY.md Appendix A.3-A.6) need no copy.
  *   csb_dwconv_nhwc     depthwise KxK (K = 3/5/7, stride 1, zero pad K/2) + bias, then LayerNorm over C (ln_gamma/ln_beta != NULL:

@@ -96,3 +96,36 @@ def test_conv_rejects_bad_arguments(eng):
     w = torch.zeros(16, 3, 3, 24, device='cuda', dtype=torch.float16)
     with pytest.raises(Exception):
         eng.conv2d_nhwc(x, w, None, pad=1)           # Cin = 24 is not a multiple of 16
+
+
+@pytest.mark.parametrize("N,H,W,C,mean_shift", [(2, 18, 23, 128, 0.0), (1, 16, 16, 256, 3.0), (2, 9, 40, 512, -1.5), (1, 7, 7, 1024, 0.5)])
+def test_convnext_block_head_ln_folded(eng, N, H, W, C, mean_shift):
+    """depthwise 7x7 -> LayerNorm -> Linear(C, 4C) -> GELU (mmpretrain ConvNeXtBlock) with the LayerNorm folded into the GEMM
+    epilogue (csb_dwconv_stats_nhwc + csb_conv2d_ln_nhwc) against plain PyTorch fp32 and against the unfused kernels.  `mean_shift` moves
+    the per-pixel mean away from zero (the folded form subtracts mean * colsum in fp32)."""
+    g = torch.Generator(device='cuda').manual_seed(C + H)
+    x = (torch.randn(N, H, W, C, device='cuda', generator=g) + mean_shift).half()
+    dw = torch.randn(7, 7, C, device='cuda', generator=g) / 7.0
+    dwb = torch.randn(C, device='cuda', generator=g) * 0.1 + mean_shift
+    gamma = torch.rand(C, device='cuda', generator=g) + 0.5
+    beta = torch.randn(C, device='cuda', generator=g) * 0.2
+    w1 = torch.randn(4 * C, C, device='cuda', generator=g) / C ** 0.5
+    b1 = torch.randn(4 * C, device='cuda', generator=g) * 0.1
+    # fp32 reference on the fp16-rounded depthwise output (what both GPU paths normalise)
+    u_ref = F.conv2d(x.float().permute(0, 3, 1, 2), dw.permute(2, 0, 1)[:, None], dwb, padding=3, groups=C).permute(0, 2, 3, 1)
+    u16 = u_ref.half().float()
+    ref = F.gelu(F.linear(F.layer_norm(u16, (C,), gamma, beta, 1e-6), w1, b1))
+    u, stats = eng.dwconv_stats_nhwc(x, dw.contiguous(), dwb)
+    assert (u.float() - u_ref).abs().max() <= 2e-3 * u_ref.abs().max() + 1e-3
+    s = stats.sum(1)
+    uf = u.float().reshape(-1, C)
+    assert torch.allclose(s[:, 0], uf.sum(1), rtol=1e-4, atol=1e-2) and torch.allclose(s[:, 1], (uf * uf).sum(1), rtol=1e-4, atol=1e-2)
+    wl, bl, cs = eng.fold_layernorm(w1, b1, gamma, beta)
+    y = eng.conv2d_ln_nhwc(u, stats, wl, bl, cs, eps=1e-6, act='gelu').float()
+    tol = 3e-3 * ref.abs().max() + 2e-3
+    assert (y - ref).abs().max() <= tol, ((y - ref).abs().max().item(), tol.item())
+    # the unfused kernels (dwconv + k_layernorm, then the plain GEMM) agree to the same tolerance
+    u2 = eng.dwconv_nhwc(x, dw.contiguous(), dwb, ln=(gamma.contiguous(), beta.contiguous()), eps=1e-6)
+    y2 = eng.conv2d_nhwc(u2, eng.pack_conv_weight(w1[:, :, None, None]), b1, act='gelu').float()
+    assert (y2 - ref).abs().max() <= tol
+    assert ((y - ref) ** 2).mean().sqrt() <= 1.5 * ((y2 - ref) ** 2).mean().sqrt() + 1e-4          # folding does not cost accuracy
