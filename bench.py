@@ -252,6 +252,18 @@ def run_other(pipe, imgs_np, args):
                                    "host ndarray in, list of host uint8 frames out" % (pipe.cfg.depth_est, pipe.cfg.num_frame),
                             "input_images_per_s": n_img / (ms * 1e-3), "output_frames_per_s": sum(frames) / (ms * 1e-3), "ms_per_image": ms / n_img,
                             "images": n_img, "h2d_bytes_per_image": H * W * 3, "d2h_bytes_per_image": pipe.cfg.num_frame * H * W * 3}
+    # ---- the same with the options the reference ships in configs/3dkenburns.yaml: ISNet mask refinement (refine_size 720) + depth_field (bokeh)
+    pipe.cfg.mask_refine_kwargs = {'refine_method': 'refinenet_isnet', 'refine_size': 720}
+    pipe.cfg.depth_field = True
+    kb_image(0)
+    n_y = min(2, n_img)
+    ms, frames = timed(lambda: [len(kb_image(1 + i)) for i in range(n_y)])
+    res["kenburns_full_shipped_yaml"] = {"api": "as kenburns_full with mask_refine_kwargs={refinenet_isnet, 720} and depth_field=True (configs/3dkenburns.yaml:16,36-38)",
+                                         "input_images_per_s": n_y / (ms * 1e-3), "output_frames_per_s": sum(frames) / (ms * 1e-3), "ms_per_image": ms / n_y,
+                                         "images": n_y}
+    pipe.cfg.mask_refine_kwargs = {}
+    pipe.cfg.depth_field = False
+    seg.set_refine_method('none')
     return res
 
 

@@ -19,8 +19,12 @@ import math
 import numpy as np
 import torch
 
+import os
+
 from .. import engine as E
 from .._lib import check, lib, ptr, stream
+
+ATTN_TC = os.environ.get("CSB_ATTN_TC", "1") != "0"          # tcgen05 attention (zoe_attn_tc.cu); 0 = the mma.sync kernel (zoe_attn.cu)
 
 N_BINS, EMB, N_ATTR = 64, 128, (16, 8, 4, 1)
 MIN_TEMP, MAX_TEMP, P_EPS = 0.0212, 50.0, 1e-4
@@ -254,11 +258,11 @@ class BeitDPT:
         self.zero256 = torch.zeros(256, device=dev)
 
     def _bias(self, hp, wp):
-        """per-block additive attention bias [16, Tp, Tp] fp16, rows/cols padded to a multiple of 64 (padding columns = -60000)."""
+        """per-block additive attention bias [16, Tp, Tp] fp16, rows/cols padded to a multiple of 128 (padding columns = -60000)."""
         key = (hp, wp)
         if key not in self._bias_cache:
             T = hp * wp + 1
-            Tp = (T + 63) // 64 * 64
+            Tp = (T + 127) // 128 * 128
             out = []
             for tab in self.tables:
                 rb = relative_position_bias(tab.to(self.dev), (BEIT['window'],) * 2, (hp, wp))
@@ -293,12 +297,20 @@ class BeitDPT:
         x = torch.empty((B, 1, T, D), device=self.dev, dtype=torch.float16)
         check(lib().csb_tokens_assemble(ptr(emb), ptr(self.cls), B, P, D, ptr(x), stream()), "csb_tokens_assemble")
         hooked = []
+        use_tc = ATTN_TC
+        if use_tc:
+            lib().csb_attention_tc_scratch_bytes.restype = C.c_longlong
+            vt = torch.empty(int(lib().csb_attention_tc_scratch_bytes(B, T, heads)), device=self.dev, dtype=torch.uint8)
         for i, blk in enumerate(self.blocks):
             h = E.layernorm_nhwc(x, blk['n1'][0], blk['n1'][1], self.eps)
             qkv = E.conv2d_nhwc(h, blk['qkv'][0], blk['qkv'][1])
             att = torch.empty((B, 1, T, D), device=self.dev, dtype=torch.float16)
-            check(lib().csb_attention_bias(ptr(qkv), B, T, heads, D // heads, ptr(biases[i]), Tp, C.c_float((D // heads) ** -0.5), ptr(att), stream()),
-                  "csb_attention_bias")
+            if use_tc:      # tcgen05 kernel (zoe_attn_tc.cu)
+                check(lib().csb_attention_bias_tc(ptr(qkv), B, T, heads, D // heads, ptr(biases[i]), Tp, C.c_float((D // heads) ** -0.5), ptr(vt), ptr(att),
+                                                  stream()), "csb_attention_bias_tc")
+            else:           # mma.sync kernel (zoe_attn.cu), kept for A/B runs: CSB_ATTN_TC=0
+                check(lib().csb_attention_bias(ptr(qkv), B, T, heads, D // heads, ptr(biases[i]), Tp, C.c_float((D // heads) ** -0.5), ptr(att), stream()),
+                      "csb_attention_bias")
             x = E.conv2d_nhwc(att, blk['proj'][0], blk['proj'][1], residual=x, res_mode=2)          # x + gamma_1 * proj(attn)
             h = E.layernorm_nhwc(x, blk['n2'][0], blk['n2'][1], self.eps)
             h = E.conv2d_nhwc(h, blk['fc1'][0], blk['fc1'][1], act='gelu')

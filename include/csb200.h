@@ -153,6 +153,12 @@ CSB_API int csb_leres_depth_tail(const float* logits, int N, int h, int w, int H
  *   csb_zoe_finish       net depth [1|2][Hn][Wn] fp32 -> out [H][W]: bicubic (A=-0.75, align_corners=False) to the padded size, crop, un-flip, mean
  *   csb_zoe_disparity    depth -> disparity (kenburns_effect.py:812-818); scratch: one uint32 */
 CSB_API int csb_attention_bias(const void* qkv, int B, int T, int heads, int head_dim, const void* bias, int Tp, float scale, void* out, void* stream);
+/*   csb_attention_bias_tc  the same contract on tcgen05 (csrc/zoe_attn_tc.cu: S = Q K^T and O = P V as tcgen05.mma with TMEM accumulators, TMA-staged
+ *                        operands, one query row per thread); bias padded to a multiple of 128; vt_scratch: csb_attention_tc_scratch_bytes(B, T, heads)
+ *                        bytes of device memory owned by the caller (V transposed to [B][heads][64][keys]). */
+CSB_API long long csb_attention_tc_scratch_bytes(int B, int T, int heads);
+CSB_API int csb_attention_bias_tc(const void* qkv, int B, int T, int heads, int head_dim, const void* bias, int Tp, float scale, void* vt_scratch, void* out,
+                          void* stream);
 CSB_API int csb_tokens_assemble(const void* patches, const void* cls, int B, int P, int C, void* tokens, void* stream);
 CSB_API int csb_readout_concat(const void* tokens, int B, int P, int C, void* out, void* stream);
 CSB_API int csb_pixel_shuffle_nhwc(const void* x, int B, int h, int w, int k, int C, void* y, void* stream);

@@ -19,18 +19,27 @@ def _rr(a, b):
     return float(np.sqrt(((a - b) ** 2).mean() / ((b ** 2).mean() + 1e-30)))
 
 
-@pytest.mark.parametrize("B,T", [(2, 577), (1, 321), (3, 64), (1, 65)])
-def test_attention_vs_torch(built_lib, B, T):
+@pytest.mark.parametrize("kernel", ["tc", "mma_sync"])
+@pytest.mark.parametrize("B,T", [(2, 577), (1, 321), (3, 64), (1, 65), (2, 1765), (1, 128), (1, 129)])
+def test_attention_vs_torch(built_lib, B, T, kernel):
+    """both attention kernels (tcgen05: zoe_attn_tc.cu; mma.sync: zoe_attn.cu) against plain PyTorch fp32; T = 1765 is the 672 x 672 input of the
+    reference's Ken-Burns pipeline, 577 the 384 x 384 MidasCore default, the rest exercise ragged query / key blocks"""
     import ctypes as C
     from cartoonsegmentation_b200._lib import check, lib, ptr, stream
     heads, d = 16, 64
     g = torch.Generator(device='cuda').manual_seed(T)
     qkv = (torch.randn(B, T, 3 * heads * d, generator=g, device='cuda') * 1.5).half()
-    Tp = (T + 63) // 64 * 64
+    Tp = (T + 127) // 128 * 128
     bias = torch.full((heads, Tp, Tp), -60000.0, device='cuda', dtype=torch.float16)
     bias[:, :T, :T] = (torch.randn(heads, T, T, generator=g, device='cuda') * 2).half()
     out = torch.empty(B, T, heads * d, device='cuda', dtype=torch.float16)
-    check(lib().csb_attention_bias(ptr(qkv), B, T, heads, d, ptr(bias), Tp, C.c_float(d ** -0.5), ptr(out), stream()), "csb_attention_bias")
+    if kernel == "tc":
+        lib().csb_attention_tc_scratch_bytes.restype = C.c_longlong
+        vt = torch.empty(int(lib().csb_attention_tc_scratch_bytes(B, T, heads)), device='cuda', dtype=torch.uint8)
+        check(lib().csb_attention_bias_tc(ptr(qkv), B, T, heads, d, ptr(bias), Tp, C.c_float(d ** -0.5), ptr(vt), ptr(out), stream()), "csb_attention_bias_tc")
+    else:
+        check(lib().csb_attention_bias(ptr(qkv), B, T, heads, d, ptr(bias), Tp, C.c_float(d ** -0.5), ptr(out), stream()), "csb_attention_bias")
+    torch.cuda.synchronize()
     q, k, v = qkv.float().view(B, T, 3, heads, d).permute(2, 0, 3, 1, 4)
     ref = ((q @ k.transpose(-2, -1) * d ** -0.5 + bias[:, :T, :T].float()[None]).softmax(-1) @ v).transpose(1, 2).reshape(B, T, heads * d)
     assert torch.isfinite(out).all()
