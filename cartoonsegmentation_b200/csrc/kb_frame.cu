@@ -37,9 +37,15 @@ struct CropParams {
 };
 
 // getRectSubPix_Cn_<uchar,uchar,int,scale_fixpt,cast_8u> (OpenCV samplers.cpp), one crop pixel, 3 channels.
+template <bool COPY>
 __device__ __forceinline__ void crop_px(const uint8_t* __restrict__ src, int H, int W, const CropParams& p, int x, int y, int (&o)[3]) {
     int y0 = clampi(p.ipy + y, 0, H - 1), y1 = clampi(p.ipy + y + 1, 0, H - 1);
     int x0 = clampi(p.ipx + x, 0, W - 1), x1 = clampi(p.ipx + x + 1, 0, W - 1);
+    if constexpr (COPY) {       // integer crop origin (a11 = 65536, the other weights 0): (v * 65536 + 32768) >> 16 == v, one tap instead of four
+        const uint8_t* r00 = src + ((size_t) y0 * W + x0) * 3;
+        o[0] = r00[0]; o[1] = r00[1]; o[2] = r00[2];
+        return;
+    }
     const uint8_t *r00 = src + ((size_t) y0 * W + x0) * 3, *r01 = src + ((size_t) y0 * W + x1) * 3;
     const uint8_t *r10 = src + ((size_t) y1 * W + x0) * 3, *r11 = src + ((size_t) y1 * W + x1) * 3;
 #pragma unroll
@@ -50,6 +56,7 @@ __device__ __forceinline__ void crop_px(const uint8_t* __restrict__ src, int H, 
 }
 
 // resize.cpp: HResizeLinear<uchar,int,short,2048> + VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>.  6 B/px.
+template <bool COPY>
 __global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__ src, int H, int W, CropParams p, int Ho, int Wo, uint8_t* __restrict__ dst) {
     const int total = Ho * Wo;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -67,10 +74,10 @@ __global__ void __launch_bounds__(256) k_crop_resize(const uint8_t* __restrict__
         int b0 = (int) (short) __float2int_rn((1.f - fy) * 2048.f), b1 = (int) (short) __float2int_rn(fy * 2048.f);
         int x1 = ix + 1 < p.pw ? ix + 1 : ix;
         int c00[3], c01[3], c10[3], c11[3];
-        crop_px(src, H, W, p, ix, y0, c00);
-        crop_px(src, H, W, p, x1, y0, c01);
-        crop_px(src, H, W, p, ix, y1, c10);
-        crop_px(src, H, W, p, x1, y1, c11);
+        crop_px<COPY>(src, H, W, p, ix, y0, c00);
+        crop_px<COPY>(src, H, W, p, x1, y0, c01);
+        crop_px<COPY>(src, H, W, p, ix, y1, c10);
+        crop_px<COPY>(src, H, W, p, x1, y1, c11);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             int s0 = c00[c] * ax0 + c01[c] * ax1, s1 = c10[c] * ax0 + c11[c] * ax1;
@@ -227,7 +234,8 @@ extern "C" int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw,
     CSB_REQUIRE(H > 0 && W > 0, "bad shape");
     CropParams p;
     CSB_REQUIRE(make_crop(H, W, pw, ph, cx, cy, p) == CSB_OK, "bad crop size");
-    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(frame, H, W, p, H, W, out);
+    if (p.a12 == 0 && p.a21 == 0 && p.a22 == 0 && p.a11 == 65536) k_crop_resize<true><<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(frame, H, W, p, H, W, out);
+    else k_crop_resize<false><<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(frame, H, W, p, H, W, out);
     return csb::launched("k_crop_resize", (cudaStream_t) stream);
 }
 
@@ -239,7 +247,8 @@ extern "C" int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, i
     }
     CropParams p;   // full-frame 'crop' at integer offset 0: getRectSubPix degenerates to a copy, leaving cv2.resize(INTER_LINEAR)
     CSB_REQUIRE(make_crop(Ho, Wo, W, H, (W - 1) * 0.5, (H - 1) * 0.5, p) == CSB_OK, "bad size");
-    k_crop_resize<<<csb::wave_grid((long long) Ho * Wo, 256, 8), 256, 0, (cudaStream_t) stream>>>(src, H, W, p, Ho, Wo, dst);
+    if (p.a12 == 0 && p.a21 == 0 && p.a22 == 0 && p.a11 == 65536) k_crop_resize<true><<<csb::wave_grid((long long) Ho * Wo, 256, 8), 256, 0, (cudaStream_t) stream>>>(src, H, W, p, Ho, Wo, dst);
+    else k_crop_resize<false><<<csb::wave_grid((long long) Ho * Wo, 256, 8), 256, 0, (cudaStream_t) stream>>>(src, H, W, p, Ho, Wo, dst);
     return csb::launched("k_crop_resize", (cudaStream_t) stream);
 }
 
@@ -264,6 +273,7 @@ extern "C" int csb_kenburns_frame(const float* points, const float* data, int N,
     k_fill_holes<<<csb::num_sms() * 8, 256, 0, st>>>(acc, mask, zkey, nholes, H, W, packed, depth_out);
     CSB_TRY(csb::launched("k_fill_holes", st));
     if (!out) return CSB_OK;                       // caller post-processes `packed` (bokeh) and crops with csb_frame_crop_resize
-    k_crop_resize<<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, H, W, out);
+    if (p.a12 == 0 && p.a21 == 0 && p.a22 == 0 && p.a11 == 65536) k_crop_resize<true><<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, H, W, out);
+    else k_crop_resize<false><<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, H, W, out);
     return csb::launched("k_crop_resize", st);
 }

@@ -229,11 +229,15 @@ __global__ void __launch_bounds__(256) k_resample(const __half* __restrict__ x, 
     const long long total = (long long) N * Ho * Wo * cv;
     const float sh = mode == 2 ? (Ho > 1 ? (float) (Hi - 1) / (float) (Ho - 1) : 0.0f) : (float) Hi / (float) Ho;
     const float sw = mode == 2 ? (Wo > 1 ? (float) (Wi - 1) / (float) (Wo - 1) : 0.0f) : (float) Wi / (float) Wo;
+    const unsigned ucv = (unsigned) cv, uWo = (unsigned) Wo, uHo = (unsigned) Ho;
     for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
-        const int c0 = (int) (i % cv) * 8;
-        const long long p = i / cv;
-        const int ox = (int) (p % Wo), oy = (int) ((p / Wo) % Ho);
-        const long long n = p / ((long long) Wo * Ho);
+        // index split in 32-bit arithmetic (the host guarantees N*Ho*Wo*cv < 2^32): 64-bit div/mod cost ~200 instructions per thread here
+        const unsigned ui = (unsigned) i;
+        const int c0 = (int) (ui % ucv) * 8;
+        const unsigned up = ui / ucv;
+        const long long p = up;
+        const int ox = (int) (up % uWo), oy = (int) ((up / uWo) % uHo);
+        const long long n = up / (uWo * uHo);
         const __half* xb = x + n * Hi * Wi * ldx + xoff + c0;
         H8 out;
         if (mode == 0) {
@@ -296,6 +300,40 @@ __global__ void __launch_bounds__(256) k_image_prep_s2d(const uint8_t* __restric
         }
         if (r == P - 1)
             for (int e = P * P * 3; e < CP; ++e) y[cell * CP + e] = __float2half_rn(0.f);
+    }
+}
+
+// The detector's case (P = 4, CP = 64, W % 4 == 0): one thread per output cell.  Each patch row is 12 bytes at a 4-byte aligned address (three 32-bit
+// loads), the 48 + 16 halves of the cell leave as eight 16-byte stores; index arithmetic in 32 bits.  (The generic kernel above issues 2-byte stores
+// and three 64-bit div/mods per thread: 0.73 ms per 32 frames against ~0.1 ms of HBM time.)
+__global__ void __launch_bounds__(256) k_image_prep_s2d4(const uint8_t* __restrict__ img, unsigned ncell, int Ho, int Wo, int H, int W, float m0, float m1,
+                                                         float m2, float s0, float s1, float s2, int swap_rb, __half* __restrict__ y) {
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    for (unsigned cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncell; cell += gridDim.x * blockDim.x) {
+        const unsigned ox = cell % (unsigned) Wo, t = cell / (unsigned) Wo, oy = t % (unsigned) Ho, n = t / (unsigned) Ho;
+        const uint8_t* src = img + (((size_t) n * H + (size_t) oy * 4) * W + (size_t) ox * 4) * 3;
+        float o[64];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(src + (size_t) r * W * 3);
+            const uint32_t w0 = __ldg(row), w1 = __ldg(row + 1), w2 = __ldg(row + 2);
+            uint8_t px[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { px[k] = (uint8_t) (w0 >> (8 * k)); px[4 + k] = (uint8_t) (w1 >> (8 * k)); px[8 + k] = (uint8_t) (w2 >> (8 * k)); }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const int c = e % 3, cs = swap_rb ? 2 - c : c;
+                o[r * 12 + e] = ((float) px[e - c + cs] - mean[c]) / sd[c];
+            }
+        }
+#pragma unroll
+        for (int e = 48; e < 64; ++e) o[e] = 0.f;
+        __half* dst = y + (size_t) cell * 64;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float v[8] = {o[8 * g], o[8 * g + 1], o[8 * g + 2], o[8 * g + 3], o[8 * g + 4], o[8 * g + 5], o[8 * g + 6], o[8 * g + 7]};
+            *reinterpret_cast<H8*>(dst + 8 * g) = pack8(v);
+        }
     }
 }
 
@@ -386,8 +424,13 @@ extern "C" int csb_image_prep_s2d_nhwc(const uint8_t* img, int N, int H, int W, 
                                        void* stream) {
     CSB_REQUIRE(img && mean3 && std3 && y, "null pointer");
     CSB_REQUIRE(N > 0 && P > 0 && H % P == 0 && W % P == 0 && CP >= P * P * 3 && CP % 8 == 0, "H and W must be multiples of P, CP >= 3 P^2");
-    k_image_prep_s2d<<<csb::wave_grid((long long) N * (H / P) * (W / P) * P, 256, 8), 256, 0, (cudaStream_t) stream>>>(
-        img, N, H, W, P, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], swap_rb, CP, (__half*) y);
+    const long long ncell = (long long) N * (H / P) * (W / P);
+    if (P == 4 && CP == 64 && ncell < (1ll << 31) && ((uintptr_t) img & 3) == 0 && ((uintptr_t) y & 15) == 0)
+        k_image_prep_s2d4<<<csb::wave_grid(ncell, 256, 8), 256, 0, (cudaStream_t) stream>>>(img, (unsigned) ncell, H / P, W / P, H, W, mean3[0], mean3[1], mean3[2],
+                                                                                              std3[0], std3[1], std3[2], swap_rb, (__half*) y);
+    else
+        k_image_prep_s2d<<<csb::wave_grid((long long) N * (H / P) * (W / P) * P, 256, 8), 256, 0, (cudaStream_t) stream>>>(
+            img, N, H, W, P, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], swap_rb, CP, (__half*) y);
     return csb::launched("k_image_prep", (cudaStream_t) stream);
 }
 
@@ -709,6 +752,7 @@ extern "C" int csb_resample_nhwc(const void* x, int ldx, int xoff, int N, int Hi
                                  void* stream) {
     CSB_REQUIRE(x && y, "null pointer");
     CSB_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && xoff % 8 == 0 && ldy % 8 == 0 && yoff % 8 == 0 && mode >= 0 && mode <= 2, "bad channel layout or mode");
+    CSB_REQUIRE((long long) N * Ho * Wo * (C / 8) < (1ll << 32), "output too large for the 32-bit index split (split the batch)");
     k_resample<<<csb::wave_grid((long long) N * Ho * Wo * (C / 8), 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) x, ldx, xoff, N, Hi, Wi, C, Ho, Wo,
                                                                                                              mode, (__half*) y, ldy, yoff);
     return csb::launched("k_resample", (cudaStream_t) stream);
