@@ -39,6 +39,7 @@ struct AttnParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -109,19 +110,22 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// shared memory map (offsets from the 1 KiB-aligned base); every streamed tile is double-buffered
+// shared memory map (offsets from the 1 KiB-aligned base): K double-buffered (consumed early, by the S GEMM two blocks ahead), V^T and bias / P in a
+// ring of three (their loads are issued a whole block before use, once P V of the block that last used the stage has completed)
 constexpr uint32_t kOffQ = 0;                      // 128 q x 128 B
 constexpr uint32_t kOffK = 16384;                  // 2 stages x (64 keys x 128 B)
-constexpr uint32_t kOffV = 32768;                  // 2 stages x (64 d x 128 B of keys)
-constexpr uint32_t kOffP = 49152;                  // 2 stages x (128 q x 128 B of keys): bias tile, overwritten in place by P
-constexpr uint32_t kOffBar = 81920;                // barriers q, k[2], v[2], b[2], s[2], o[2] + TMEM slot
-constexpr uint32_t kSmemBytes = kOffBar + 128 + 1024 /*alignment slack*/;
+constexpr uint32_t kOffV = 32768;                  // 3 stages x (64 d x 128 B of keys)
+constexpr uint32_t kOffP = 57344;                  // 3 stages x (128 q x 128 B of keys): bias tile, overwritten in place by P
+constexpr uint32_t kOffBar = 106496;               // barriers q, k[2], v[3], b[3], s[2], o, p[3], done + TMEM slot
+constexpr uint32_t kSmemBytes = kOffBar + 192 + 1024 /*alignment slack*/;
+constexpr int kThreadsAttn = 160;                  // warps 0-3: softmax (thread t <-> query row t <-> TMEM lane t); warp 4: TMA + MMA issuer
 
-__global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(kThreadsAttn, 2) k_attention_tc(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmK,
                                                          const __grid_constant__ CUtensorMap tmVT, const __grid_constant__ CUtensorMap tmBias, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_q = base + kOffBar, bar_k = bar_q + 8, bar_v = bar_q + 24, bar_b = bar_q + 40, bar_s = bar_q + 56, bar_o = bar_q + 72, tmem_slot = bar_q + 88;      // bar_o: one barrier (one O accumulator)
+    const uint32_t bar_q = base + kOffBar, bar_k = bar_q + 8, bar_v = bar_q + 24, bar_b = bar_q + 48, bar_s = bar_q + 72, bar_o = bar_q + 88, bar_p = bar_q + 96, bar_done = bar_q + 120,
+                   tmem_slot = bar_q + 128;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x >> 5, tid = threadIdx.x;
     // batch fastest: the CTAs that share one (head, query block) slice of the bias run together and hit it in L2
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVT) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBias) : "memory");
-        for (int i = 0; i < 11; ++i) mbar_init(bar_q + 8u * i, 1);
+        for (int i = 0; i < 16; ++i) mbar_init(bar_q + 8u * i, (i >= 12 && i <= 14) ? 128u : 1u);      // bar_p: one arrival per softmax thread
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -157,15 +161,15 @@ __global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__
         mbar_expect_tx(bar, kBK * 128);
         tma_load_3d(base + kOffK + (uint32_t) (j & 1) * 8192u, &tmK, bar, ck, j * kBK, b);
     };
-    auto load_v = [&](int j) {          // V^T [64 d][keys j*64 .. +64)
-        const uint32_t bar = bar_v + 8u * (j & 1);
+    auto load_v = [&](int j) {          // V^T [64 d][keys j*64 .. +64) -> stage j % 3
+        const uint32_t bar = bar_v + 8u * (uint32_t) (j % 3);
         mbar_expect_tx(bar, kD * 128);
-        tma_load_3d(base + kOffV + (uint32_t) (j & 1) * 8192u, &tmVT, bar, j * kBK, 0, b * p.heads + h);
+        tma_load_3d(base + kOffV + (uint32_t) (j % 3) * 8192u, &tmVT, bar, j * kBK, 0, b * p.heads + h);
     };
-    auto load_bias = [&](int j) {       // bias[h][q0 .. +128)[j*64 .. +64) INTO the P stage
-        const uint32_t bar = bar_b + 8u * (j & 1);
+    auto load_bias = [&](int j) {       // bias[h][q0 .. +128)[j*64 .. +64) INTO P stage j % 3
+        const uint32_t bar = bar_b + 8u * (uint32_t) (j % 3);
         mbar_expect_tx(bar, kBQ * 128);
-        tma_load_3d(base + kOffP + (uint32_t) (j & 1) * 16384u, &tmBias, bar, j * kBK, q0, h);
+        tma_load_3d(base + kOffP + (uint32_t) (j % 3) * 16384u, &tmBias, bar, j * kBK, q0, h);
     };
     auto issue_s = [&](int j) {         // S_j = Q K_j^T -> S[j & 1]
         const uint64_t adesc = make_desc(base + kOffQ), bdesc = make_desc(base + kOffK + (uint32_t) (j & 1) * 8192u);
@@ -174,26 +178,51 @@ __global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__
         umma_commit(bar_s + 8u * (j & 1));
     };
 
-    if (tid == 0) {
-        mbar_expect_tx(bar_q, kBQ * 128);
-        tma_load_3d(base + kOffQ, &tmQKV, bar_q, cq, q0, b);
-        load_k(0);
-        load_bias(0);
-        if (n > 1) load_k(1);
-        load_v(0);
-        if (n > 1) { load_bias(1); load_v(1); }
-        mbar_wait(bar_q, 0);
-        mbar_wait(bar_k, 0);
-        tc_fence_after();
-        issue_s(0);
-        if (n > 1) {
-            mbar_wait(bar_k + 8, 0);
+    if (warp == 4) {
+        // ===================================================== TMA + MMA issuer (one lane): the softmax warps never wait for each other or for a GEMM
+        if (threadIdx.x == 128) {
+            mbar_expect_tx(bar_q, kBQ * 128);
+            tma_load_3d(base + kOffQ, &tmQKV, bar_q, cq, q0, b);
+            load_k(0);
+            load_bias(0);
+            if (n > 1) load_k(1);
+            load_v(0);
+            if (n > 1) { load_bias(1); load_v(1); }
+            mbar_wait(bar_q, 0);
+            mbar_wait(bar_k, 0);
             tc_fence_after();
-            issue_s(1);
+            issue_s(0);
+            if (n > 1) {
+                mbar_wait(bar_k + 8, 0);
+                tc_fence_after();
+                issue_s(1);
+            }
+            for (int j = 0; j < n; ++j) {
+                const int st = j & 1, s3 = j % 3;
+                const uint32_t ph = (uint32_t) ((j >> 1) & 1), ph3 = (uint32_t) ((j / 3) & 1);
+                if (j + 2 < n) {                                                            // S_j complete -> K stage st is free: prefetch K_{j+2}
+                    mbar_wait(bar_s + 8u * st, ph);
+                    load_k(j + 2);
+                }
+                if (j > 0) mbar_wait(bar_o, (uint32_t) ((j - 1) & 1));                      // P V_{j-1} done: V / P stage (j + 2) % 3 is free
+                if (j + 2 < n) { load_bias(j + 2); load_v(j + 2); }
+                mbar_wait(bar_p + 8u * (uint32_t) s3, ph3);                                 // P_j written by all 128 rows, S_j fully read
+                mbar_wait(bar_v + 8u * (uint32_t) s3, ph3);
+                tc_fence_after();
+                const uint64_t adesc = make_desc(base + kOffP + (uint32_t) s3 * 16384u), bdesc = make_desc(base + kOffV + (uint32_t) s3 * 8192u);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) umma_f16(tmem_base + 128u, adesc + 2u * k, bdesc + 2u * k, idesc, (j | k) != 0);      // O += P V_j
+                umma_commit(bar_o);
+                if (j + 2 < n) {                                                            // S GEMM of block j + 2 into the S buffer just released
+                    mbar_wait(bar_k + 8u * st, ph ^ 1u);
+                    tc_fence_after();
+                    issue_s(j + 2);
+                }
+            }
+            mbar_wait(bar_o, (uint32_t) ((n - 1) & 1));                                     // the last P V: O is final
+            mbar_arrive(bar_done);
         }
-    }
-    __syncwarp();
-
+    } else {
     // Online softmax with LAZY rescaling: O accumulates in TMEM across the key blocks (tcgen05.mma accumulate) relative to a reference maximum
     // m_ref per row that is only moved -- and O / l only rescaled, by the warp that owns the rows -- when some row's maximum has grown by more
     // than 2^8 since (P then stays <= 256, exact enough in fp16 and fp32).  The per-block read-modify of O through registers that the textbook
@@ -205,24 +234,14 @@ __global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__
     constexpr float kLog2e = 1.4426950408889634f;
 
     for (int j = 0; j < n; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (uint32_t) ((j >> 1) & 1);
-        // ---------------- 1. P V_{j-1} has finished (it ran during the tail of the previous iteration): its V / P stages are free again;
-        //                  prefetch block j + 1 into them now, so that the loads hide behind this block's softmax
-        if (j > 0) {
-            mbar_wait(bar_o, (uint32_t) ((j - 1) & 1));
-            tc_fence_after();
-            if (tid == 0 && j + 1 < n) { load_bias(j + 1); load_v(j + 1); }
-            __syncwarp();
-        }
-        // ---------------- 2. softmax of block j (S_j in TMEM, bias tile in shared memory)
-        mbar_wait(bar_b + 8u * st, ph);
+        const int st = j & 1, s3 = j % 3;                                                  // S / K stage, V / bias / P stage
+        const uint32_t ph = (uint32_t) ((j >> 1) & 1), ph3 = (uint32_t) ((j / 3) & 1);
+        // ---------------- 1. softmax of block j (S_j in TMEM, bias tile in shared memory); nothing of the previous block is waited for
+        mbar_wait(bar_b + 8u * (uint32_t) s3, ph3);
         mbar_wait(bar_s + 8u * st, ph);
         tc_fence_after();
-        if (tid == 0 && j + 2 < n) load_k(j + 2);                                           // S_j is complete: K stage st is free
-        __syncwarp();
         const uint32_t tmem_s = tmem_base + (uint32_t) st * 64u + lane_addr;
-        const uint32_t prow = base + kOffP + (uint32_t) st * 16384u + (uint32_t) tid * 128u;
+        const uint32_t prow = base + kOffP + (uint32_t) s3 * 16384u + (uint32_t) tid * 128u;
         // S_j is read from TMEM ONCE (64 fp32 per thread stay in registers between the maximum and the exponentials)
         float t[kBK];
         float mxp[8];                                                                       // 8 independent maxima: no 64-deep FMNMX chain
@@ -254,7 +273,10 @@ __global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__
             const float alpha = ex2(m_ref - m_new);                                        // first block: exp2(-inf) = 0
             m_ref = m_new;
             l_run *= alpha;
-            if (j > 0) {                                                                    // O rows of this warp *= alpha (P V_{j-1} is complete)
+            if (j > 0) {                                                                    // O rows of this warp *= alpha, once P V_{j-1} is complete
+                // (no parity aliasing: S_j is complete, hence P V_{j-2} is; bar_o has seen j - 1 or j completions)
+                mbar_wait(bar_o, (uint32_t) ((j - 1) & 1));
+                tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t v[32];
@@ -281,26 +303,11 @@ __global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__
         l_run += (sump[0] + sump[1]) + (sump[2] + sump[3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                        // P (generic proxy) -> tcgen05.mma (async proxy)
         tc_fence_before();
-        __syncthreads();                                                                    // all rows of P written, all reads of S_j done
-        // ---------------- 3. O += P V_j, and the S GEMM of block j + 2 into the S buffer just released
-        if (tid == 0) {
-            tc_fence_after();
-            mbar_wait(bar_v + 8u * st, ph);
-            tc_fence_after();
-            const uint64_t adesc = make_desc(base + kOffP + (uint32_t) st * 16384u), bdesc = make_desc(base + kOffV + (uint32_t) st * 8192u);
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) umma_f16(tmem_base + 128u, adesc + 2u * k, bdesc + 2u * k, idesc, (j | k) != 0);
-            umma_commit(bar_o);
-            if (j + 2 < n) {
-                mbar_wait(bar_k + 8u * st, ph ^ 1u);                                        // K_{j+2}: the next fill of this stage
-                tc_fence_after();
-                issue_s(j + 2);
-            }
-        }
-        __syncwarp();
+        mbar_arrive(bar_p + 8u * (uint32_t) s3);                                            // this row of P is written, this row of S_j is read
     }
-    // ---------------- normalise and store this query row (128 B)
-    mbar_wait(bar_o, (uint32_t) ((n - 1) & 1));
+    // ---------------- normalise and store this query row (128 B).  (A parity wait can only tell the current phase from the one before it, and the
+    // softmax threads do not follow bar_o phase by phase: the issuer signals the final P V on its own barrier.)
+    mbar_wait(bar_done, 0);
     tc_fence_after();
     {
         const float inv = 1.0f / l_run;
@@ -320,6 +327,7 @@ __global__ void __launch_bounds__(128, 2) k_attention_tc(const __grid_constant__
             }
         }
     }
+    }   // softmax warps
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -412,6 +420,6 @@ extern "C" int csb_attention_bias_tc(const void* qkv, int B, int T, int heads, i
     static std::once_flag attr_once;
     std::call_once(attr_once, [] { cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes); });
     const long long grid = (long long) B * p.nqb * heads;
-    k_attention_tc<<<(unsigned) grid, 128, kSmemBytes, st>>>(tmQKV, tmK, tmVT, tmBias, p);
+    k_attention_tc<<<(unsigned) grid, kThreadsAttn, kSmemBytes, st>>>(tmQKV, tmK, tmVT, tmBias, p);
     return csb::launched("k_attention_tc", st);
 }
