@@ -53,17 +53,19 @@ __global__ void __launch_bounds__(256) k_attractor(const float* __restrict__ A, 
 // reads of the 128-channel embedding are contiguous across lanes even though the +33 channel offset leaves them unaligned).
 __global__ void __launch_bounds__(256) k_zoe_cond_input(const __half* __restrict__ feat, const float* __restrict__ rel, int hr, int wr,
                                                         const __half* __restrict__ emb, int he, int we, int N, int H, int W, __half* __restrict__ out) {
-    const long long total = (long long) N * H * W * 22;
+    const long long total = (long long) N * H * W * 22;           // < 2^32 (checked by the host): index split in 32-bit arithmetic
     for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < total; i += (long long) gridDim.x * blockDim.x) {
-        const int g = (int) (i % 22);
-        const long long pix = i / 22;
+        const unsigned ui = (unsigned) i;
+        const int g = (int) (ui % 22u);
+        const unsigned upix = ui / 22u;
+        const long long pix = upix;
         uint4* o4 = reinterpret_cast<uint4*>(out + pix * 176) + g;
         if (g < 4) {                                                          // outconv_activation, copied
             *o4 = reinterpret_cast<const uint4*>(feat + pix * 32)[g];
             continue;
         }
-        const int x = (int) (pix % W), y = (int) ((pix / W) % H);
-        const long long n = pix / ((long long) W * H);
+        const int x = (int) (upix % (unsigned) W), y = (int) ((upix / (unsigned) W) % (unsigned) H);
+        const long long n = upix / ((unsigned) W * (unsigned) H);
         int y0, y1, x0, x1;
         float ly, lx;
         ac_coord(y, he, H, y0, y1, ly);
@@ -102,6 +104,62 @@ __device__ __forceinline__ float log_binom(float n, float k) {     // dist_layer
     n += 1e-7f;
     k += 1e-7f;
     return n * logf(n) - k * logf(k) - (n - k) * logf(n - k + 1e-7f);
+}
+
+// K = 64 (the shipped config): log_binom(K-1, k) does not depend on the pixel -- one evaluation per CTA into shared memory (the same fp32
+// expression, so results are bit-identical to the generic kernel below, which evaluated 6 K logf per pixel) -- and y_k is computed once and kept in
+// registers for the max and the exp pass.
+__global__ void __launch_bounds__(256) k_logbinom_depth64(const float* __restrict__ pt, const float* __restrict__ bc, int hb, int wb, int N, int H, int W,
+                                                          float p_eps, float min_temp, float max_temp, float* __restrict__ depth) {
+    constexpr int K = 64;
+    __shared__ float s_lb[K];
+    if (threadIdx.x < K) s_lb[threadIdx.x] = log_binom((float) (K - 1), (float) threadIdx.x);
+    __syncthreads();
+    const long long total = (long long) N * H * W;
+    for (long long pix = blockIdx.x * (long long) blockDim.x + threadIdx.x; pix < total; pix += (long long) gridDim.x * blockDim.x) {
+        const unsigned upix = (unsigned) pix;                                 // N*H*W < 2^32 (checked by the host)
+        const int x = (int) (upix % (unsigned) W), y = (int) ((upix / (unsigned) W) % (unsigned) H);
+        const long long n = upix / ((unsigned) W * (unsigned) H);
+        const float4 q = *reinterpret_cast<const float4*>(pt + pix * 4);
+        const float p0 = q.x + p_eps, p1 = q.y + p_eps, t0 = q.z + p_eps, t1 = q.w + p_eps;
+        float p = p0 / (p0 + p1);
+        const float t = (max_temp - min_temp) * (t0 / (t0 + t1)) + min_temp;
+        const float omp = fminf(fmaxf(1.f - p, 1e-4f), 1.f);
+        p = fminf(fmaxf(p, 1e-4f), 1.f);
+        const float lp = logf(p), lq = logf(omp);
+        int y0, y1, x0, x1;
+        float ly, lx;
+        ac_coord(y, hb, H, y0, y1, ly);
+        ac_coord(x, wb, W, x0, x1, lx);
+        const float* B = bc + n * hb * wb * K;
+        const float4* b00 = reinterpret_cast<const float4*>(B + ((size_t) y0 * wb + x0) * K);
+        const float4* b01 = reinterpret_cast<const float4*>(B + ((size_t) y0 * wb + x1) * K);
+        const float4* b10 = reinterpret_cast<const float4*>(B + ((size_t) y1 * wb + x0) * K);
+        const float4* b11 = reinterpret_cast<const float4*>(B + ((size_t) y1 * wb + x1) * K);
+        float yk[K];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            yk[k] = (s_lb[k] + (float) k * lp + (float) (K - 1 - k) * lq) / t;
+            mx = fmaxf(mx, yk[k]);
+        }
+        float se = 0.f, sc = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < K / 4; ++k4) {
+            const float4 c00 = __ldg(b00 + k4), c01 = __ldg(b01 + k4), c10 = __ldg(b10 + k4), c11 = __ldg(b11 + k4);
+            const float cc[4] = {(1.f - ly) * ((1.f - lx) * c00.x + lx * c01.x) + ly * ((1.f - lx) * c10.x + lx * c11.x),
+                                 (1.f - ly) * ((1.f - lx) * c00.y + lx * c01.y) + ly * ((1.f - lx) * c10.y + lx * c11.y),
+                                 (1.f - ly) * ((1.f - lx) * c00.z + lx * c01.z) + ly * ((1.f - lx) * c10.z + lx * c11.z),
+                                 (1.f - ly) * ((1.f - lx) * c00.w + lx * c01.w) + ly * ((1.f - lx) * c10.w + lx * c11.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float e = expf(yk[4 * k4 + j] - mx);
+                se += e;
+                sc += e * cc[j];
+            }
+        }
+        depth[pix] = sc / se;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_logbinom_depth(const float* __restrict__ pt, const float* __restrict__ bc, int hb, int wb, int N, int H, int W, int K,
@@ -152,6 +210,7 @@ extern "C" int csb_zoe_attractor(const float* A, int na, const float* b_prev, in
 extern "C" int csb_zoe_cond_input(const void* feat32, const float* rel, int hr, int wr, const void* emb128, int he, int we, int N, int H, int W, void* out176,
                                   void* stream) {
     CSB_REQUIRE(feat32 && rel && emb128 && out176 && N > 0 && H > 0 && W > 0, "bad arguments");
+    CSB_REQUIRE((long long) N * H * W * 22 < (1ll << 32), "batch too large for the 32-bit index split (split it)");
     k_zoe_cond_input<<<csb::wave_grid((long long) N * H * W * 22, 256, 8), 256, 0, (cudaStream_t) stream>>>((const __half*) feat32, rel, hr, wr, (const __half*) emb128, he, we,
                                                                                                        N, H, W, (__half*) out176);
     return csb::launched("k_zoe_cond_input", (cudaStream_t) stream);
@@ -160,7 +219,11 @@ extern "C" int csb_zoe_cond_input(const void* feat32, const float* rel, int hr, 
 extern "C" int csb_zoe_logbinom_depth(const float* pt4, const float* b_centers, int hb, int wb, int N, int H, int W, int nbins, float p_eps, float min_temp,
                                       float max_temp, float* depth, void* stream) {
     CSB_REQUIRE(pt4 && b_centers && depth && N > 0 && H > 0 && W > 0 && nbins > 1, "bad arguments");
-    k_logbinom_depth<<<csb::wave_grid((long long) N * H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(pt4, b_centers, hb, wb, N, H, W, nbins, p_eps, min_temp, max_temp,
-                                                                                                       depth);
+    if (nbins == 64 && (long long) N * H * W < (1ll << 32) && ((uintptr_t) b_centers & 15) == 0)
+        k_logbinom_depth64<<<csb::wave_grid((long long) N * H * W, 256, 4), 256, 0, (cudaStream_t) stream>>>(pt4, b_centers, hb, wb, N, H, W, p_eps, min_temp, max_temp,
+                                                                                                             depth);
+    else
+        k_logbinom_depth<<<csb::wave_grid((long long) N * H * W, 256, 8), 256, 0, (cudaStream_t) stream>>>(pt4, b_centers, hb, wb, N, H, W, nbins, p_eps, min_temp,
+                                                                                                           max_temp, depth);
     return csb::launched("k_logbinom_depth", (cudaStream_t) stream);
 }
