@@ -82,7 +82,12 @@ class ZoeHead:
         self.seed_proj = _MLP(sd, "seed_projector._net", dev)
         self.proj = [_MLP(sd, f"projectors.{i}._net", dev) for i in range(4)]
         self.attr = [_MLP(sd, f"attractors.{i}._net", dev, last_act='softplus') for i in range(4)]
-        self.clb = _MLP(sd, "conditional_log_binomial.mlp", dev, last_act='softplus', cin_pad=176)
+        # csb_zoe_cond_input writes [feat 0..31 | embedding 32..159 | rel_depth 160] (the reference concatenates [feat, rel, embedding]): permute the
+        # input channels of the first 1x1 conv to that order
+        clb = dict(sd)
+        w0 = sd["conditional_log_binomial.mlp.0.weight"]
+        clb["conditional_log_binomial.mlp.0.weight"] = torch.cat([w0[:, :32], w0[:, 33:161], w0[:, 32:33]], 1)
+        self.clb = _MLP(clb, "conditional_log_binomial.mlp", dev, last_act='softplus', cin_pad=176)
 
     def forward(self, rel_depth, outconv, btlnck, blocks):
         N = btlnck.shape[0]

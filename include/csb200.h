@@ -309,7 +309,9 @@ CSB_API int csb_refine_post(const float* d1, int K, int S, int h, int w, int H, 
  * layers/attractor.py:139-208, layers/dist_layers.py:29-121.  All fp32 NHWC unless stated.
  *   csb_zoe_attractor      A [N,h,w,na] (softplus outputs), b_prev [N,hp,wp,nbins] -> bilinear(align_corners=True) -> b_new [N,h,w,nbins] =
  *                          c + mean_a dx/(1 + alpha dx^2), dx = A_a - c  (alpha = 300: the function default the reference actually uses).
- *   csb_zoe_cond_input     out176 [N,H,W,176] fp16 = [feat32 fp16 | interp(rel [N,hr,wr]) | interp(emb128 fp16 [N,he,we,128]) | 0-pad].
+ *   csb_zoe_cond_input     out176 [N,H,W,176] fp16 = [feat32 fp16 (0..31) | interp(emb128 fp16 [N,he,we,128]) (32..159) | interp(rel [N,hr,wr]) (160) | 0-pad]:
+ *                          the reference's cat([feat, rel, emb]) with the rel channel moved behind the embedding (16 B aligned groups); permute the input
+ *                          channels of conditional_log_binomial.mlp.0 accordingly.
  *   csb_zoe_logbinom_depth pt4 [N,H,W,4] (softplus outputs: p0,p1,t0,t1), b_centers [N,hb,wb,nbins] -> depth [N,H,W]. */
 CSB_API int csb_zoe_attractor(const float* A, int na, const float* b_prev, int hp, int wp, int N, int h, int w, int nbins, float alpha, float* b_new, void* stream);
 CSB_API int csb_zoe_cond_input(const void* feat32, const float* rel, int hr, int wr, const void* emb128, int he, int we, int N, int H, int W, void* out176,
