@@ -1,0 +1,65 @@
+"""CPU suite: host-side logic added around the CUDA path (no GPU, no compute calls into the library)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def test_fold_layernorm_is_layernorm_then_linear():
+    """engine.fold_layernorm: LayerNorm(gamma, beta) -> Linear(W, b) == rstd * (x W'^T - mean * colsum) + b' on the un-normalised x -- the identity the
+    fc1 GEMM epilogue of the ConvNeXt block (csb_conv2d_ln_nhwc) relies on (mmpretrain ConvNeXtBlock: norm -> pointwise_conv1)."""
+    from cartoonsegmentation_b200 import engine as E
+    g = torch.Generator().manual_seed(0)
+    C, Co, P = 128, 512, 37
+    x = torch.randn(P, C, generator=g) * 2.0 + 1.5
+    w, b = torch.randn(Co, C, generator=g) / C ** 0.5, torch.randn(Co, generator=g) * 0.1
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    ref = F.linear(F.layer_norm(x, (C,), gamma, beta, 1e-6), w, b)
+    wp, bp, cs = E.fold_layernorm(w, b, gamma, beta, dtype=torch.float32)
+    assert wp.shape == (Co, 1, 1, C) and bp.shape == (Co,) and cs.shape == (Co,)
+    mean = x.mean(1, keepdim=True)
+    rstd = torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-6)
+    out = rstd * (x @ wp.reshape(Co, C).t() - mean * cs[None]) + bp[None]
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4)
+    # the column sums are those of the ROUNDED fp16 weights, so that the mean term cancels exactly against the fp16 GEMM
+    wp16, _, cs16 = E.fold_layernorm(w, b, gamma, beta)
+    assert wp16.dtype == torch.float16 and torch.equal(cs16, wp16.float().reshape(Co, C).sum(1))
+
+
+def test_midas_net_size_matches_reference_resize():
+    """`Resize(width, height, keep_aspect_ratio=True, ensure_multiple_of=32, resize_method='minimal').get_size` (midas.py:104-148) for the sizes on
+    the path: the Ken-Burns pipeline's img_size [672, 672] on a reflect-padded 1024^2 frame, MidasCore's default 384, load_zoe's [512, 672]."""
+    from cartoonsegmentation_b200.depth_modules.zoedepth import midas_net_size
+
+    def ref(h, w, net_h, net_w, m=32):
+        sh, sw = net_h / h, net_w / w
+        if abs(1 - sw) < abs(1 - sh):
+            sh = sw
+        else:
+            sw = sh
+        c = lambda v: int(np.round(v / m) * m)
+        return c(sh * h), c(sw * w)
+
+    pad = int(np.sqrt(1024 / 2) * 3)
+    assert midas_net_size(1024 + 2 * pad, 1024 + 2 * pad, [672, 672]) == (672, 672)
+    assert midas_net_size(1158, 1158) == (384, 384) == midas_net_size(1158, 1158, 384)
+    for (h, w, net) in [(720, 960, (512, 672)), (480, 640, (384, 384)), (1000, 700, (672, 672)), (333, 517, (512, 672))]:
+        assert midas_net_size(h, w, net) == ref(h, w, *net)
+
+
+def test_bench_workload_config_names_the_stages():
+    import bench
+    c = bench.workload_config(32, 8, ("seg", "depth", "warp"), "leres")
+    assert c["stages"] == ["seg", "depth", "warp"] and c["depth"] == "leres" and "LeReS" in c["workload"] and c["batch_frames_per_step"] == 32
+    z = bench.workload_config(32, 8, ("seg", "depth", "warp"), "zoe")
+    assert "ZoeDepth" in z["workload"] and "672" in z["workload"]
+    w = bench.workload_config(4, 2, ("warp",))
+    assert w["depth"] is None and any("seg" in m for m in w["stages_missing"])
+
+
+def test_zoe_cond_input_channel_permutation_is_a_permutation():
+    """ZoeHead feeds ConditionalLogBinomial.mlp.0 the channel order [feat 0..31 | embedding 32..159 | rel 160] (csb_zoe_cond_input); the reference
+    concatenates [feat, rel, embedding] (zoedepth_v1.py:176-184).  The weight columns must be the matching permutation."""
+    w0 = torch.arange(161, dtype=torch.float32)[None].repeat(3, 1)
+    perm = torch.cat([w0[:, :32], w0[:, 33:161], w0[:, 32:33]], 1)
+    assert perm.shape == w0.shape and sorted(perm[0].tolist()) == list(range(161))
+    assert perm[0, 160] == 32 and perm[0, 32] == 33 and perm[0, 159] == 160
