@@ -111,13 +111,32 @@ class _FTB:
         return self.cb(t, pad=1, act='relu', residual=y, res_mode=1)
 
 
+STEM_S2D = __import__("os").environ.get("CSB_LERES_S2D", "1") != "0"       # space-to-depth form of the 7x7 stride-2 stem (see LeReS.__init__)
+
+
 class LeReS:
     """B200 forward of RelDepthModel(backbone='resnext101').depth_model: [N,H,W,3] uint8 BGR -> [N,H,W] fp32 depth logits."""
 
     def __init__(self, state_dict=None, device='cuda'):
         sd = synthetic_state_dict(0) if state_dict is None else {k[7:] if k.startswith('module.') else k: v for k, v in state_dict.items()}
         dev = self.dev = torch.device(device)
-        self.stem = _C(*_fold(sd[f"{ENC}.conv1.weight"], None, sd, f"{ENC}.bn1"), dev, cin_pad=16)
+        w7, b7 = _fold(sd[f"{ENC}.conv1.weight"], None, sd, f"{ENC}.bn1")
+        self.stem = _C(w7, b7, dev, cin_pad=16)
+        # The 7x7 stride-2 pad-3 stem (Resnext_torch.py:156) as a 5x5 stride-1 pad-2 conv over the 2x2 space-to-depth image (12 channels, padded to
+        # 16): in[2y + r - 3] = s2d[y + a][dy] with r - 3 = 2a + dy, a in [-2, 1] (tap a = 2 is zero).  K shrinks from 49 x 16 to 25 x 16 and the
+        # prep kernel writes a quarter of the bytes; same products, same zero padding.
+        w5 = torch.zeros((w7.shape[0], 12, 5, 5), dtype=w7.dtype)
+        for a in range(-2, 2):
+            for dy in range(2):
+                r = 2 * a + dy + 3
+                if not 0 <= r <= 6:
+                    continue
+                for bb in range(-2, 2):
+                    for dx in range(2):
+                        s_ = 2 * bb + dx + 3
+                        if 0 <= s_ <= 6:
+                            w5[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3, a + 2, bb + 2] = w7[:, :, r, s_]
+        self.stem_s2d = _C(w5, b7, dev, cin_pad=16)
         self.layers = []
         for li, nblk in enumerate(LAYERS, start=1):
             blocks = []
@@ -137,8 +156,8 @@ class LeReS:
         self.ao0 = _C(*_fold(sd[f"{DEC}.outconv.adapt_conv.0.weight"], sd[f"{DEC}.outconv.adapt_conv.0.bias"], sd, f"{DEC}.outconv.adapt_conv.1"), dev)
         self.ao1 = _C(sd[f"{DEC}.outconv.adapt_conv.3.weight"], sd[f"{DEC}.outconv.adapt_conv.3.bias"], dev)
 
-    def encoder(self, x16):
-        x = self.stem(x16, stride=2, pad=3, act='relu')
+    def encoder(self, x16, s2d=False):
+        x = self.stem_s2d(x16, stride=1, pad=2, act='relu') if s2d else self.stem(x16, stride=2, pad=3, act='relu')
         x = E.maxpool3s2_nhwc(x)
         feats = []
         for blocks in self.layers:
@@ -163,8 +182,11 @@ class LeReS:
         N, H, W, _ = img_u8.shape
         assert H % 32 == 0 and W % 32 == 0
         # estimateleres: BGR -> RGB (depthmap.py:35), ToTensor on float (no /255 again), Normalize(ImageNet) (:26) on img/255
-        x16 = E.image_prep_nhwc(img_u8, [255.0 * m for m in IMAGENET_MEAN], [255.0 * s for s in IMAGENET_STD], swap_rb=not rgb_input, CP=16)
-        f = self.encoder(x16)
+        mean, std = [255.0 * m for m in IMAGENET_MEAN], [255.0 * s for s in IMAGENET_STD]
+        if STEM_S2D:
+            f = self.encoder(E.image_prep_s2d_nhwc(img_u8, mean, std, 2, 16, swap_rb=not rgb_input), s2d=True)
+        else:
+            f = self.encoder(E.image_prep_nhwc(img_u8, mean, std, swap_rb=not rgb_input, CP=16))
         x32 = self.conv1(self.conv(f[3]), pad=1)
         x16_ = E.resample_nhwc(x32, x32.shape[1] * 2, x32.shape[2] * 2, 'bilinear_ac')
         x8 = self._ffm("ffm2", f[2], x16_)

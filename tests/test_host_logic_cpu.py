@@ -63,3 +63,24 @@ def test_zoe_cond_input_channel_permutation_is_a_permutation():
     perm = torch.cat([w0[:, :32], w0[:, 33:161], w0[:, 32:33]], 1)
     assert perm.shape == w0.shape and sorted(perm[0].tolist()) == list(range(161))
     assert perm[0, 160] == 32 and perm[0, 32] == 33 and perm[0, 159] == 160
+
+
+def test_leres_stem_space_to_depth_rearrangement():
+    """LeReS.__init__: the 7x7 stride-2 pad-3 stem (Resnext_torch.py:156) == a 5x5 stride-1 pad-2 conv over the 2x2 space-to-depth image with the
+    weights rearranged as in depth_modules/leres.py (channel (dy*2+dx)*3 + c = pixel (2Y+dy, 2X+dx), what csb_image_prep_s2d_nhwc writes)."""
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 32, 48, generator=g)
+    w7 = torch.randn(8, 3, 7, 7, generator=g)
+    w5 = torch.zeros(8, 12, 5, 5)
+    for a in range(-2, 2):
+        for dy in range(2):
+            r = 2 * a + dy + 3
+            if not 0 <= r <= 6:
+                continue
+            for bb in range(-2, 2):
+                for dx in range(2):
+                    s_ = 2 * bb + dx + 3
+                    if 0 <= s_ <= 6:
+                        w5[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3, a + 2, bb + 2] = w7[:, :, r, s_]
+    s2d = torch.stack([x[:, :, dy::2, dx::2] for dy in range(2) for dx in range(2)], 1).reshape(2, 12, 16, 24)
+    assert torch.allclose(F.conv2d(s2d, w5, stride=1, padding=2), F.conv2d(x, w7, stride=2, padding=3), atol=1e-4)
