@@ -443,7 +443,11 @@ def main():
             ach = gflop / prof[dom]["ms"]                             # GFLOP / ms = TFLOP/s
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
                     "peak_source": "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback",
-                    "launches_per_step": prof[dom]["count"], "algorithmic_gflop_per_step": gflop, "avg_launch_us": 1e3 * prof[dom]["ms"] / prof[dom]["count"]}
+                    "launches_per_step": prof[dom]["count"], "algorithmic_gflop_per_step": gflop, "avg_launch_us": 1e3 * prof[dom]["ms"] / prof[dom]["count"],
+                    # `traffic` stays null: one step is ~270 launches of ~60 different layer shapes, so there is no single per-launch figure; the ncu
+                    # --set full captures of the two heaviest shapes are summarised in profiles/ (DRAM bytes == algorithmic bytes there)
+                    "traffic_note": "profiles/r1_fc1_epilogue_ncu.md: 512->2048 @32x64x64 moves 623 MB of DRAM traffic for 673 MB algorithmic, "
+                                    "128->512 @16x256x256 1290 MB for 1342 MB"}
         elif dom:
             alg_bytes = {"k_splat": 52 * P, "k_zpass": 16 * P, "k_degrid": 8 * P, "k_norm_pack_mark": 24 * P, "k_crop_resize": 6 * P, "k_d2c_max": 4 * P,
                          "k_d2c_scale": 12 * P, "k_d2c_points": 55 * P}
