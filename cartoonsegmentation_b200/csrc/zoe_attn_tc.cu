@@ -5,18 +5,22 @@
 //
 //   out[b, q, h*64 + :] = softmax_k( Q[b,h,q,:] . K[b,h,k,:] * scale + bias[h, q, k] ) . V[b,h,k,:]
 //
-// One CTA = 128 queries of one (batch, head), 4 warps, thread t <-> query row t <-> TMEM lane t, so the softmax needs no cross-thread reduction.
-// Per 64-key block (every streamed tile -- K, V^T, bias / P -- and both TMEM accumulators are double-buffered):
-//   S   = Q K^T        4 x tcgen05.mma M128 N64 K16, operands TMA-staged in 128B-swizzled shared memory (Q once, K double-buffered), S in TMEM
-//   P   = exp2(S * scale * log2e + bias * log2e - m)   two passes over the TMEM row (row maximum, then exponentials), fp32 -> fp16 into a
-//                      128B-swizzled shared tile that is the A operand of the second GEMM.  The 128 x 128 bias tile is TMA-loaded INTO that
-//                      tile (same shape, same swizzle) and each thread overwrites its bias chunk with its P chunk in place: a thread reading
+// One CTA = 128 queries of one (batch, head): warps 0-3 do the softmax (thread t <-> query row t <-> TMEM lane t, so it needs no cross-thread
+// reduction), warp 4 is the TMA + MMA issuer; the two sides talk through mbarriers only (no CTA barrier inside the key loop -- with
+// __syncthreads the softmax warps spent 27 % of their time waiting for the warp that also issued, ncu).
+// Per 64-key block:
+//   S   = Q K^T        4 x tcgen05.mma M128 N64 K16, operands TMA-staged in 128B-swizzled shared memory (Q once, K double-buffered), S
+//                      double-buffered in TMEM: S_{j+2} is issued right behind P V_j
+//   P   = exp2(S * scale * log2e + bias * log2e - m_ref)   S is read from TMEM once (64 fp32 per thread), fp32 -> fp16 into a 128B-swizzled
+//                      shared tile that is the A operand of the second GEMM.  The 128 x 64 bias tile is TMA-loaded INTO that tile (same shape,
+//                      same swizzle, ring of three) and each thread overwrites its bias chunk with its P chunk in place: a thread reading
 //                      its own bias row straight from global memory touches 32 different lines per warp instruction, which made the first
 //                      version of this kernel L1-tag bound at the speed of the mma.sync kernel (2.19 ms per launch at B = 32, T = 1765)
-//   O_j = P V          4 x tcgen05.mma M128 N64 K16; V arrives TRANSPOSED ([b, h, d, key], written by k_transpose_v) so that both operands are
+//   O  += P V          4 x tcgen05.mma M128 N64 K16; V arrives TRANSPOSED ([b, h, d, key], written by k_transpose_v) so that both operands are
 //                      K-major; O accumulates in TMEM over all key blocks (online softmax with lazy rescaling, see below)
-// S_{j+2} is issued right behind P V_j, so neither GEMM nor any TMA load sits on the softmax's critical path.  Two CTAs per SM (82 KB shared memory, 256 TMEM columns each).
-// Work per (b, h): 4 T^2 64 FLOP; the kernel is bound by the softmax's instruction issue / MUFU.EX2 (one exp2 per score), not by the tensor pipe.
+// Two CTAs per SM (105 KB shared memory, 256 TMEM columns each).  Work per (b, h): 4 T^2 64 FLOP; 0.94 ms per launch at B = 32, T = 1765
+// (434 TFLOP/s); the kernel is bound by the softmax's instruction issue (654 warp instructions per block and warp, one MUFU.EX2 per score),
+// not by the tensor pipe.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
