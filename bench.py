@@ -48,6 +48,28 @@ def make_inputs(n_scenes):
     return imgs, disp
 
 
+# ------------------------------------------------------------------------------------------------ exactly ONE line on stdout
+# Libraries write to file descriptor 1 behind Python's back (NCCL prints "NCCL version ..." at communicator creation).  Everything written to
+# fd 1 during the run is sent to stderr; the JSON line goes to the saved, real stdout.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -177,7 +199,7 @@ def run_reference(args):
     steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
     sec = cpu.time(imgs, disp, steps, warm)
     fps = 1.0 / sec
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1000.0 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(1, 2, stages, args.depth),
@@ -282,6 +304,7 @@ def main():
     ap.add_argument("--no-other", action="store_true", help="skip other_workloads (infer_batch32, kenburns_full)")
     ap.add_argument("--other-images", type=int, default=3, help="input images of the kenburns_full workload")
     args = ap.parse_args()
+    capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -480,7 +503,7 @@ def main():
                 out["cpu_baseline"] = {"value": cpu_arm(imgs_np[:2], disp_np[:2], 4, 1), "unit": "frames/s", "cores": 1, "kind": "port",
                                        "sample": "4 frames of 1024x1024 on 1 thread through the WARP stage only (oracle/kb_oracle.c); the DPT-BEiT-L CPU oracle @672^2 "
                                                  "needs minutes per frame -- run the default --depth leres workload for an all-stage CPU baseline"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
