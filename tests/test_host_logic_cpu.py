@@ -84,3 +84,80 @@ def test_leres_stem_space_to_depth_rearrangement():
                         w5[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3, a + 2, bb + 2] = w7[:, :, r, s_]
     s2d = torch.stack([x[:, :, dy::2, dx::2] for dy in range(2) for dx in range(2)], 1).reshape(2, 12, 16, 24)
     assert torch.allclose(F.conv2d(s2d, w5, stride=1, padding=2), F.conv2d(x, w7, stride=2, padding=3), atol=1e-4)
+
+
+def _constants_from(path, pattern):
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), path)).read()
+    return [float(x) for x in re.findall(pattern, src)]
+
+
+def test_gelu_sigmoid_form_constants_reproduce_exact_gelu():
+    """csrc/tc_conv.cu gelu2_mufu: gelu(x) = x / (1 + 2^(x * q(min(x^2, 64)))) with the three constants in the source (which carry -2 log2 e): the
+    float32 evaluation stays within 3e-5 of the exact erf GELU (nn.GELU(), mmpretrain ConvNeXtBlock) over [-12, 12], saturates correctly beyond."""
+    from scipy.special import erf
+    body = open(__file__.replace("tests/test_host_logic_cpu.py", "cartoonsegmentation_b200/csrc/tc_conv.cu")).read()
+    body = body[body.index("void gelu2_mufu"):body.index("#ifndef CSB_GELU_MUFU_PAIRS")]
+    import re
+    c5, c3, c1 = [np.float32(v) for v in re.findall(r"CSB_C2\((-?[0-9.eE+-]+)f\)", body)[:3]]
+    assert c1 < 0 and abs(c1 / (-2 * np.log2(np.e)) - 0.7975) < 1e-3          # leading coefficient ~ sqrt(2/pi)
+    x = np.linspace(-12, 12, 200001).astype(np.float32)
+    x2 = np.minimum(x * x, np.float32(64))
+    q = (c5 * x2 + c3) * x2 + c1
+    with np.errstate(over='ignore'):
+        y = x * (np.float32(1) / (np.float32(1) + np.exp2((q * x).astype(np.float64)).astype(np.float32)))
+    ref = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
+    assert np.abs(y - ref).max() < 3e-5
+    for big in (-1e4, -50.0, 50.0, 1e4):                                      # exp overflow -> 0, underflow -> x
+        xb = np.float32(big)
+        qb = (c5 * np.float32(64) + c3) * np.float32(64) + c1
+        with np.errstate(over='ignore'):
+            eb = np.float32(np.exp2(np.float64(qb * xb)))                      # ex2.approx.ftz.f32: overflows to +inf, underflows to 0
+            yb = xb * (np.float32(1) / (np.float32(1) + eb))
+        assert yb == (0.0 if big < 0 else big)
+
+
+def test_lazy_rescaling_online_softmax_matches_attention():
+    """The algorithm of csrc/zoe_attn_tc.cu restated in numpy: 64-key blocks, scores in log2 units, a reference maximum that only moves (and
+    rescales O and l) when a row's block maximum exceeds it by more than 8, P rounded to fp16 before P V, fp32 accumulation -- against plain
+    softmax attention with an additive bias (timm BEiT Attention as MiDaS patches it)."""
+    rng = np.random.default_rng(0)
+    T, d = 300, 64
+    q, k, v = (rng.standard_normal((T, d)).astype(np.float32) * 1.5 for _ in range(3))
+    bias = (rng.standard_normal((T, T)) * 4).astype(np.float32)
+    bias[:, 5] += 40.0                                                        # a late, dominant key forces rescaling steps
+    scale = d ** -0.5
+    s = q @ k.T * scale + bias
+    ref = np.exp(s - s.max(1, keepdims=True))
+    ref = (ref / ref.sum(1, keepdims=True)) @ v
+    log2e = np.float32(1.4426950408889634)
+    Tp = (T + 63) // 64 * 64
+    sp = np.full((T, Tp), -60000.0, np.float32)
+    sp[:, :T] = bias
+    kp = np.zeros((Tp, d), np.float32); kp[:T] = k
+    vp = np.zeros((Tp, d), np.float32); vp[:T] = v
+    m_ref = np.full(T, -np.inf, np.float32)
+    l = np.zeros(T, np.float32)
+    o = np.zeros((T, d), np.float32)
+    rescales = 0
+    for j in range(Tp // 64):
+        t = (q @ kp[j * 64:(j + 1) * 64].T) * np.float32(scale) * log2e + sp[:, j * 64:(j + 1) * 64] * log2e
+        mx = t.max(1)
+        for w in range(0, T, 32):                                             # the decision is per warp (32 rows)
+            rows = slice(w, min(T, w + 32))
+            if np.any(mx[rows] - m_ref[rows] > 8.0):
+                m_new = np.maximum(m_ref[rows], mx[rows])
+                with np.errstate(invalid='ignore'):
+                    alpha = np.where(np.isinf(m_ref[rows]), 0.0, np.exp2(m_ref[rows] - m_new)).astype(np.float32)
+                m_ref[rows] = m_new
+                l[rows] *= alpha
+                o[rows] *= alpha[:, None]
+                rescales += 1
+        p = np.exp2(t - m_ref[:, None]).astype(np.float32)
+        assert p.max() <= 256.0 * 1.0001                                       # what keeps fp16 P exact enough
+        l += p.sum(1)
+        o += p.astype(np.float16).astype(np.float32) @ vp[j * 64:(j + 1) * 64]
+    out = o / l[:, None]
+    rr = np.sqrt(((out - ref) ** 2).mean() / (ref ** 2).mean())
+    assert rr < 1e-3 and rescales < (Tp // 64) * ((T + 31) // 32)              # exact enough, and genuinely lazy
