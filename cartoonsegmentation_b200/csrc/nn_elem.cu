@@ -553,10 +553,14 @@ constexpr int kDwThreads = 128;
 // STATS: also emit, per pixel and per 64-channel chunk, (sum, sum of squares) of the fp16-rounded outputs -> stats[pixel][C/64][2] fp32.  The
 // following C -> 4C GEMM applies the LayerNorm of the ConvNeXt block in its epilogue from these (csb_conv2d_ln_nhwc), so the separate
 // LayerNorm pass over the activations (read + write of 2 C B/px) disappears.
-template <int K, int ACT, bool STATS = false>       // ACT: the fused activation, compiled in (CSB_ACT_NONE / CSB_ACT_SILU), or -1 = decided at run time from `act`
-__global__ void __launch_bounds__(kDwThreads, 3) k_dwconv_tile(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, int act, int N, int H, int W, int C, __half* __restrict__ y, int ldy,
+// LDC > 0: the channel stride of x and y is the compile-time constant LDC (dense tensors, ldx == ldy == C): the (2 + K - 1) x (8 + K - 1) halo loads and
+// the 16 stores of a tile then address [base + immediate] instead of spending 3-4 integer instructions each on `ix * ldx` -- SASS of the generic build:
+// 224 FFMA2 in a 703-instruction filter-row loop, i.e. the kernel was issue-bound by address arithmetic at 33 % of the FFMA peak.
+template <int K, int ACT, bool STATS = false, int LDC = 0>       // ACT: the fused activation, compiled in (CSB_ACT_NONE / CSB_ACT_SILU), or -1 = decided at run time
+__global__ void __launch_bounds__(kDwThreads, 3) k_dwconv_tile(const __half* __restrict__ x, int ldx_, int xoff, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int act, int N, int H, int W, int C_, __half* __restrict__ y, int ldy_,
                                                         int yoff, float* __restrict__ stats = nullptr) {
+    const int ldx = LDC > 0 ? LDC : ldx_, ldy = LDC > 0 ? LDC : ldy_, C = LDC > 0 ? LDC : C_;
     constexpr int R = K / 2, TSY = 2, TSX = 8, INX = TSX + K - 1;
     __shared__ float2 wsm[K * K * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -710,7 +714,10 @@ extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w,
         const dim3 grid(gx, chunks);
         const int a = ln_gamma ? CSB_ACT_NONE : act;
 #define CSB_DW_LAUNCH(KK, AA) k_dwconv_tile<KK, AA><<<grid, kDwThreads, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff)
-        if (K == 5) { if (a == CSB_ACT_NONE) CSB_DW_LAUNCH(5, CSB_ACT_NONE); else if (a == CSB_ACT_SILU) CSB_DW_LAUNCH(5, CSB_ACT_SILU); else CSB_DW_LAUNCH(5, -1); }
+        static const bool const_ld = [] { const char* e = getenv("CSB_DW_CONST_LD"); return !e || atoi(e) != 0; }();
+        if (K == 5 && a == CSB_ACT_SILU && const_ld && C == 128 && ldx == C && ldy == C)       // CSPNeXtPAFPN blocks: dense 128-channel tensors
+            k_dwconv_tile<5, CSB_ACT_SILU, false, 128><<<grid, kDwThreads, 0, st>>>(xh, ldx, xoff, w, bias, a, N, H, W, C, yh, ldy, yoff);
+        else if (K == 5) { if (a == CSB_ACT_NONE) CSB_DW_LAUNCH(5, CSB_ACT_NONE); else if (a == CSB_ACT_SILU) CSB_DW_LAUNCH(5, CSB_ACT_SILU); else CSB_DW_LAUNCH(5, -1); }
         else { if (a == CSB_ACT_NONE) CSB_DW_LAUNCH(7, CSB_ACT_NONE); else if (a == CSB_ACT_SILU) CSB_DW_LAUNCH(7, CSB_ACT_SILU); else CSB_DW_LAUNCH(7, -1); }
 #undef CSB_DW_LAUNCH
         CSB_TRY(csb::launched("k_dwconv_tile", st));
@@ -736,8 +743,16 @@ extern "C" int csb_dwconv_stats_nhwc(const void* x, int ldx, int xoff, const flo
     const long long need = (ntiles + kDwThreads / 32 - 1) / (kDwThreads / 32);
     gx = gx > need ? (int) need : gx;
     gx = gx < 1 ? 1 : gx;
-    k_dwconv_tile<7, CSB_ACT_NONE, true><<<dim3(gx, chunks), kDwThreads, 0, st>>>((const __half*) x, ldx, xoff, w, bias, CSB_ACT_NONE, N, H, W, C, (__half*) y, ldy,
-                                                                                  yoff, stats);
+#define CSB_DWS(LDC_) k_dwconv_tile<7, CSB_ACT_NONE, true, LDC_><<<dim3(gx, chunks), kDwThreads, 0, st>>>((const __half*) x, ldx, xoff, w, bias, CSB_ACT_NONE, N, H, W, C, \
+                                                                                                      (__half*) y, ldy, yoff, stats)
+    static const bool const_ld = [] { const char* e = getenv("CSB_DW_CONST_LD"); return !e || atoi(e) != 0; }();
+    const bool dense = const_ld && ldx == C && ldy == C;            // the ConvNeXt stages: compile-time channel stride
+    if (dense && C == 128) CSB_DWS(128);
+    else if (dense && C == 256) CSB_DWS(256);
+    else if (dense && C == 512) CSB_DWS(512);
+    else if (dense && C == 1024) CSB_DWS(1024);
+    else CSB_DWS(0);
+#undef CSB_DWS
     return csb::launched("k_dwconv_tile", st);
 }
 
