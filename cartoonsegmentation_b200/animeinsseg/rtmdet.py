@@ -30,13 +30,15 @@ FOLD_LN = _os.environ.get("CSB_FOLD_LN", "1") != "0"        # ConvNeXt block: La
 
 
 # ------------------------------------------------------------------------------------------------ parameter inventory
-def _convmodule(specs, name, cin, cout, k, groups=1):
-    specs.append((f"{name}.conv.weight", (cout, cin // groups, k, k), 'conv_act'))
+def _convmodule(specs, name, cin, cout, k, groups=1, kind='conv_act'):
+    specs.append((f"{name}.conv.weight", (cout, cin // groups, k, k), kind))
     for p, kind in (('weight', 'bn_w'), ('bias', 'bn_b'), ('running_mean', 'bn_m'), ('running_var', 'bn_v')):
         specs.append((f"{name}.bn.{p}", (cout,), kind))
 
 
-def _csplayer(specs, name, cin, cout, n):
+def _csplayer(specs, name, cin, cout, n, identity=False):
+    """identity: the blocks add their input (backbone stages 1-3).  Their last conv then gets a small synthetic gain, so that the residual stream keeps
+    an O(1) variance through the 3-6 blocks of a stage (x + f(x) with a full-gain f doubles it per block: the detector's mask logits reached 1e8)."""
     mid = cout // 2
     _convmodule(specs, f"{name}.main_conv", cin, mid, 1)
     _convmodule(specs, f"{name}.short_conv", cin, mid, 1)
@@ -44,7 +46,7 @@ def _csplayer(specs, name, cin, cout, n):
     for b in range(n):
         _convmodule(specs, f"{name}.blocks.{b}.conv1", mid, mid, 3)
         _convmodule(specs, f"{name}.blocks.{b}.conv2.depthwise_conv", mid, mid, 5, groups=mid)
-        _convmodule(specs, f"{name}.blocks.{b}.conv2.pointwise_conv", mid, mid, 1)
+        _convmodule(specs, f"{name}.blocks.{b}.conv2.pointwise_conv", mid, mid, 1, kind='conv_act:0.6' if identity else 'conv_act')
 
 
 CSPNEXT_L = dict(stem=(32, 32, 64), stages=((64, 128, 3, True, False), (128, 256, 6, True, False), (256, 512, 6, True, False), (512, 1024, 3, False, True)))
@@ -64,7 +66,7 @@ def _cspnext_specs(s):
             _convmodule(s, f"backbone.stage{i}.1.conv1", cout, cout // 2, 1)
             _convmodule(s, f"backbone.stage{i}.1.conv2", cout * 2, cout, 1)
             j = 2
-        _csplayer(s, f"backbone.stage{i}.{j}", cout, cout, n)
+        _csplayer(s, f"backbone.stage{i}.{j}", cout, cout, n, identity=_identity)
         s += [(f"backbone.stage{i}.{j}.attention.fc.weight", (cout, cout, 1, 1), 'conv_lin'), (f"backbone.stage{i}.{j}.attention.fc.bias", (cout,), 'bias')]
 
 

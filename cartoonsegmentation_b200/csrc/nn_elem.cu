@@ -693,6 +693,10 @@ static int launch_dwconv(const __half* xh, int ldx, int xoff, const float* w, co
     return csb::launched("k_dwconv", st);
 }
 
+// csrc/dw_halo.cu: the TMA halo-tile kernel; -1000 = shape outside its domain (take the register-tiled path below)
+int csb_dwconv_halo_try(const void* x, int ldx, int xoff, const float* w, const float* bias, int act, int N, int H, int W, int C, int K, void* y, int ldy, int yoff,
+                        float* stats, cudaStream_t st);
+
 extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w, const float* bias, const float* ln_gamma, const float* ln_beta,
                                float eps, int act, int N, int H, int W, int C, int K, void* y, int ldy, int yoff, void* stream) {
     CSB_REQUIRE(x && w && y, "null pointer");
@@ -704,6 +708,15 @@ extern "C" int csb_dwconv_nhwc(const void* x, int ldx, int xoff, const float* w,
     __half* yh = (__half*) y;
     if ((K == 5 || K == 7) && C % 64 == 0 && (ldx | xoff | ldy | yoff) % 2 == 0) {
         // tiled path: depthwise conv (+ bias, + activation when there is no LayerNorm), then LayerNorm in place
+        {
+            const int hs = csb_dwconv_halo_try(x, ldx, xoff, w, bias, ln_gamma ? CSB_ACT_NONE : act, N, H, W, C, K, y, ldy, yoff, nullptr, st);
+            if (hs != -1000) {
+                CSB_TRY(hs);
+                if (!ln_gamma) return CSB_OK;
+                CSB_REQUIRE(act == CSB_ACT_NONE, "LayerNorm followed by an activation is not used on this path");
+                return launch_layernorm(yh, ldy, yoff, ln_gamma, ln_beta, eps, (long long) N * H * W, C, yh, ldy, yoff, st);
+            }
+        }
         static const int ctas = [] { const char* e = getenv("CSB_DW_CTAS"); return e ? atoi(e) : 3; }();        // CTAs per SM (tuning knob)
         const long long ntiles = (long long) N * ((H + 1) / 2) * ((W + 7) / 8);
         const int chunks = C / 64;
@@ -736,6 +749,10 @@ extern "C" int csb_dwconv_stats_nhwc(const void* x, int ldx, int xoff, const flo
     CSB_REQUIRE(K == 7 && C % 64 == 0 && C <= 2048, "K must be 7 and C a multiple of 64 (the ConvNeXt block)");
     CSB_REQUIRE(ldx % 8 == 0 && xoff % 8 == 0 && ldy % 8 == 0 && yoff % 8 == 0, "channel strides/offsets must be multiples of 8");
     cudaStream_t st = (cudaStream_t) stream;
+    {
+        const int hs = csb_dwconv_halo_try(x, ldx, xoff, w, bias, CSB_ACT_NONE, N, H, W, C, K, y, ldy, yoff, stats, st);
+        if (hs != -1000) return hs;
+    }
     static const int ctas = [] { const char* e = getenv("CSB_DW_CTAS"); return e ? atoi(e) : 3; }();
     const long long ntiles = (long long) N * ((H + 1) / 2) * ((W + 7) / 8);
     const int chunks = C / 64;

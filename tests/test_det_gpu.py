@@ -78,7 +78,7 @@ def test_network_forward_vs_oracle(env, size):
         errs[f'cls{l}'] = rel_rms(nchw(cls[l]), o_cls[l]); errs[f'reg{l}'] = rel_rms(nchw(reg[l]), o_reg[l]); errs[f'ker{l}'] = rel_rms(nchw(ker[l]), o_ker[l])
     errs['mask_feat'] = rel_rms(nchw(mf), o_mf)
     print("relative RMS error of the fp16 network vs the fp32 oracle:", {k: round(v, 5) for k, v in errs.items()})
-    assert max(errs.values()) < 2e-2, errs
+    assert max(errs.values()) < 5e-3, errs                                       # measured on the B200: 2.5e-3 (cls2), 1.7e-3 (ker2), 1.2e-3 (mask_feat)
 
 
 def _to_nhwc(ts):
@@ -144,11 +144,11 @@ def test_animeinsseg_infer_end_to_end(env):
     best, idx = iou.max(1)
     matched = best > 0.9
     print(f"instances: ours {len(inst)}, oracle {len(ref['scores'])}, matched(IoU>0.9) {int(matched.sum())}")
-    assert matched.float().mean().item() > 0.7
+    assert matched.float().mean().item() >= 0.97                                    # measured: 100 of 100
     mi = [(inst.masks[i].cpu() & ref['masks'][idx[i]]).sum().item() / max(1, (inst.masks[i].cpu() | ref['masks'][idx[i]]).sum().item())
           for i in range(len(inst)) if matched[i] and ref['masks'][idx[i]].any()]
     print("mask IoU of matched instances: mean %.4f min %.4f" % (float(np.mean(mi)), float(np.min(mi))))
-    assert float(np.mean(mi)) > 0.97
+    assert float(np.mean(mi)) > 0.9976                                               # measured 0.9988 (tie-band pixels included; see tests/test_parity_full_gpu.py)
     lst = seg.infer([img, img[:, ::-1].copy()], output_type='numpy', det_size=size)          # list in -> list out, numpy
     assert isinstance(lst, list) and len(lst) == 2 and isinstance(lst[0].masks, np.ndarray)
     assert np.array_equal(lst[0].masks, inst.masks.cpu().numpy())                              # batched == single
@@ -178,7 +178,7 @@ def test_cspnext_l_forward_vs_oracle(built_lib, size):
         errs[f'cls{l}'] = rel_rms(nchw(cls[l]), o_cls[l]); errs[f'reg{l}'] = rel_rms(nchw(reg[l]), o_reg[l]); errs[f'ker{l}'] = rel_rms(nchw(ker[l]), o_ker[l])
     errs['mask_feat'] = rel_rms(nchw(mf), o_mf)
     print("CSPNeXt-L: relative RMS error of the fp16 network vs the fp32 oracle:", {k: round(v, 5) for k, v in errs.items()})
-    assert max(errs.values()) < 2e-2, errs
+    assert max(errs.values()) < 4e-3, errs                                       # measured 1.2e-3
 
 
 def test_cspnext_l_infer_surface(built_lib):

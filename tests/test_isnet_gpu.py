@@ -25,7 +25,7 @@ def test_isnet_forward_vs_reference_golden(built_lib, name):
     rel = np.sqrt(((d1 - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean())
     relc = np.sqrt((((d1 - d1.mean()) - (ref - ref.mean())) ** 2).mean()) / ref.std()
     print(f"{name}: relative RMS error {rel:.5f} (centred {relc:.5f})")
-    assert d1.shape == ref.shape and rel < 1e-2 and relc < 2e-2
+    assert d1.shape == ref.shape and rel < 9e-4 and relc < 2.4e-3          # measured 3.5e-4 / 4.5e-4 (centred 9.4e-4 / 1.2e-3)
     # decision parity at the data's own median level (random weights give all-positive logits; the median puts the threshold inside the data)
     t = np.median(ref)
     assert ((d1 > t) != (ref > t)).mean() < 5e-3

@@ -60,12 +60,12 @@ def test_leres_forward_vs_reference_golden(eng, name):
     rel = np.sqrt(((out - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean())
     rel_c = np.sqrt((((out - out.mean()) - (ref - ref.mean())) ** 2).mean()) / ref.std()
     print(f"{name}: relative RMS error {rel:.5f}, centred (what min-max normalisation sees) {rel_c:.5f}")
-    assert out.shape == ref.shape and rel < 2e-2 and rel_c < 3e-2
-    # after the reference's own 16 -> 8 bit quantisation (apply_leres) the maps agree to a few grey levels
+    assert out.shape == ref.shape and rel < 1e-3 and rel_c < 3.5e-3     # measured 4.4e-4 / 5.7e-4 (centred 1.3e-3 / 1.8e-3); north_star 1e-3
+    # after the reference's own 16 -> 8 bit quantisation (apply_leres) the maps agree to one grey level
     qa, qb = L.quantise_depth(out), L.quantise_depth(ref)
     d = np.abs(qa.astype(int) - qb.astype(int))
     print(f"   8-bit depth image: max |diff| {d.max()} levels, mean {d.mean():.3f}")
-    assert d.mean() < 2.0 and np.percentile(d, 99) <= 6
+    assert d.max() <= 1 and d.mean() < 0.17                                      # measured: max 1 level, mean 0.05 / 0.085 (+-1 LSB)
 
 
 @pytest.mark.parametrize("hw,HW", [((640, 640), (1024, 1024)), ((480, 640), (720, 960)), ((96, 128), (100, 131)), ((64, 96), (64, 96))])

@@ -118,7 +118,7 @@ def test_inpaint_net_vs_reference_golden(built_lib):
         a, b = o[k].cpu().numpy(), g[k]
         rel = np.sqrt(((a - b) ** 2).mean()) / np.sqrt((b ** 2).mean())
         print(f"{k}: relative RMS error {rel:.5f}, max abs {np.abs(a - b).max():.4f}")
-        assert a.shape == b.shape and rel < 2e-2
+        assert a.shape == b.shape and rel < 8.5e-4                                 # measured 3.4e-4 (tenImage) / 4.1e-4 (tenDisparity)
 
 
 @pytest.mark.parametrize("H,W,K,mode", [(200, 260, 9, 'positive'), (200, 260, 9, 'zeros'), (96, 130, 5, 'positive'), (256, 512, 100, 'positive'), (128, 256, 40, 'negative')])

@@ -23,7 +23,7 @@ def test_refine_vs_reference_golden(built_lib):
         assert y.shape == (1, 1) + tuple(hw)
         err = float(np.sqrt(((y[0, 0].cpu().numpy() - ref) ** 2).mean() / (ref ** 2).mean()))
         print("Refine rel RMS vs reference module:", hw, dhw, round(err, 5))
-        assert err < 3e-3, err
+        assert err < 3.5e-4, err                                                    # measured 1.7e-4
 
 
 def test_pipeline_depth_refine_hook(built_lib):

@@ -68,7 +68,7 @@ def test_dpt_beit_vs_transformers_golden(built_lib, hf_weights, Hn, Wn):
         st = max(1, t.shape[1] // 24)
         errs[f"fused{k}"] = _rr(t[0, ::st, ::st].float().cpu(), g[f"fused{k}"].astype(np.float32))
     print("DPT-BEiT-L rel RMS vs transformers fp32:", {k: round(v, 5) for k, v in errs.items()})
-    assert max(errs.values()) < 1e-2, errs                                                  # fp16 storage through 24 blocks + decoder
+    assert max(errs.values()) < 4.4e-3, errs                                                # measured 2.2e-3 (rel)                                                  # fp16 storage through 24 blocks + decoder
 
 
 def test_wrapper_prep_and_finish_vs_torch(built_lib):

@@ -21,4 +21,4 @@ def test_zoe_head_vs_reference_golden(built_lib):
     rel = np.sqrt(((d - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean())
     relc = np.sqrt((((d - d.mean()) - (ref - ref.mean())) ** 2).mean()) / ref.std()
     print(f"ZoeDepth head: relative RMS error {rel:.5f} (centred {relc:.5f}), max abs {np.abs(d - ref).max():.5f}")
-    assert d.shape == ref.shape and rel < 5e-3 and relc < 5e-2
+    assert d.shape == ref.shape and rel < 1e-4 and relc < 1.3e-3       # measured 5e-5 (centred 6.4e-4)
