@@ -210,19 +210,30 @@ def scaledown_maxsize(img: np.ndarray, max_size: int, divisior: int = None):
 
 
 def depth_adjustment_animesseg(instances: AnimeInstances, tenDisparity, tenImage, use_medium=False):
-    """reference :39-91 -- per instance, in order: flatten the disparity under the mask to the maximum found in the bottom 3% of its rows.
-    Same-size, non-median case (the pipeline's): csb_depth_adjust_batch, ONE cooperative launch and NO host sync (the reference does
-    ~8 ATen kernels and 5 `.item()` syncs per instance).  The resized / median variants keep the reference's torch formulation."""
+    """reference :39-91 -- per instance, in order: flatten the disparity under the mask to the maximum found in the bottom 3% of its rows
+    (use_medium: to the lower median of the masked positive disparities, :80).  All variants run on the device without a host sync (the reference
+    does ~8 ATen kernels and 5 `.item()` syncs per instance): csb_depth_adjust_batch (one cooperative launch) / csb_depth_adjust_median (exact radix
+    select); when disparity and image differ in size (:50-56, :86-90) the map goes through csb_resample_f32 (bilinear, align_corners=False) both ways."""
     assert tenDisparity.shape[0] == 1
-    same = tenDisparity.shape[2] == tenImage.shape[2] and tenDisparity.shape[3] == tenImage.shape[3]
-    if same and not use_medium and tenDisparity.is_cuda:
-        out = tenDisparity.contiguous().float().clone()
-        if instances is not None and not instances.is_empty:
-            masks = instances.masks.contiguous()
-            K, H, W = masks.shape
+    if not tenDisparity.is_cuda:
+        raise RuntimeError("depth_adjustment_animesseg: CUDA tensors only (no CPU path)")
+    from ..engine import resample_f32
+    h, w = tenDisparity.shape[2:]
+    H, W = tenImage.shape[2:]
+    out = tenDisparity.contiguous().float()
+    out = resample_f32(out.view(1, h, w), H, W, False).view(1, 1, H, W) if (h, w) != (H, W) else out.clone()
+    if instances is not None and not instances.is_empty:
+        masks = instances.masks.contiguous()
+        K = masks.shape[0]
+        assert masks.shape[1:] == (H, W)
+        if use_medium:
+            state = torch.empty(1040 // 4, device=out.device, dtype=torch.int32)
+            check(lib().csb_depth_adjust_median(ptr(out), ptr(masks.view(torch.uint8)), K, H, W, ptr(state), stream()), "csb_depth_adjust_median")
+        else:
             depth_adjust_batch(out.view(1, H, W), masks.view(1, K, H, W), torch.tensor([K], device=out.device, dtype=torch.int32))
-        return out
-    return depth_adjustment_animesseg_torch(instances, tenDisparity, tenImage, use_medium)
+    if (h, w) != (H, W):
+        out = resample_f32(out.view(1, H, W), h, w, False).view(1, 1, h, w)
+    return out
 
 
 def depth_adjust_batch(disparity, masks, num):
@@ -232,28 +243,6 @@ def depth_adjust_batch(disparity, masks, num):
     state = torch.empty(int(lib().csb_depth_adjust_state_words(N, Kmax, H, W)), device=disparity.device, dtype=torch.int32)
     check(lib().csb_depth_adjust_batch(ptr(disparity), ptr(masks.view(torch.uint8)), ptr(num), N, Kmax, H, W, ptr(state), stream()), "csb_depth_adjust_batch")
     return disparity
-
-
-def depth_adjustment_animesseg_torch(instances: AnimeInstances, tenDisparity, tenImage, use_medium=False):
-    """The reference's own torch formulation (:39-91), kept for the resized / median variants."""
-    assert tenDisparity.shape[0] == 1
-    tenMasks = [] if instances is None or instances.is_empty else [instances.masks[i].float() for i in range(instances.masks.shape[0])]
-    resized = tenDisparity.shape[2] != tenImage.shape[2] or tenDisparity.shape[3] != tenImage.shape[3]
-    tenAdjusted = torch.nn.functional.interpolate(tenDisparity, size=(tenImage.shape[2], tenImage.shape[3]), mode='bilinear', align_corners=False) \
-        if resized else tenDisparity
-    for tenAdjust in tenMasks:
-        tenPlane = tenAdjusted * tenAdjust
-        if tenPlane.sum().item() == 0:
-            continue
-        if not use_medium:
-            rows = (tenPlane.sum([3], True) > 0.0).flatten().nonzero()
-            intTop, intBottom = rows[0].item(), rows[-1].item()
-            tenAdjusted = ((1.0 - tenAdjust) * tenAdjusted) + (tenAdjust * tenPlane[:, :, int(round(intTop + (0.97 * (intBottom - intTop)))):, :].max())
-        else:
-            tenAdjusted[tenPlane > 0] = tenAdjusted[tenPlane > 0].median()
-    if resized:
-        return torch.nn.functional.interpolate(tenAdjusted, size=(tenDisparity.shape[2], tenDisparity.shape[3]), mode='bilinear', align_corners=False)
-    return tenAdjusted
 
 
 class KenBurnsPipeline:
@@ -364,8 +353,8 @@ class KenBurnsPipeline:
             q8 = torch.empty((n, h, w), device=self.device, dtype=torch.uint8)
             out = torch.empty((n, 1, ori_h, ori_w), device=self.device, dtype=torch.float32)
             check(lib().csb_leres_depth_tail(ptr(logits), n, h, w, ori_h, ori_w, ptr(mm), ptr(q8), ptr(out), stream()), "csb_leres_depth_tail")
-            pos_min = torch.where(out > 0, out, torch.full_like(out, float('inf'))).amin(dim=(1, 2, 3), keepdim=True)       # :577, per image
-            out = torch.where(out == 0, pos_min, out)
+            scr = torch.empty(n, device=self.device, dtype=torch.int32)                                    # :577 depth[depth == 0] = depth[depth > 0].min(), per image
+            check(lib().csb_zero_to_min_positive(ptr(out), n, C.c_longlong(ori_h * ori_w), ptr(scr), stream()), "csb_zero_to_min_positive")
             return (None, (ori_h, ori_w), n, out)
         key = tuple(logits.shape)
         if getattr(self, '_leres_pin', None) is None or tuple(self._leres_pin.shape) != key:
@@ -394,8 +383,8 @@ class KenBurnsPipeline:
             self._disp_pin[i, 0] = torch.from_numpy(d)
         out = self._disp_pin.to(self.device, non_blocking=True)               # [N,1,H,W]
         # depth[depth == 0] = depth[depth > 0].min()  (:577), per image, without a host sync
-        pos_min = torch.where(out > 0, out, torch.full_like(out, float('inf'))).amin(dim=(1, 2, 3), keepdim=True)
-        out = torch.where(out == 0, pos_min, out)
+        scr = torch.empty(n, device=self.device, dtype=torch.int32)
+        check(lib().csb_zero_to_min_positive(ptr(out), n, C.c_longlong(ori_h * ori_w), ptr(scr), stream()), "csb_zero_to_min_positive")
         return [out[i:i + 1] for i in range(n)]
 
     def set_inpainting(self, inpainting: str, ckpt=None):
@@ -449,7 +438,13 @@ class KenBurnsPipeline:
         disparity = depth_adjustment_animesseg(instances, disparity, img_tensor, use_medium=self.cfg.depthest_use_medium)      # :604
         if self.cfg.default_depth_refine:                                                                                       # :619-620
             disparity = self.refine_depth(img_tensor, disparity)
-        return disparity                   # refine_crf (:621-622) is out of scope
+        elif self.cfg.refine_crf and not getattr(KenBurnsPipeline, '_warned_crf', False):                                     # :621-622
+            import warnings
+            KenBurnsPipeline._warned_crf = True
+            warnings.warn("KenBurnsConfig.refine_crf=True (the dataclass default; configs/3dkenburns.yaml sets it False): the reference would run its CPU "
+                          "KMeans + floodFill + dense-CRF depth refinement here (kenburns_effect.py:636-809), which is outside this package's hot path "
+                          "(SURVEY.md §8f rank 4) -- the instance-adjusted disparity is used unrefined.  Set refine_crf=False to silence this.")
+        return disparity
 
     # ---- reference :898-951
     def generate_kenburns_config(self, img: np.ndarray, instances: Optional[AnimeInstances] = None, verbose: bool = False, savep=None, disparity=None):

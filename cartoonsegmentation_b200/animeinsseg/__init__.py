@@ -53,8 +53,11 @@ class AnimeInsSeg:
     """reference animeinsseg/__init__.py:185.  `ckpt`: path to a checkpoint whose 'state_dict' uses mmdet parameter names, a state_dict,
     or None for the seeded synthetic ConvNeXt-B RTMDet-Ins weights (BASELINE.json: 'random-init ConvNeXt-B RTMDet weights')."""
 
-    def __init__(self, ckpt=None, default_det_size: int = 640, device: str = None, refine_kwargs: dict = {'refine_method': 'none'},
-                 tagger_path: str = None, mask_thr=0.3) -> None:
+    def __init__(self, ckpt=None, default_det_size: int = 640, device: str = None, refine_kwargs: dict = {'refine_method': 'refinenet_isnet'},
+                 tagger_path: str = None, mask_thr=0.3, max_det_batch: int = 32) -> None:
+        """Defaults as the reference's (:187-189): ISNet mask refinement is ON unless `refine_kwargs={'refine_method': 'none'}` is passed.
+        `max_det_batch` (extension): same-shape images of one `infer` call run through the detector in sub-batches of at most this many
+        (activations of 32 x 1024^2 are ~12 GB, the [N,K,H,W] mask buffer 3.4 GB), so a long list costs no more memory than a short one."""
         self.device = torch.device('cuda' if device is None else device)
         if self.device.type != 'cuda':
             raise RuntimeError("cartoonsegmentation_b200 has no CPU path (the reference's device='cpu' mode is the oracle's job)")
@@ -69,6 +72,7 @@ class AnimeInsSeg:
         test_cfg = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_threshold=0.6), max_per_img=100, min_bbox_size=0, mask_thr_binary=0.5)
         self.model = SimpleNamespace(net=net, bbox_head=SimpleNamespace(test_cfg=test_cfg, prior_generator=SimpleNamespace(strides=[(s, s) for s in STRIDES])))
         self.default_det_size = default_det_size
+        self.max_det_batch = max(1, int(max_det_batch))
         self.det_size = (default_det_size, default_det_size)
         self.postprocess_refine = None
         self.refinenet = None
@@ -180,9 +184,11 @@ class AnimeInsSeg:
             arr, sf, ori = self._prepare(im)
             groups.setdefault((arr.shape, sf, ori), []).append((i, arr))
         for (shape, sf, ori), items in groups.items():
-            batch = torch.from_numpy(np.stack([a for _, a in items])).to(self.device, non_blocking=True)
-            for j, inst in enumerate(self._det_forward(batch, sf, ori, pred_score_thr)):
-                preds[items[j][0]] = inst
+            for s0 in range(0, len(items), self.max_det_batch):           # bounded sub-batches: memory does not grow with the list length
+                sub = items[s0:s0 + self.max_det_batch]
+                batch = torch.from_numpy(np.stack([a for _, a in sub])).to(self.device, non_blocking=True)
+                for j, inst in enumerate(self._det_forward(batch, sf, ori, pred_score_thr)):
+                    preds[sub[j][0]] = inst
         for inst, im in zip(preds, loaded):
             if self.postprocess_refine is not None:
                 self.postprocess_refine(inst, im)

@@ -43,33 +43,30 @@ class AnimeInstances:
     def is_empty(self):
         return self.masks is None or len(self.masks) == 0
 
-    def remove_duplicated(self):
-        """reference :84-127"""
-        num_masks = len(self)
-        if num_masks < 2:
+    def remove_duplicated(self, overlap: float = 0.8):
+        """Drop instances that are mostly covered by larger ones (reference :84-127): visit the masks from the largest to the smallest; an
+        instance whose intersection with the union of the instances kept so far exceeds `overlap` of its own area is a duplicate.
+        (The reference never adds the LAST visited mask to the union -- it has no successor -- which does not change the outcome.)"""
+        n = len(self)
+        if n < 2:
             return
-        need_cvt = False
-        if self.is_numpy:
-            need_cvt = True
-            self.to_tensor()
-        mask_areas = torch.Tensor([mask.sum() for mask in self.masks])
-        sids = torch.argsort(mask_areas, descending=True).cpu().numpy().tolist()
-        mask_areas = mask_areas[sids]
-        masks, bboxes, scores = self.masks[sids], self.bboxes[sids], self.scores[sids]
-        tags = [self.tags[sid] for sid in sids]
-        canvas = masks[0]
-        valid_ids = np.arange(num_masks).tolist()
-        for ii, mask in enumerate(masks[1:]):
-            mask_id = ii + 1
-            and_area = torch.bitwise_and(canvas, mask).sum()
-            if and_area / mask_areas[mask_id] > 0.8:
-                valid_ids.remove(mask_id)
-            elif mask_id != num_masks - 1:
-                canvas = torch.bitwise_or(canvas, mask)
-        self.masks, self.bboxes, self.scores = masks[valid_ids], bboxes[valid_ids], scores[valid_ids]
-        self.tags = [tags[sid] for sid in valid_ids]
-        if need_cvt:
-            self.to_numpy()
+        was_numpy = self.is_numpy
+        masks = torch.from_numpy(self.masks) if was_numpy else self.masks
+        areas = masks.flatten(1).sum(1).to(torch.float32)
+        order = torch.argsort(areas, descending=True)
+        union = torch.zeros_like(masks[0])
+        kept = []
+        for rank, idx in enumerate(order.tolist()):
+            m = masks[idx]
+            if rank > 0 and float((union & m).sum()) / float(areas[idx]) > overlap:
+                continue
+            kept.append(idx)
+            union = union | m
+        sel = torch.as_tensor(kept, device=masks.device, dtype=torch.long)
+        take = (lambda t: t[sel.cpu().numpy()]) if was_numpy else (lambda t: t[sel.to(t.device)])
+        self.masks, self.bboxes, self.scores = take(self.masks), take(self.bboxes), take(self.scores)
+        self.tags = [self.tags[i] for i in kept]
+        self.character_tags = [self.character_tags[i] for i in kept] if self.character_tags is not None else None
 
     def cuda(self):
         if self.is_empty:
@@ -117,26 +114,39 @@ class AnimeInstances:
         return 0 if self.is_empty else len(self.masks)
 
     def resize(self, h, w, mode='area'):
-        """reference :268-280 (incl. its quirk: x scaled by the height ratio, y by the width ratio)"""
+        """reference :268-280: masks -> float -> F.interpolate(mode='area') -> > 0.3; bboxes scaled (x by the height ratio, y by the width ratio:
+        the reference's quirk, kept) and rounded.  On the device: one kernel (csrc/masks.cu), bit-identical to those torch ops."""
         if self.is_empty:
             return
         if self.is_tensor:
-            masks = self.masks.to(torch.float).unsqueeze(1)
-            oh, ow = masks.shape[2], masks.shape[3]
-            hs, ws = h / oh, w / ow
-            bboxes = self.bboxes.float()
-            bboxes[:, ::2] *= hs
-            bboxes[:, 1::2] *= ws
-            self.bboxes = torch.round(bboxes).int()
-            masks = torch.nn.functional.interpolate(masks, (h, w), mode=mode)
-            self.masks = masks.squeeze(1) > 0.3
+            if mode != 'area' or not self.masks.is_cuda:
+                raise NotImplementedError("AnimeInstances.resize: only mode='area' on CUDA tensors (the reference's only call, kenburns_effect.py:918)")
+            from .._lib import check, lib, ptr, stream
+            import ctypes as C
+            K, oh, ow = self.masks.shape
+            src = self.masks.contiguous().view(torch.uint8)
+            out = torch.empty((K, h, w), device=src.device, dtype=torch.uint8)
+            bin_ = self.bboxes.to(torch.int32).contiguous()
+            bout = torch.empty_like(bin_)
+            check(lib().csb_masks_area_resize(ptr(src), K, oh, ow, ptr(out), int(h), int(w), C.c_float(0.3), ptr(bin_), ptr(bout), stream()), "csb_masks_area_resize")
+            self.masks, self.bboxes = out.view(torch.bool), bout
 
     def compose_masks(self, output_type=None):
+        """reference :282-298: logical OR over the instances"""
         if self.is_empty:
             return None
-        mask = self.masks[0]
-        if len(self.masks) > 1:
-            mask = np.logical_or.reduce(self.masks, 0) if self.is_numpy else self.masks.any(0)
+        if self.is_numpy:
+            mask = self.masks[0] if len(self.masks) == 1 else np.logical_or.reduce(self.masks, 0)
+        elif self.masks.is_cuda:
+            from .._lib import check, lib, ptr, stream
+            import ctypes as C
+            K, H, W = self.masks.shape
+            src = self.masks.contiguous().view(torch.uint8)
+            out = torch.empty((H, W), device=src.device, dtype=torch.uint8)
+            check(lib().csb_masks_compose(ptr(src), K, C.c_longlong(H * W), ptr(out), stream()), "csb_masks_compose")
+            mask = out.view(torch.bool)
+        else:
+            mask = self.masks.any(0)
         if output_type is not None:
             if output_type == 'numpy' and not self.is_numpy:
                 mask = mask.cpu().numpy()

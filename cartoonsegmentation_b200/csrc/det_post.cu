@@ -436,7 +436,7 @@ extern "C" int csb_rtmdet_select(const float* const* cls, const float* const* re
     }
     int p2 = 1;
     while (p2 < maxloc) p2 <<= 1;
-    CSB_REQUIRE((size_t) p2 * 8 <= 200 * 1024, "level too large for the shared-memory sort (max 25600 locations)");
+    CSB_REQUIRE((size_t) p2 * 8 <= 200 * 1024, "level too large for the shared-memory sort: the location count is padded to a power of two and must be <= 16384 per level (det_size <= 1024)");
     cudaStream_t st = (cudaStream_t) stream;
     static std::once_flag once;
     std::call_once(once, [] {

@@ -7,7 +7,7 @@
 //   * a CTA walks a contiguous range of (64-channel chunk, 32 x 16 pixel tile) tasks; for every task ONE 4-D TMA box {64 ch, 32 + K - 1, 16 + K - 1, 1}
 //     lands in shared memory (zero padding = the TMA unit's out-of-bounds fill: no boundary predicates in the inner loop), double buffered, the box of
 //     task t + 1 in flight while task t is computed (one mbarrier per buffer);
-//   * 8 warps each own an 8-pixel-wide column strip x 8 rows of the tile and slide the round-1 register micro-kernel (2 x 8 outputs x 2 channels per
+//   * 16 warps each own an 8-pixel-wide column strip x 4 rows of the tile and slide the round-1 register micro-kernel (2 x 8 outputs x 2 channels per
 //     lane, fp32 packed FFMA2, taps in shared memory) down it, reading inputs with immediate-offset LDS.32 (a warp reads one 128 B pixel: no conflicts);
 //   * halo re-reads drop from 7x to 1.63x and come from L2; DRAM traffic is the compulsory 4 C B/px.
 // Arithmetic order per output is the one of k_dwconv_tile (bias, then taps row-major), so results are bit-identical to round 1.
@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kWarps = 16, kThreads = kWarps * 32;    // 4 warps per scheduler: ncu of the 8-warp build showed the FMA pipe 59 % busy, `wait` / `math_pipe_throttle` the top stalls
 constexpr int BW = 32, BH = 16;                    // output pixels of one CTA tile (per 64-channel chunk)
 
 struct DwHaloParams {
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dwconv_halo(const __grid_consta
     const uint32_t bar0 = sbase + 2u * G::kStageBytes + G::kWeightBytes;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cx = warp & 3, ry = warp >> 2;                       // 4 column strips of 8 px x 2 row groups of 8 rows
+    const int cx = warp & 3, ry = warp >> 2;                       // 4 column strips of 8 px x kWarps/4 row groups
+    constexpr int kRowsPerWarp = BH / (kWarps / 4);
     const long long total = p.ntiles * p.chunks;                   // chunk-major task order: a CTA's range touches at most a few chunks
     const long long t0 = total * blockIdx.x / gridDim.x, t1 = total * (blockIdx.x + 1) / gridDim.x;
 
@@ -135,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dwconv_halo(const __grid_consta
         const __half2* strip = reinterpret_cast<const __half2*>(smem + (size_t) s * G::kStageBytes) + (size_t) (cx * TSX) * 32 + lane;
         if (ox0 < p.W) {
 #pragma unroll 1
-            for (int rp = 0; rp < BH / 4; ++rp) {                  // 4 row pairs per warp
-                const int ly = ry * (BH / 2) + rp * 2, oy0 = ty * BH + ly;
+            for (int rp = 0; rp < kRowsPerWarp / 2; ++rp) {        // row pairs of this warp
+                const int ly = ry * kRowsPerWarp + rp * 2, oy0 = ty * BH + ly;
                 if (oy0 >= p.H) break;
                 const __half2* win = strip + (size_t) ly * IW * 32;           // input row iy of this row pair = win + iy * IW * 32
                 auto load_row = [&](int iy, __half2 (&row)[INX]) {
@@ -187,31 +188,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_dwconv_halo(const __grid_consta
                 __half* yb = p.y + ((img * p.H + oy0) * p.W + ox0) * p.ldy + p.yoff + c0;
                 const bool row1 = oy0 + 1 < p.H;
                 if constexpr (STATS) {
-                    float v[32];                                   // [0,16): per-pixel sum over this lane's 2 channels, [16,32): sum of squares
+                    // per output row: 16 values per lane ([0,8): per-pixel sum over this lane's 2 channels, [8,16): sum of squares of the fp16-rounded
+                    // outputs) -> transposed butterfly: lane l ends with the warp total of value (l & 15) (16 shuffles instead of 80)
+                    const bool full_x = ox0 + TSX <= p.W;              // warp-uniform: interior strips store without per-pixel predicates
+                    auto row_stats = [&](const float2 (&acc)[TSX], int oy, bool store, int writer_half) {
+                        float v[16];
 #pragma unroll
-                    for (int j = 0; j < TSX; ++j) {
-                        const __half2 h0 = __floats2half2_rn(acc0[j].x, acc0[j].y), h1 = __floats2half2_rn(acc1[j].x, acc1[j].y);
-                        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-                        v[j] = f0.x + f0.y; v[16 + j] = fmaf(f0.x, f0.x, f0.y * f0.y);
-                        v[8 + j] = f1.x + f1.y; v[24 + j] = fmaf(f1.x, f1.x, f1.y * f1.y);
-                        if (ox0 + j < p.W) {
-                            *reinterpret_cast<__half2*>(yb + (size_t) j * p.ldy) = h0;
-                            if (row1) *reinterpret_cast<__half2*>(yb + ((size_t) p.W + j) * p.ldy) = h1;
+                        for (int j = 0; j < TSX; ++j) {
+                            const __half2 h = __floats2half2_rn(acc[j].x, acc[j].y);
+                            const float2 f = __half22float2(h);
+                            v[j] = f.x + f.y; v[8 + j] = fmaf(f.x, f.x, f.y * f.y);
+                            if (store && (full_x || ox0 + j < p.W)) *reinterpret_cast<__half2*>(yb + ((size_t) (oy - oy0) * p.W + j) * p.ldy) = h;
                         }
-                    }
-                    // transposed butterfly: 32 values x 32 lanes -> lane l ends with the warp total of value l (31 shuffles instead of 160)
 #pragma unroll
-                    for (int sft = 0; sft < 5; ++sft) {
-                        const int m = 16 >> sft;
-                        const bool up = (lane & m) != 0;
+                        for (int sft = 0; sft < 4; ++sft) {
+                            const int m = 8 >> sft;
+                            const bool up = (lane & m) != 0;
 #pragma unroll
-                        for (int i = 0; i < m; ++i) {
-                            const float send = up ? v[i] : v[i + m], keep = up ? v[i + m] : v[i];
-                            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                            for (int i = 0; i < m; ++i) {
+                                const float send = up ? v[i] : v[i + m], keep = up ? v[i + m] : v[i];
+                                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                            }
                         }
-                    }
-                    const int pl = lane & 15, py = oy0 + (pl >> 3), px = ox0 + (pl & 7);
-                    if (py < p.H && px < p.W) p.stats[(((img * p.H + py) * p.W + px) * (p.C >> 6) + chunk) * 2 + (lane >> 4)] = v[0];
+                        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+                        const int px = ox0 + (lane & 7);
+                        if (store && (lane >> 4) == writer_half && px < p.W)
+                            p.stats[(((img * p.H + oy) * p.W + px) * (p.C >> 6) + chunk) * 2 + ((lane >> 3) & 1)] = v[0];
+                    };
+                    row_stats(acc0, oy0, true, 0);
+                    row_stats(acc1, oy0 + 1, row1, 1);
                 } else {
 #pragma unroll
                     for (int j = 0; j < TSX; ++j) {
@@ -257,8 +262,8 @@ int launch(const CUtensorMap& tm, const DwHaloParams& p, cudaStream_t st) {
 // (nn_elem.cu) takes the register-tiled path.
 int csb_dwconv_halo_try(const void* x, int ldx, int xoff, const float* w, const float* bias, int act, int N, int H, int W, int C, int K, void* y, int ldy, int yoff,
                         float* stats, cudaStream_t st) {
-    static const bool enabled = [] { const char* e = getenv("CSB_DW_HALO"); return !e || atoi(e) != 0; }();
-    if (!enabled || !(K == 5 || K == 7) || C % 64 != 0 || ldx % 8 != 0 || xoff % 8 != 0 || ldy % 2 != 0 || yoff % 2 != 0 || ((uintptr_t) x & 15) != 0) return -1000;
+    const char* env = getenv("CSB_DW_HALO");                         // read per call: tests A/B the two kernels inside one process
+    if ((env && atoi(env) == 0) || !(K == 5 || K == 7) || C % 64 != 0 || ldx % 8 != 0 || xoff % 8 != 0 || ldy % 2 != 0 || yoff % 2 != 0 || ((uintptr_t) x & 15) != 0) return -1000;
     if (stats && K != 7) return -1000;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return -1000;

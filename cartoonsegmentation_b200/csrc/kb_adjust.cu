@@ -514,3 +514,86 @@ extern "C" int csb_depth_adjust_instances(float* disparity, const uint8_t* masks
     }
     return CSB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ median variant (use_medium=True)
+// reference kenburns_effect.py:80: `tenAdjusted[tenPlane > 0] = tenAdjusted[tenPlane > 0].median()` per instance, in order (torch.median = the LOWER
+// median: sorted[(n - 1) / 2]).  Exact selection by a 4-pass byte radix select on the float bit patterns (the selected disparities are > 0, and
+// positive floats order like their bits); per instance 4 x (histogram, pick) + 1 apply launch, no host read.  An instance with no positive masked
+// disparity is skipped (the reference skips when the masked SUM is zero, which for the positive disparities of this path is the same condition).
+namespace {
+struct MedState { uint32_t hist[256]; uint32_t prefix, rank, count, pad; };
+
+__global__ void __launch_bounds__(256) k_med_hist(const float* __restrict__ d, const uint8_t* __restrict__ m, long long P, MedState* st, int shift) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t pre = st->prefix;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long) gridDim.x * blockDim.x) {
+        const float f = d[i];
+        if (!m[i] || !(f > 0.f)) continue;
+        const uint32_t k = __float_as_uint(f);
+        if (shift == 24 || (k >> (shift + 8)) == (pre >> (shift + 8))) atomicAdd(&h[(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void k_med_pick(MedState* st, int shift) {                 // one warp
+    const int lane = threadIdx.x;
+    uint32_t c[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = st->hist[lane * 8 + j]; s += c[j]; }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t rank = st->rank, pre = shift == 24 ? 0u : st->prefix;
+    if (shift == 24) rank = total ? (total - 1) / 2 : 0;
+    __syncwarp();
+    const uint32_t excl = incl - s;
+    if (total && rank >= excl && rank < incl) {
+        uint32_t run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (rank >= run && rank < run + c[j]) { st->prefix = pre | ((uint32_t) (lane * 8 + j) << shift); st->rank = rank - run; }
+            run += c[j];
+        }
+    }
+    if (shift == 24 && lane == 0) st->count = total;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) st->hist[lane * 8 + j] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_med_apply(float* __restrict__ d, const uint8_t* __restrict__ m, long long P, const MedState* __restrict__ st) {
+    if (st->count == 0) return;
+    const float v = __uint_as_float(st->prefix);
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long) gridDim.x * blockDim.x)
+        if (m[i] && d[i] > 0.f) d[i] = v;
+}
+}  // namespace
+
+extern "C" int csb_depth_adjust_median(float* disparity, const uint8_t* masks, int K, int H, int W, void* state, void* stream) {
+    CSB_REQUIRE(disparity && state && (masks || K == 0), "null pointer");
+    CSB_REQUIRE(K >= 0 && H > 0 && W > 0, "bad shape");
+    cudaStream_t st = (cudaStream_t) stream;
+    MedState* s = reinterpret_cast<MedState*>(state);
+    const long long P = (long long) H * W;
+    const int g = csb::wave_grid(P, 256, 4);
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(s, 0, sizeof(MedState), st), "memset"));
+    csb::memset_done(st);
+    for (int k = 0; k < K; ++k) {
+        const uint8_t* m = masks + (long long) k * P;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            k_med_hist<<<g, 256, 0, st>>>(disparity, m, P, s, shift);
+            CSB_TRY(csb::launched("k_med_hist", st));
+            k_med_pick<<<1, 32, 0, st>>>(s, shift);
+            CSB_TRY(csb::launched("k_med_pick", st));
+        }
+        k_med_apply<<<g, 256, 0, st>>>(disparity, m, P, s);
+        CSB_TRY(csb::launched("k_med_apply", st));
+    }
+    return CSB_OK;
+}

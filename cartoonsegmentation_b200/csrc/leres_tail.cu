@@ -96,7 +96,40 @@ __global__ void __launch_bounds__(256) k_lt_tofloat(const uint8_t* __restrict__ 
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) out[i] = (float) q[i];
 }
 
+// depth[depth == 0] = depth[depth > 0].min()  (kenburns_effect.py:577), per image: positive floats order like their bit patterns
+__global__ void __launch_bounds__(256) k_min_positive(const float* __restrict__ x, long long per, unsigned* __restrict__ slot) {
+    const int img = blockIdx.y;
+    const float* X = x + (long long) img * per;
+    unsigned lo = 0x7f800000u;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long) gridDim.x * blockDim.x) {
+        const float v = X[i];
+        if (v > 0.f) lo = min(lo, __float_as_uint(v));
+    }
+    for (int o = 16; o; o >>= 1) lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(slot + img, lo);
+}
+__global__ void __launch_bounds__(256) k_zero_fill(float* __restrict__ x, long long per, const unsigned* __restrict__ slot) {
+    const int img = blockIdx.y;
+    float* X = x + (long long) img * per;
+    const float m = __uint_as_float(slot[img]);
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long) gridDim.x * blockDim.x)
+        if (X[i] == 0.f) X[i] = m;
+}
+
 }  // namespace
+
+extern "C" int csb_zero_to_min_positive(float* x, int N, long long per, unsigned* scratch, void* stream) {
+    CSB_REQUIRE(x && scratch && N > 0 && per > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t) stream;
+    CSB_TRY(csb::cuda_ok(cudaMemsetAsync(scratch, 0x7f, sizeof(unsigned) * N, st), "memset"));      // 0x7f7f7f7f = 3.39e38 (+inf stand-in: no positive pixel)
+    csb::memset_done(st);
+    int gx = (4 * csb::num_sms() + N - 1) / N;
+    gx = gx < 1 ? 1 : gx;
+    k_min_positive<<<dim3(gx, N), 256, 0, st>>>(x, per, scratch);
+    CSB_TRY(csb::launched("k_min_positive", st));
+    k_zero_fill<<<dim3(gx, N), 256, 0, st>>>(x, per, scratch);
+    return csb::launched("k_zero_fill", st);
+}
 
 extern "C" int csb_leres_depth_tail(const float* logits, int N, int h, int w, int H, int W, unsigned* minmax, uint8_t* q8, float* out, void* stream) {
     CSB_REQUIRE(logits && minmax && q8 && out && N > 0 && h > 0 && w > 0, "bad arguments");

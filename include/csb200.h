@@ -90,6 +90,10 @@ CSB_API int csb_disocclusion_fill(const float* input, const float* depth, int B,
  * on the device without host syncs.  disparity [H,W] fp32 in place; masks [K,H,W] uint8 0/1 (torch.bool); state: 16 bytes of device scratch.
  * (The reference's `.sum() == 0` skip and row tests are evaluated as "any plane > 0", identical for non-negative disparities.) */
 CSB_API int csb_depth_adjust_instances(float* disparity, const uint8_t* masks, int K, int H, int W, void* state, void* stream);
+
+/* The `use_medium=True` variant of depth_adjustment_animesseg (kenburns_effect.py:80): per instance, in order, every masked pixel with a positive
+ * disparity is set to the (lower) median of those disparities -- exact, by radix select on the device.  state: 1040 bytes of scratch. */
+CSB_API int csb_depth_adjust_median(float* disparity, const uint8_t* masks, int K, int H, int W, void* state, void* stream);
 /* The same for a batch without host synchronisation: disparity [N,H,W] in place, masks [N,Kmax,H,W], num [N] device int32 (instances per image,
  * e.g. straight from csb_rtmdet_select), state: csb_depth_adjust_state_words(N, Kmax, H, W) int32 of device scratch.  N <= number of SMs.
  * When every disparity under a mask is > 0 (what the depth estimators produce) the recurrence is evaluated order-free in four parallel passes
@@ -138,6 +142,19 @@ CSB_API int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int 
  * bitwise_not) + kenburns_effect.py:572-577 (cv2.resize INTER_AREA back to the frame size, astype(float32)), bit-exact against numpy + OpenCV, for
  * the upscaling / same-size branch.  logits [N,h,w] fp32 -> out [N,H,W] fp32 (8-bit values); minmax: 2*N uint32, q8: N*h*w bytes of scratch. */
 CSB_API int csb_leres_depth_tail(const float* logits, int N, int h, int w, int H, int W, unsigned* minmax, uint8_t* q8, float* out, void* stream);
+
+/* `depth[depth == 0] = depth[depth > 0].min()` (anime_3dkenburns/kenburns_effect.py:577, :815), per image, in place: x [N, per] fp32,
+ * scratch: N uint32.  Two launches, no host read. */
+CSB_API int csb_zero_to_min_positive(float* x, int N, long long per, unsigned* scratch, void* stream);
+
+/* AnimeInstances.resize (animeinsseg/anime_instances.py:268-280): masks [K,H0,W0] bool bytes -> F.interpolate(mode='area') > thr (0.3) ->
+ * out [K,H,W] bool bytes, bit-identical to the torch ops; boxes_in/boxes_out (optional, [K,4] int32 xywh): the reference's scaling
+ * (columns 0,2 by H/H0, columns 1,3 by W/W0 -- its x/y swap kept) and torch.round. */
+CSB_API int csb_masks_area_resize(const uint8_t* masks, int K, int H0, int W0, uint8_t* out, int H, int W, float thr, const int* boxes_in, int* boxes_out,
+                                  void* stream);
+
+/* AnimeInstances.compose_masks (anime_instances.py:282-298): logical OR of K masks of P = H*W bool bytes -> out [P]. */
+CSB_API int csb_masks_compose(const uint8_t* masks, int K, long long P, uint8_t* out, void* stream);
 
 /* ZoeDepth / MiDaS DPT-BEiT-L encoder pieces (the encoder is torch.hub `intel-isl/MiDaS` `DPT_BEiT_L_384`, loaded at
  * depth_modules/zoedepth/models/base_models/midas.py:341 and NOT vendored in the reference: restated from timm's BEiT + MiDaS v3.1's DPT).

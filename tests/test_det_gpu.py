@@ -184,6 +184,6 @@ def test_cspnext_l_forward_vs_oracle(built_lib, size):
 def test_cspnext_l_infer_surface(built_lib):
     """AnimeInsSeg built from a CSPNeXt-L state_dict (what loading rtmdetl_e60.ckpt produces) runs `infer` end to end."""
     from cartoonsegmentation_b200.animeinsseg import AnimeInsSeg, rtmdet as R
-    seg = AnimeInsSeg(R.synthetic_state_dict(0, backbone='cspnext_l'), default_det_size=320)
+    seg = AnimeInsSeg(R.synthetic_state_dict(0, backbone='cspnext_l'), default_det_size=320, refine_kwargs={'refine_method': 'none'})
     inst = seg.infer(smooth_image(300, 280, seed=2), output_type='tensor', pred_score_thr=0.0)
     assert inst.masks is None or inst.masks.shape[1:] == (300, 280)

@@ -85,7 +85,8 @@ def test_depth_adjustment_kernel_matches_reference_formulation(built_lib):
     inst = AnimeInstances(masks, torch.zeros(9, 4, dtype=torch.int32, device='cuda'), torch.ones(9, device='cuda'))
     img = torch.zeros(1, 3, H, W, device='cuda')
     a = kb.depth_adjustment_animesseg(inst, disp, img)                       # csb_depth_adjust_batch (one cooperative launch)
-    b = kb.depth_adjustment_animesseg_torch(inst, disp.clone(), img)
+    from oracle import kb_adjust_oracle as AO                                # the reference's torch formulation, run on the GPU tensors
+    b = AO.depth_adjustment_animesseg(inst.masks, disp.clone(), img)
     assert torch.equal(a, b)
     from cartoonsegmentation_b200._lib import check, lib, ptr, stream
     c = disp.clone().contiguous()
@@ -97,7 +98,7 @@ def test_depth_adjustment_kernel_matches_reference_formulation(built_lib):
     m3 = masks[None].repeat(3, 1, 1, 1).contiguous()
     kb.depth_adjust_batch(d3, m3, torch.tensor([0, 9, 4], device='cuda', dtype=torch.int32))
     assert torch.equal(d3[0], disp[0, 0]) and torch.equal(d3[1], b[0, 0])
-    b4 = kb.depth_adjustment_animesseg_torch(AnimeInstances(masks[:4], torch.zeros(4, 4, dtype=torch.int32, device='cuda'), torch.ones(4, device='cuda')), disp.clone(), img)
+    b4 = AO.depth_adjustment_animesseg(masks[:4], disp.clone(), img)
     assert torch.equal(d3[2], b4[0, 0])
     assert torch.equal(kb.depth_adjustment_animesseg(AnimeInstances(), disp, img), disp)
 
@@ -148,5 +149,31 @@ def test_depth_adjust_batch_paths_match_reference_formulation(built_lib, H, W, K
     kb.depth_adjust_batch(d3, m[None].repeat(3, 1, 1, 1).contiguous(), torch.tensor(counts, device='cuda', dtype=torch.int32))
     for i, c in enumerate(counts):
         inst = AnimeInstances(m[:c], torch.zeros(c, 4, dtype=torch.int32, device='cuda'), torch.ones(c, device='cuda')) if c else AnimeInstances()
-        ref = kb.depth_adjustment_animesseg_torch(inst, disp.clone(), img)
+        from oracle import kb_adjust_oracle as AO
+        ref = AO.depth_adjustment_animesseg(None if inst.is_empty else inst.masks, disp.clone(), img)
         assert torch.equal(d3[i], ref[0, 0]), (mode, i, float((d3[i] - ref[0, 0]).abs().max()))
+
+
+def test_depth_adjustment_median_and_resized_variants(built_lib):
+    """use_medium=True (kenburns_effect.py:80, exact lower median by radix select) and the resized form (:50-56, :86-90) against the reference's
+    torch formulation (oracle/kb_adjust_oracle.py) on the same tensors."""
+    from cartoonsegmentation_b200.animeinsseg import AnimeInstances
+    from cartoonsegmentation_b200.anime_3dkenburns import kenburns_effect as kb
+    from cartoonsegmentation_b200.utils.synthetic import ellipse_masks
+    from oracle import kb_adjust_oracle as AO
+    H, W = 200, 260
+    disp = torch.from_numpy(smooth_disparity(H, W, seed=5)).cuda()
+    masks = torch.from_numpy(ellipse_masks(H, W, k=9, seed=6)).cuda()
+    masks[3] = False
+    masks[5] = True
+    inst = AnimeInstances(masks, torch.zeros(9, 4, dtype=torch.int32, device='cuda'), torch.ones(9, device='cuda'))
+    img = torch.zeros(1, 3, H, W, device='cuda')
+    a = kb.depth_adjustment_animesseg(inst, disp, img, use_medium=True)
+    b = AO.depth_adjustment_animesseg(masks, disp.clone(), img, use_medium=True)
+    assert torch.equal(a, b)                                                  # selection, not arithmetic: exact
+    small = torch.nn.functional.interpolate(disp, size=(H // 2, W // 2 + 3), mode='bilinear', align_corners=False).contiguous()
+    for um in (False, True):
+        a = kb.depth_adjustment_animesseg(inst, small, img, use_medium=um)
+        b = AO.depth_adjustment_animesseg(masks, small.clone(), img, use_medium=um)
+        assert a.shape == b.shape == small.shape
+        assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item()      # two bilinear resamplings: fp32 rounding order only

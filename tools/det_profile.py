@@ -17,7 +17,7 @@ from cartoonsegmentation_b200.utils.synthetic import smooth_image          # noq
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/det_profile.json"
-    seg = AnimeInsSeg(None, default_det_size=1024)
+    seg = AnimeInsSeg(None, default_det_size=1024, refine_kwargs={'refine_method': 'none'})
     imgs = torch.from_numpy(np.stack([smooth_image(1024, 1024, seed=100 + i) for i in range(min(B, 8))])).cuda()
     imgs = imgs.repeat((B + imgs.shape[0] - 1) // imgs.shape[0], 1, 1, 1)[:B].contiguous()
     cfg = seg.model.bbox_head.test_cfg

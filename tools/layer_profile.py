@@ -53,7 +53,7 @@ def table(name, prof):
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/layer_profile.json"
-    seg = AnimeInsSeg(None, default_det_size=1024)
+    seg = AnimeInsSeg(None, default_det_size=1024, refine_kwargs={'refine_method': 'none'})
     imgs = torch.from_numpy(np.stack([smooth_image(1024, 1024, seed=100 + i) for i in range(8)])).cuda().repeat(B // 8, 1, 1, 1).contiguous()
     det = table("detector", profile(lambda: seg.model.net.forward(imgs)))
     del seg

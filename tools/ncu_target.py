@@ -14,7 +14,7 @@ from cartoonsegmentation_b200.utils.synthetic import smooth_disparity, smooth_im
 what = sys.argv[1] if len(sys.argv) > 1 else "det"
 if what == "det":
     from cartoonsegmentation_b200.animeinsseg import AnimeInsSeg, rtmdet_postprocess
-    seg = AnimeInsSeg(None, default_det_size=1024)
+    seg = AnimeInsSeg(None, default_det_size=1024, refine_kwargs={'refine_method': 'none'})
     imgs = torch.from_numpy(np.stack([smooth_image(1024, 1024, seed=i) for i in range(2)])).cuda()
     for _ in range(2):
         cls, reg, ker, mf = seg.model.net.forward(imgs)
