@@ -107,7 +107,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_frame(orc, img, raw):
-    """One input frame through the oracle port of the same path -> uint8 frame."""
+    """One input frame through the oracle port of the warp stage -> uint8 frame."""
     cloud = orc.disparity_to_cloud(raw[None, None], FOCAL, BASELINE)
     common = {'objDepthrange': cloud['depthrange'], 'intWidth': W, 'intHeight': H, 'fltFocal': FOCAL, 'fltBaseline': BASELINE}
     dmin = cloud['depthrange'][0]
@@ -122,7 +122,7 @@ def cpu_frame(orc, img, raw):
 
 
 def cpu_arm(imgs, disp, n_frames, threads):
-    """Oracle port on `threads` host threads (ctypes releases the GIL); returns frames/s."""
+    """Warp stage only, `threads` frames in flight (ctypes releases the GIL); returns frames/s."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import kb_oracle as orc
     orc.lib()
@@ -135,16 +135,16 @@ def cpu_arm(imgs, disp, n_frames, threads):
 
 class CpuPath:
     """The CPU arm: the oracle port of every stage of the workload for ONE input frame (PyTorch fp32 on all host threads for the networks,
-    oracle/kb_oracle.c for the Ken-Burns kernels).  The real reference package cannot run on a CPU at all (mmdet / mmcv / cupy absent in the
-    image; its Ken-Burns kernels are GPU-only cupy strings and anime_3dkenburns/common.py:74 hard-codes .cuda()), so its CPU implementation of
-    this path *is* the port."""
+    oracle/kb_oracle.c -- scalar C, ONE thread -- for the Ken-Burns kernels).  The real reference package cannot run on a CPU at all (mmdet / mmcv /
+    cupy absent in the image; its Ken-Burns kernels are GPU-only cupy strings and anime_3dkenburns/common.py:74 hard-codes .cuda()), so its CPU
+    implementation of this path *is* the port."""
 
     def __init__(self, stages, depth='leres'):
         import torch
         from cartoonsegmentation_b200.animeinsseg import rtmdet
         from cartoonsegmentation_b200.depth_modules import leres as L
-        from oracle import det_oracle as D, kb_oracle as orc, leres_oracle as LO
-        self.torch, self.D, self.orc, self.LO = torch, D, orc, LO
+        from oracle import det_oracle as D, kb_adjust_oracle as AO, kb_oracle as orc, leres_oracle as LO
+        self.torch, self.D, self.orc, self.LO, self.AO = torch, D, orc, LO, AO
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
         self.stages = stages
@@ -157,35 +157,43 @@ class CpuPath:
         elif self.depth == 'zoe':
             raise SystemExit("--impl reference --depth zoe: the CPU oracle of DPT-BEiT-L @672^2 x 2 flips needs minutes per frame; time the LeReS workload")
         orc.lib()
+        self.stage_s = {"seg": 0.0, "depth": 0.0, "adjust": 0.0, "warp_single_thread_c": 0.0}
 
-    def frame(self, img, raw_synth):
+    def frame(self, img, raw_synth, keep=False):
         torch = self.torch
         masks = None
+        t = time.perf_counter()
         with torch.no_grad():
             if self.det is not None:
                 masks = self.D.infer(self.det, img)['masks']
+            t1 = time.perf_counter(); self.stage_s["seg"] += t1 - t
             raw = self.LO.depth_est_leres(self.ler, img) if self.ler is not None else raw_synth
+            t2 = time.perf_counter(); self.stage_s["depth"] += t2 - t1
             if masks is not None and len(masks):                       # depth_adjustment_animesseg (kenburns_effect.py:39-91)
-                d = torch.from_numpy(raw)[None, None].clone()
-                for m in masks.float():
-                    plane = d * m
-                    if plane.sum().item() == 0:
-                        continue
-                    rows = (plane.sum([3], True) > 0.0).flatten().nonzero()
-                    top, bottom = rows[0].item(), rows[-1].item()
-                    d = ((1.0 - m) * d) + (m * plane[:, :, int(round(top + (0.97 * (bottom - top)))):, :].max())
-                raw = d[0, 0].numpy()
-        if 'warp' in self.stages:
-            return cpu_frame(self.orc, img, np.ascontiguousarray(raw))
-        return None
+                raw = self.AO.depth_adjustment_animesseg(masks, torch.from_numpy(np.ascontiguousarray(raw))[None, None], torch.zeros(1, 3, H, W))[0, 0].numpy()
+            t3 = time.perf_counter(); self.stage_s["adjust"] += t3 - t2
+        out = cpu_frame(self.orc, img, np.ascontiguousarray(raw)) if 'warp' in self.stages else None
+        self.stage_s["warp_single_thread_c"] += time.perf_counter() - t3
+        return (out, raw, 0 if masks is None else len(masks)) if keep else out
 
-    def time(self, imgs, disp, steps, warm):
+    def time(self, imgs, disp, steps, warm, keep=False):
         for i in range(warm):
             self.frame(imgs[i % len(imgs)], disp[i % len(disp)])
+        self.stage_s = {k: 0.0 for k in self.stage_s}
+        kept = []
         t0 = time.perf_counter()
         for i in range(steps):
-            self.frame(imgs[i % len(imgs)], disp[i % len(disp)])
-        return (time.perf_counter() - t0) / steps
+            r = self.frame(imgs[i % len(imgs)], disp[i % len(disp)], keep)
+            if keep:
+                kept.append(r)
+        sec = (time.perf_counter() - t0) / steps
+        self.kept = kept
+        return sec
+
+    def sample_text(self, steps):
+        st = {k: round(v / max(1, steps), 3) for k, v in self.stage_s.items()}
+        return (f"{steps} frame(s) of 1024x1024 (after 1 warm-up) through the oracle port of every stage of the workload: oracle/det_oracle.py + oracle/leres_oracle.py + "
+                f"oracle/kb_adjust_oracle.py (PyTorch fp32, {self.cores} threads) + oracle/kb_oracle.c (scalar C on ONE thread); seconds per frame by stage: {st}")
 
 
 def run_reference(args):
@@ -203,8 +211,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1000.0 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(1, 2, stages, args.depth),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
-                         "sample": f"{steps} step(s) x 1 frame of 1024x1024 through the oracle port of every stage (PyTorch fp32 on {cpu.cores} threads + C)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.cores, "kind": "port", "sample": cpu.sample_text(steps)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
 
@@ -219,48 +226,97 @@ def workload_config(batch, scenes, stages=("seg", "depth", "warp"), depth="leres
     missing = [v for k, v in {"seg": "seg", "depth": "depth (raw disparity is then a synthetic input)", "warp": "warp"}.items() if k not in stages]
     missing += ["ISNet mask refine (A10) and Inpaint net + autozoom (C4-C6) are per-image, not per-frame: measured in other_workloads"]
     return {"workload": "per input frame @1024x1024: " + " -> ".join(names[s_] for s_ in ("seg", "depth", "warp") if s_ in stages),
+            "api": "KenBurnsPipeline.render_frame_batch(frames uint8 [B,1024,1024,3]) -> one warped uint8 frame per input frame",
             "stages": list(stages), "depth": depth if "depth" in stages else None, "stages_missing": missing, "frame": [H, W], "batch_frames_per_step": batch, "focal": FOCAL, "baseline": BASELINE,
-            "l2_policy": f"inputs cycle over {scenes} distinct scenes; every frame streams > 126 MB of intermediates, so no input survives in L2 between uses"}
+            "partitioning": "one frame stream, frame i -> rank i mod G (utils/dist.py:shard_indices); scene of frame i = i mod scenes",
+            "l2_policy": f"inputs cycle over {scenes} distinct scenes in two alternating batch buffers; every frame streams > 126 MB of intermediates, so no input survives in L2 between uses"}
 
 
-# ------------------------------------------------------------------------------------------------ API-level workloads (BASELINE configs[1], [3])
-def run_other(pipe, imgs_np, args):
+def timed_call(fn):
+    import torch
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), r
+
+
+def profile_call(lib, fn):
+    """per-kernel device time of fn(): a CUDA event after every library launch (csb_profile_begin/end)"""
+    import torch
+    torch.cuda.synchronize()
+    lib.csb_profile_begin(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    fn()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.csb_profile_end(buf, len(buf))
+    return json.loads(buf.value.decode())
+
+
+# ------------------------------------------------------------------------------------------------ API-level workloads (BASELINE configs[0..3])
+def run_other(pipe, imgs_np, args, lib):
     """Workloads measured through the reference-facing Python API, host numpy in / host numpy (or AnimeInstances) out, CUDA events around the
     calls (the host gaps between launches are inside the timed region)."""
     import torch
+    from cartoonsegmentation_b200.anime_3dkenburns import kenburns_effect as kb
     seg = pipe.animeinsseg
     S = len(imgs_np)
-
-    def timed(fn):
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1), r
-
     res = {}
+    off, on = {'refine_method': 'none'}, {'refine_method': 'refinenet_isnet'}
+    # ---- BASELINE configs[0]: AnimeInsSeg.infer on ONE 512 x 512 example image (examples/1562990.jpg, fixture made by tests/golden/make_example_fixture.py)
+    ex = os.path.join(ROOT, "tests", "golden", "example_1562990_512.jpg")
+    if os.path.exists(ex):
+        import cv2
+        img512 = cv2.imread(ex)
+        for kw, name in ((off, "refine_off"), (on, "refine_isnet")):
+            for _ in range(2):
+                seg.infer(img512, 0.3, kw, 'tensor', det_size=512)
+            ms, inst = timed_call(lambda: [seg.infer(img512, 0.3, kw, 'tensor', det_size=512) for _ in range(5)])
+            res.setdefault("infer_512_example", {"api": "AnimeInsSeg.infer(ndarray 512x512x3 = examples/1562990.jpg resized + centre-cropped, pred_score_thr=0.3, det_size=512), "
+                                                       "one image per call (BASELINE configs[0]; the CPU arm of the same call is cpu_baseline_512)"})[name] = \
+                {"ms_per_image": ms / 5, "images_per_s": 5e3 / ms, "instances": len(inst[-1])}
+        seg.set_refine_method('none')
     # ---- BASELINE configs[1]: AnimeInsSeg.infer on a batch (python list) of 32 images of 1024x1024, det_size 1024
     lst = [imgs_np[i % S] for i in range(32)]
-    off = {'refine_method': 'none'}
     seg.infer(lst[:8], 0.3, off, 'tensor', det_size=H)
-    ms, inst = timed(lambda: seg.infer(lst, 0.3, off, 'tensor', det_size=H))
+    ms, inst = timed_call(lambda: seg.infer(lst, 0.3, off, 'tensor', det_size=H))
     K = float(np.mean([len(i) for i in inst]))
     res["infer_batch32"] = {"api": "AnimeInsSeg.infer(list of 32 ndarray 1024x1024x3, pred_score_thr=0.3, refine off, output_type='tensor', det_size=1024)",
                             "frames_per_s": 32 / (ms * 1e-3), "ms": ms, "instances_per_image": K, "h2d_bytes": 32 * H * W * 3}
     del inst
     # ---- the same with the reference's default-on ISNet refinement (A10): 159.5 GFLOP per instance at 720^2
     n_ref = 4
-    on = {'refine_method': 'refinenet_isnet'}
     seg.infer(lst[:1], 0.3, on, 'tensor', det_size=H)
-    ms, inst = timed(lambda: seg.infer(lst[:n_ref], 0.3, on, 'tensor', det_size=H))
+    ms, inst = timed_call(lambda: seg.infer(lst[:n_ref], 0.3, on, 'tensor', det_size=H))
     K = float(np.mean([len(i) for i in inst]))
+    tf = 159.5e-3 * K * n_ref / (ms * 1e-3)
     res["infer_refine_isnet"] = {"api": f"AnimeInsSeg.infer(list of {n_ref} ndarray 1024x1024x3, refine_method='refinenet_isnet' (reference default), det_size=1024)",
-                                 "frames_per_s": n_ref / (ms * 1e-3), "ms": ms, "instances_per_image": K,
-                                 "isnet_tflops": 159.5e-3 * K * n_ref / (ms * 1e-3)}
+                                 "frames_per_s": n_ref / (ms * 1e-3), "ms": ms, "instances_per_image": K, "isnet_tflops": tf,
+                                 "roofline": {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "note": "159.5 GFLOP per instance x K x images over the whole call (detector included in the time)"}}
     del inst
     seg.set_refine_method('none')
+    # ---- BASELINE configs[2]: seg + ZoeDepth forward over 32 frames (DPT-BEiT-L @672^2, 2 net inputs per frame), no warp
+    if not args.no_zoe:
+        zcfg = kb.KenBurnsConfig(det_size=H, max_size=H, depth_est='zoe', pred_score_thr=0.3, refine_crf=False)
+        zp = kb.KenBurnsPipeline.__new__(kb.KenBurnsPipeline)
+        zp.__dict__.update(pipe.__dict__)                      # shares the detector; adds the ZoeDepth estimator
+        zp.cfg, zp.depth_zoe = zcfg, None
+        zp.set_depth_estimation('zoe')
+        zb = torch.from_numpy(np.stack(lst)).to(pipe.device)
+        zp.render_frame_batch(zb, warp=False)
+        ms, _ = timed_call(lambda: zp.render_frame_batch(zb, warp=False))
+        prof = profile_call(lib, lambda: zp.render_frame_batch(zb, warp=False))
+        zoe_lin = 2 * (24 * 1765 * 12 * 1024 * 1024 * 2 / 1e9 + 291.0) * 32 + 1011.9 * 32          # GFLOP on k_conv_tc: BEiT linears + DPT convs (2 net inputs) + detector
+        att = 2 * 24 * 16 * 4 * 1765 * 1765 * 64 / 1e9 * 32                                          # GFLOP on k_attention_tc
+        res["seg_zoedepth_batch32"] = {"api": "KenBurnsPipeline(depth_est='zoe').render_frame_batch(32 frames 1024x1024x3 resident in HBM, warp=False): detector + "
+                                              "ZoeDepth.infer(pad_input, with_flip_aug) + depth->disparity + instance flattening (BASELINE configs[2])",
+                                       "frames_per_s": 32e3 / ms, "ms": ms,
+                                       "k_conv_tc_tflops": zoe_lin / prof["k_conv_tc"]["ms"] if "k_conv_tc" in prof else None,
+                                       "k_attention_tc_tflops": att / prof["k_attention_tc"]["ms"] if "k_attention_tc" in prof else None,
+                                       "per_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:10]}}
+        del zp, zb
+        torch.cuda.empty_cache()
     # ---- BASELINE configs[3]: full 3D Ken Burns per input image: seg + depth + adjust + cloud + autozoom (256 candidate renders) + 2 inpaint passes
     #      + num_frame (75) output frames, uint8 frames returned on the host (run_kenburns.py:19-33)
     n_img = max(1, args.other_images)
@@ -269,17 +325,22 @@ def run_other(pipe, imgs_np, args):
         kcfg = pipe.generate_kenburns_config(imgs_np[i % S])
         return pipe.autozoom(kcfg)
     kb_image(0)
-    ms, frames = timed(lambda: [len(kb_image(1 + i)) for i in range(n_img)])
+    ms, frames = timed_call(lambda: [len(kb_image(1 + i)) for i in range(n_img)])
+    l0 = lib.csb_launch_count()
+    prof = profile_call(lib, lambda: kb_image(0))
+    n_launch = lib.csb_launch_count() - l0
     res["kenburns_full"] = {"api": "KenBurnsPipeline.generate_kenburns_config(img) + .autozoom(cfg): seg + depth(%s) + autozoom + 2 x inpaint + %d frames, "
                                    "host ndarray in, list of host uint8 frames out" % (pipe.cfg.depth_est, pipe.cfg.num_frame),
                             "input_images_per_s": n_img / (ms * 1e-3), "output_frames_per_s": sum(frames) / (ms * 1e-3), "ms_per_image": ms / n_img,
-                            "images": n_img, "h2d_bytes_per_image": H * W * 3, "d2h_bytes_per_image": pipe.cfg.num_frame * H * W * 3}
+                            "images": n_img, "h2d_bytes_per_image": H * W * 3, "d2h_bytes_per_image": pipe.cfg.num_frame * H * W * 3, "launches_per_image": int(n_launch),
+                            "per_kernel_ms_profiled": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]) if k != "memset"},
+                            "profile_note": "a CUDA event after every library launch; 'memset' (dropped) also absorbs non-library work between launches (copies, host gaps)"}
     # ---- the same with the options the reference ships in configs/3dkenburns.yaml: ISNet mask refinement (refine_size 720) + depth_field (bokeh)
     pipe.cfg.mask_refine_kwargs = {'refine_method': 'refinenet_isnet', 'refine_size': 720}
     pipe.cfg.depth_field = True
     kb_image(0)
     n_y = min(2, n_img)
-    ms, frames = timed(lambda: [len(kb_image(1 + i)) for i in range(n_y)])
+    ms, frames = timed_call(lambda: [len(kb_image(1 + i)) for i in range(n_y)])
     res["kenburns_full_shipped_yaml"] = {"api": "as kenburns_full with mask_refine_kwargs={refinenet_isnet, 720} and depth_field=True (configs/3dkenburns.yaml:16,36-38)",
                                          "input_images_per_s": n_y / (ms * 1e-3), "output_frames_per_s": sum(frames) / (ms * 1e-3), "ms_per_image": ms / n_y,
                                          "images": n_y}
@@ -287,6 +348,33 @@ def run_other(pipe, imgs_np, args):
     pipe.cfg.depth_field = False
     seg.set_refine_method('none')
     return res
+
+
+def parity_block(pipe, cpu, imgs_np, disp_np, stages):
+    """The oracle frames of the cpu_baseline leg double as the checker: the same frames through the CUDA path (same API call as the timed one),
+    compared stage by stage.  Detailed full-size numbers: profiles/r2_parity_full.json (tests/parity_full.py), asserted in tests/test_parity_full_gpu.py."""
+    import torch
+    n = len(cpu.kept)
+    batch = torch.from_numpy(imgs_np[:n]).to(pipe.device)
+    raw = None if 'depth' in stages else torch.from_numpy(disp_np[:n]).to(pipe.device)
+    r = pipe.render_frame_batch(batch, SHIFT_U, SHIFT_V, DEPTH_RATIO, raw_disparity=raw, segment='seg' in stages, warp='warp' in stages)
+    out = {"frames_compared": n, "oracle": "oracle/det_oracle.py + leres_oracle.py + kb_adjust_oracle.py + kb_oracle.c (fp32 CPU) on the same seeded frames",
+           "parity_pinning": "K1-K4/C8 pinned to the unmodified reference kernels, A10/B4/B6/C5 to reference-module goldens; A1-A6 (mmdet) and B3 (MiDaS) are "
+                             "restatements of un-vendored third-party code: parity UNPINNED for those rows",
+           "full_size_measurements": "profiles/r2_parity_full.json"}
+    disp = r['disparity'].cpu().numpy()
+    dd, fd, inst = [], [], []
+    for i, (frame_o, raw_o, k_o) in enumerate(cpu.kept):
+        d = np.abs(disp[i] - raw_o)
+        dd.append({"max_abs_levels": float(d.max()), "frac_pixels_differ": float((d > 0).mean()), "frac_gt_1_level": float((d > 1.0).mean())})
+        if r['frames'] is not None and frame_o is not None:
+            f = np.abs(r['frames'][i].cpu().numpy().astype(int) - frame_o.astype(int))
+            fd.append({"max_abs_lsb": int(f.max()), "frac_bytes_differ": float((f > 0).mean()), "frac_gt_2_lsb": float((f > 2).mean())})
+        inst.append({"ours": None if r['num_instances'] is None else r['num_instances'][i], "oracle": k_o})
+    out["adjusted_disparity_8bit_levels"] = dd
+    out["warped_frame_u8"] = fd
+    out["instances"] = inst
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -301,7 +389,8 @@ def main():
     ap.add_argument("--stages", default="seg,depth,warp", help="comma list out of seg,depth,warp (default: the full metric)")
     ap.add_argument("--depth", default="leres", choices=["leres", "zoe"], help="depth estimator of the depth stage (reference: KenBurnsConfig.depth_est)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other", action="store_true", help="skip other_workloads (infer_batch32, kenburns_full)")
+    ap.add_argument("--no-other", action="store_true", help="skip other_workloads (infer_512_example, infer_batch32, seg_zoedepth_batch32, kenburns_full)")
+    ap.add_argument("--no-zoe", action="store_true", help="skip the seg + ZoeDepth workload (BASELINE configs[2]) inside other_workloads")
     ap.add_argument("--other-images", type=int, default=3, help="input images of the kenburns_full workload")
     args = ap.parse_args()
     capture_stdout()
@@ -314,8 +403,7 @@ def main():
     import torch.distributed as dist
     from cartoonsegmentation_b200 import _lib
     from cartoonsegmentation_b200.anime_3dkenburns import kenburns_effect as kb
-    from cartoonsegmentation_b200.animeinsseg import AnimeInstances, rtmdet_postprocess
-    from cartoonsegmentation_b200.utils.dist import gather_counters, max_over_ranks
+    from cartoonsegmentation_b200.utils.dist import gather_counters, max_over_ranks, shard_indices
 
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -326,85 +414,29 @@ def main():
     B, S = args.batch, args.scenes
 
     # ---- the reference call surface: one pipeline object per rank, weights replicated from the same seed
-    cfg = kb.KenBurnsConfig(det_size=H, max_size=H, depth_est=args.depth if 'depth' in stages else 'external', depth_est_size=640, pred_score_thr=0.3)
+    cfg = kb.KenBurnsConfig(det_size=H, max_size=H, depth_est=args.depth if 'depth' in stages else 'external', depth_est_size=640, pred_score_thr=0.3,
+                            refine_crf=False)
     pipe = kb.KenBurnsPipeline(cfg, device=dev)
-    seg = pipe.animeinsseg
-    seg.set_detect_size(H)
-    test_cfg = seg.model.bbox_head.test_cfg
+    pipe.animeinsseg.set_detect_size(H)
 
-    # ---- inputs: each rank owns `scenes` distinct scenes (weak scaling: per-GPU work fixed)
+    # ---- inputs: ONE frame stream, frame i -> rank i mod G (shard_indices); frame i shows scene i mod S.  Two alternating batch buffers per rank.
     imgs_np, disp_np = make_inputs(S)
-    imgs_np = np.roll(imgs_np, rank, axis=0)
-    imgs_pin = torch.from_numpy(imgs_np).pin_memory(); disp_pin = torch.from_numpy(disp_np).pin_memory()
-    imgs_dev = imgs_pin.to(dev); disp_dev = disp_pin.to(dev)
-    scratch = kb.FrameScratch(H, W, dev)
-    clouds = [{k: torch.empty((1, c, H, W), device=dev) for k, c in (('disparity', 1), ('depth', 1), ('valid', 1), ('points', 3), ('unaltered', 3))} for _ in range(2)]
-    data = [torch.empty((1, 4, H * W), device=dev) for _ in range(2)]
-    scalars = torch.empty(8, device=dev); d2c_scratch = torch.empty(64, device=dev, dtype=torch.int64); shift_dev = torch.empty(3, device=dev)
-    adj_state = torch.empty(4, device=dev, dtype=torch.int32)
-    outs = torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8)
+    NB = 2
+    mine = shard_indices(world * B * NB, rank, world)                  # this rank's frames of the first NB steps (the pattern repeats)
+    scene = [[mine[k * B + b] % S for b in range(B)] for k in range(NB)]
+    batch_pin = [torch.from_numpy(np.stack([imgs_np[i] for i in scene[k]])).pin_memory() for k in range(NB)]
+    batch_dev = [t.to(dev) for t in batch_pin]
+    disp_dev = [torch.from_numpy(np.stack([disp_np[i] for i in scene[k]])).to(dev) for k in range(NB)] if 'depth' not in stages else None
     outs_pin = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
-    stage_img = torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8)
-    cd = ctypes.c_double
-    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    seg_sub = int(os.environ.get("CSB_SEG_SUB", "32"))              # detector sub-batch (activations of 32 x 1024^2 ~ 12 GB of the 180 GB)
-    zoe_sub = int(os.environ.get("CSB_ZOE_SUB", "16"))              # ZoeDepth sub-batch (2 net inputs of 672^2 per frame)
-    stats = {"instances": 0}
-
-    def warp(img_u8, raw, out, slot):
-        """disparity -> cloud -> camera shift -> render -> fill -> pack -> crop/resize, no host sync"""
-        c = clouds[slot]
-        _lib.check(lib.csb_disparity_to_cloud(_lib.ptr(raw), H, W, cd(FOCAL), cd(BASELINE), _lib.ptr(c['disparity']), _lib.ptr(c['depth']), _lib.ptr(c['valid']),
-                                              _lib.ptr(c['points']), _lib.ptr(c['unaltered']), _lib.ptr(scalars), _lib.ptr(d2c_scratch), _lib.ptr(img_u8),
-                                              _lib.ptr(data[slot]), st()))
-        _lib.check(lib.csb_shift_from_scalars(_lib.ptr(scalars), W, H, cd(FOCAL), cd(SHIFT_U), cd(SHIFT_V), cd(DEPTH_RATIO), _lib.ptr(shift_dev), st()))
-        _lib.check(lib.csb_kenburns_frame(_lib.ptr(c['points']), _lib.ptr(data[slot]), H * W, H, W, cd(FOCAL), cd(BASELINE), None, _lib.ptr(shift_dev), CROP, CROP,
-                                          cd(W / 2.0), cd(H / 2.0), _lib.ptr(scratch.zkey), _lib.ptr(scratch.zee), _lib.ptr(scratch.acc), _lib.ptr(scratch.packed),
-                                          _lib.ptr(out), None, st()))
+    stats = {"instances": 0, "calls": 0}
 
     def step(k, e2e):
-        idx = [(k * B + b) % S for b in range(B)]
-        if e2e:                                                      # H2D of this step's inputs from pinned host memory
-            for b, i in enumerate(idx):
-                stage_img[b].copy_(imgs_pin[i], non_blocking=True)
-            batch = stage_img
-        else:
-            batch = imgs_dev[idx] if 'seg' in stages or 'depth' in stages else None
-        masks = nums = nums_dev = None
-        depth_handle = None
-        disp = None
-        if 'depth' in stages and args.depth == 'leres':              # LeReS forward + the reference's quantisation tail, all on the device
-            depth_handle = pipe.leres_enqueue(None, imgs_dev=batch)
-        elif 'depth' in stages:                                      # ZoeDepth.infer(pad_input, with_flip_aug) + _depth_est_zoe's depth -> disparity
-            disp = []
-            for s0 in range(0, B, zoe_sub):
-                d = pipe.depth_zoe.infer_batch(batch[s0:s0 + zoe_sub])
-                disp += [pipe.depth_zoe.disparity(d[i], FOCAL, BASELINE) for i in range(d.shape[0])]
-        if 'seg' in stages:                                          # AnimeInsSeg.infer body: detector forward + post-process (A1-A9)
-            masks, nums_dev = [], []
-            for s0 in range(0, B, seg_sub):
-                sub = batch[s0:s0 + seg_sub]
-                cls, reg, ker, mf = seg.model.net.forward(sub)
-                o = rtmdet_postprocess(cls, reg, ker, mf, (H, W), test_cfg)
-                masks.append(o['masks']); nums_dev.append(o['num'])
-        if depth_handle is not None:
-            disp = pipe.leres_finish(depth_handle)
-        if 'seg' in stages:
-            nums = torch.cat(nums_dev).cpu().tolist()                # the one host read of the seg stage (instance counts for the caller)
-            stats["instances"] += sum(nums)
-        raws = torch.stack([(disp[b] if disp is not None else disp_dev[i]).reshape(H, W) for b, i in enumerate(idx)])       # [B,H,W] (a copy)
-        if masks is not None:                                        # instance-guided depth flattening (C2): one cooperative launch per sub-batch
-            for j, s0 in enumerate(range(0, B, seg_sub)):
-                kb.depth_adjust_batch(raws[s0:s0 + seg_sub], masks[j], nums_dev[j])
-        for b, i in enumerate(idx):
-            raw = raws[b]
-            if 'warp' in stages:
-                img_b = batch[b] if batch is not None else imgs_dev[i]
-                warp(img_b, raw, outs[b], b & 1)
-                if e2e:
-                    outs_pin[b].copy_(outs[b], non_blocking=True)
-        if e2e:
-            torch.cuda.current_stream().synchronize()               # the caller receives this step's frames
+        j = k % NB
+        r = pipe.render_frame_batch(batch_pin[j] if e2e else batch_dev[j], SHIFT_U, SHIFT_V, DEPTH_RATIO,
+                                    raw_disparity=None if disp_dev is None else disp_dev[j].clone() if 'seg' in stages else disp_dev[j],
+                                    segment='seg' in stages, warp='warp' in stages, out_host=outs_pin if (e2e and 'warp' in stages) else None)
+        if r['num_instances'] is not None:
+            stats["instances"] += sum(r['num_instances']); stats["calls"] += 1
 
     def barrier():
         if world > 1:
@@ -431,14 +463,9 @@ def main():
     ms_e2e, _ = timed(True, args.steps)
 
     # ---- per-kernel device time of the same step (second pass, a CUDA event after every launch) -> roofline
-    torch.cuda.synchronize()
-    lib.csb_profile_begin(st())
-    step(0, False)
-    buf = ctypes.create_string_buffer(1 << 16)
-    lib.csb_profile_end(buf, len(buf))
-    prof = json.loads(buf.value.decode())
+    prof = profile_call(lib, lambda: step(0, False))
 
-    other = run_other(pipe, imgs_np, args) if (world == 1 and not args.no_other) else None
+    other = run_other(pipe, imgs_np, args, lib) if (world == 1 and not args.no_other) else None
 
     # throughput counters: ONE all-gather of a per-rank struct over NCCL/NVLink
     frames = args.steps * B
@@ -452,9 +479,15 @@ def main():
             peaks = json.load(open(pk))
         hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")        # ncu dram__bytes per kernel of this same step (tools/ncu_traffic.py)
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))
         P = H * W
         dom = max((k for k in prof if k != "memset"), key=lambda k: prof[k]["ms"]) if prof else None
         roof = None
+        tr = traffic.get("kernels", {}).get(dom) if dom else None
+        tr_same = bool(tr) and traffic.get("batch") == B and traffic.get("stages") == ",".join(stages) and traffic.get("depth") == args.depth
         if dom == "k_conv_tc":
             # algorithmic FLOPs of the tensor-core launches of one step: detector 1011.9 GFLOP / image @1024^2 (ConvNeXt-B 641.7 + neck 132.2
             # + head 237.9), LeReS 591.9 GFLOP / image @640^2 input
@@ -464,41 +497,60 @@ def main():
             depth_gflop = 0.0 if 'depth' not in stages else (591.9 if args.depth == 'leres' else zoe_gflop)
             gflop = (1011.9 if 'seg' in stages else 0.0) * B + depth_gflop * B
             ach = gflop / prof[dom]["ms"]                             # GFLOP / ms = TFLOP/s
-            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak, "traffic": None,
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
+                    "traffic": (tr["dram_bytes_per_launch"] if tr_same else None),
                     "peak_source": "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback",
                     "launches_per_step": prof[dom]["count"], "algorithmic_gflop_per_step": gflop, "avg_launch_us": 1e3 * prof[dom]["ms"] / prof[dom]["count"],
-                    # `traffic` stays null: one step is ~270 launches of ~60 different layer shapes, so there is no single per-launch figure; the ncu
-                    # --set full captures of the two heaviest shapes are summarised in profiles/ (DRAM bytes == algorithmic bytes there)
-                    "traffic_note": "profiles/r1_fc1_epilogue_ncu.md: 512->2048 @32x64x64 moves 623 MB of DRAM traffic for 673 MB algorithmic, "
-                                    "128->512 @16x256x256 1290 MB for 1342 MB"}
+                    "flop_note": "the numerator also holds the depthwise 7x7/5x5 and mask-head FLOPs (~1-2 %), which run on other kernels: frac is that much generous"}
+            if tr:
+                roof["traffic_source"] = {"file": "profiles/r2_traffic.json", "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the "
+                                          "kernel's launches of one step)", "same_config_as_this_run": tr_same, **{k: tr[k] for k in ("launches", "dram_read_bytes", "dram_write_bytes")}}
         elif dom:
             alg_bytes = {"k_splat": 52 * P, "k_zpass": 16 * P, "k_degrid": 8 * P, "k_norm_pack_mark": 24 * P, "k_crop_resize": 6 * P, "k_d2c_max": 4 * P,
                          "k_d2c_scale": 12 * P, "k_d2c_points": 55 * P}
             dur_ms = prof[dom]["ms"] / prof[dom]["count"]
             ab = alg_bytes.get(dom)
             ach = ab / (dur_ms * 1e-3) / 1e9 if ab else None
-            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None, "traffic": None,
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": (ach / hbm_peak) if ach else None,
+                    "traffic": (tr["dram_bytes_per_launch"] if tr_same else None),
                     "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "algorithmic_bytes_per_launch": ab}
         if roof is not None:
             roof["per_kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+            if "k_dwconv_halo" in prof:                               # second kernel: fp32 FMA issue bound (49 FMA per output element), HBM floor 4 C B/px
+                dw_gflop = 2 * 49 * 97.5e6 * B / 1e9                  # ConvNeXt-B @1024^2: 97.5 M (pixel, channel) outputs per image
+                roof["second_kernel"] = {"kernel": "k_dwconv_halo", "ms_per_step": round(prof["k_dwconv_halo"]["ms"], 3), "bound": "fp32 FMA issue",
+                                         "achieved_tflops": dw_gflop / prof["k_dwconv_halo"]["ms"], "peak_tflops": 72.0,
+                                         "peak_source": "148 SMs x 128 FMA/clk x 2 x 1.9 GHz (packed FFMA2)", "hbm_floor_ms": 4 * 97.5e6 * B / (hbm_peak * 1e6)}
         h2d = B * H * W * 3                                           # the uint8 BGR frames; every later stage stays on the device
         d2h = (B * H * W * 3 if 'warp' in stages else 0) + (4 * B if 'seg' in stages else 0)     # rendered uint8 frames + instance counts
         out = {"metric": METRIC, "value": total_frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate) / f32 render",
                "data": "synthetic", "config": workload_config(B, S, stages, args.depth), "clocks": clocks,
-               "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "api": "KenBurnsPipeline.render_frame_batch(pinned host uint8 frames, out_host=pinned uint8 frames)"},
                "gpu_launches": launches, "roofline": roof,
-               "instances_per_image": stats["instances"] / max(1, (args.warmup + 1 + 2 * args.steps + 1) * B) if 'seg' in stages else None}
+               "instances_per_image": stats["instances"] / max(1, stats["calls"] * B) if 'seg' in stages else None}
         if world == 1 and not args.no_other:
             out["other_workloads"] = other
         if world == 1 and not args.no_cpu_baseline:
-            # the oracle port of the SAME workload (all stages) on the box's host cores, a bounded sample: 1 warm-up + 2 timed frames
+            # the oracle port of the SAME workload (all stages) on the box's host cores, a bounded sample: 1 warm-up + 2 timed frames; its frames are also
+            # the checker of the `parity` block
             if args.depth == 'leres':
                 cpu = CpuPath(stages, 'leres')
-                sec = cpu.time(imgs_np[:2], disp_np[:2], 2, 1)
-                out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
-                                       "sample": f"2 frames of 1024x1024 (after 1 warm-up) through every stage of the workload: oracle/det_oracle.py + oracle/leres_oracle.py "
-                                                 f"(PyTorch fp32, {cpu.cores} threads) + oracle/kb_oracle.c (scalar C)"}
+                sec = cpu.time(imgs_np[:2], disp_np[:2], 2, 1, keep=True)
+                out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cpu.cores, "kind": "port", "sample": cpu.sample_text(2)}
+                out["parity"] = parity_block(pipe, cpu, imgs_np, disp_np, stages)
+                ex = os.path.join(ROOT, "tests", "golden", "example_1562990_512.jpg")
+                if 'seg' in stages and os.path.exists(ex):            # BASELINE configs[0]: the CPU arm of AnimeInsSeg.infer on the 512 x 512 example image
+                    import cv2
+                    img512 = cv2.imread(ex)
+                    cpu.D.infer(cpu.det, img512)
+                    t0 = time.perf_counter()
+                    for _ in range(5):
+                        n512 = len(cpu.D.infer(cpu.det, img512)['scores'])
+                    s512 = (time.perf_counter() - t0) / 5
+                    out["cpu_baseline_512"] = {"value": 1.0 / s512, "unit": "images/s", "cores": cpu.cores, "kind": "port", "instances": n512,
+                                               "sample": "5 calls of oracle.det_oracle.infer (refine off) on tests/golden/example_1562990_512.jpg, det_size=512 (BASELINE configs[0])"}
             else:
                 out["cpu_baseline"] = {"value": cpu_arm(imgs_np[:2], disp_np[:2], 4, 1), "unit": "frames/s", "cores": 1, "kind": "port",
                                        "sample": "4 frames of 1024x1024 on 1 thread through the WARP stage only (oracle/kb_oracle.c); the DPT-BEiT-L CPU oracle @672^2 "

@@ -289,19 +289,18 @@ class KenBurnsPipeline:
             from ..depth_modules.leres import LeReS
             if getattr(self, 'leres', None) is None:
                 sd = None
-                if ckpt is not None:
-                    obj = torch.load(ckpt, map_location='cpu')
-                    sd = obj.get('depth_model', obj)
-                    sd = {('depth_model.' + k if not k.startswith('depth_model.') else k): v for k, v in sd.items()}
+                if ckpt is not None:                                         # res101.pth: {'depth_model': state_dict} (leres/__init__.py:84-89)
+                    from ..utils.checkpoints import leres_state_dict
+                    sd = leres_state_dict(ckpt)
                 self.leres = LeReS(sd, self.device)
             self.depth_model = lambda img, img_tensor: self._depth_est_leres(img_tensor, img)
         elif depth_est == 'zoe':
             from ..depth_modules.zoedepth import ZoeDepth
             if getattr(self, 'depth_zoe', None) is None:
                 sd = None
-                if ckpt is not None:                                         # ZoeD_M12_N.pt: {'model': state_dict} (model_io.py:49-58)
-                    obj = torch.load(ckpt, map_location='cpu')
-                    sd = obj.get('model', obj)
+                if ckpt is not None:                                         # ZoeD_M12_N.pt: {'model': state_dict} (model_io.py:27-52)
+                    from ..utils.checkpoints import zoe_state_dict
+                    sd = zoe_state_dict(ckpt)
                 self.depth_zoe = ZoeDepth(sd, self.device, img_size=[672, 672])               # reference :543
             self.depth_model = lambda img, img_tensor: self._depth_est_zoe(img_tensor, img)
 
@@ -364,6 +363,12 @@ class KenBurnsPipeline:
         ev.record()
         return (ev, (ori_h, ori_w), logits.shape[0], None)
 
+    def leres_finish_batch(self, handle):
+        """leres_finish as ONE tensor [N,1,H,W] (no per-image views / re-stacking)"""
+        if handle[0] is None:
+            return handle[3]
+        return torch.cat(self.leres_finish(handle))
+
     def leres_finish(self, handle):
         """Phase 2: wait for the logits, run the reference's host-side tail (16->8 bit quantisation, OpenCV resize; a thread pool -- OpenCV and
         numpy release the GIL), upload the disparities."""
@@ -395,7 +400,8 @@ class KenBurnsPipeline:
         self.inpaint_type = inpainting
         if self.kenburns_inpaintnet is None:
             from .models.pointcloud_inpainting import Inpaint
-            sd = torch.load(ckpt, map_location='cpu') if ckpt is not None else None
+            from ..utils.checkpoints import plain_state_dict
+            sd = plain_state_dict(ckpt) if ckpt is not None else None             # models/__init__.py:16-20
             self.kenburns_inpaintnet = Inpaint(sd, self.device)
 
     def set_depth_refinement(self, depth_refinement: str, ckpt=None):
@@ -404,7 +410,8 @@ class KenBurnsPipeline:
             raise NotImplementedError(f'Invalid depth refinement: {depth_refinement}')
         if getattr(self, 'depth_refinenet', None) is None:
             from .models.disparity_refinement import Refine
-            sd = torch.load(ckpt, map_location='cpu') if ckpt is not None else None
+            from ..utils.checkpoints import plain_state_dict
+            sd = plain_state_dict(ckpt) if ckpt is not None else None             # models/__init__.py:7-11
             self.depth_refinenet = Refine(sd, self.device)
         self._refine_depth = lambda img, disparity: self.depth_refinenet.forward(img, disparity)
 
@@ -494,22 +501,132 @@ class KenBurnsPipeline:
 
     def inpaint(self, tenShift, tenPoints, objCommon, verbose=False):
         """reference :441-512 ('default' branch): run the Inpaint net for the shifted view, lift its disparity to points, and append the pixels that
-        were holes in that view (tenExisting == 0) to the growing point cloud.  (The boolean-mask gathers are torch glue, as in the reference; the
+        were holes in that view (tenExisting == 0) to the growing point cloud.  (The
         `stage_inpainted_*` preview images of the reference, which need a D2H per call, are not produced.)"""
         from .models.utils import depth_to_points, spatial_filter
         sh = torch.as_tensor(tenShift, dtype=torch.float32).flatten()
         o = self.kenburns_inpaintnet.forward(objCommon['tenRawImage'], objCommon['tenRawDisparity'], sh, objCommon, None)
+        H_, W_ = o['tenExisting'].shape[-2:]
         focal, baseline = objCommon['fltFocal'], objCommon['fltBaseline']
         depth = (focal * baseline) / (o['tenDisparity'] + 0.0000001)                                              # :454
         valid = (spatial_filter(o['tenDisparity'] / o['tenDisparity'].max(), 'laplacian').abs() < 0.03).float()  # :455
         points = depth_to_points(depth * valid, focal).view(1, 3, -1) - sh.view(1, 3, 1).to(self.device)          # :456-458
-        tenMask = (o['tenExisting'] == 0.0).view(1, 1, -1)                                                        # :462
-        pick = lambda t, c: t.reshape(1, c, -1)[tenMask.repeat(1, c, 1)].view(1, c, -1)
-        objCommon.inpainted_img = torch.cat([objCommon.inpainted_img, pick(o['tenImage'], 3)], 2)                 # :472
-        objCommon['tenInpaDisparity'] = torch.cat([objCommon['tenInpaDisparity'], pick(o['tenDisparity'], 1)], 2)  # :510
-        objCommon['tenInpaDepth'] = torch.cat([objCommon['tenInpaDepth'], pick(depth, 1)], 2)                     # :511
-        objCommon['tenInpaPoints'] = torch.cat([objCommon['tenInpaPoints'], pick(points, 3)], 2)                  # :512
+        # :462-512 -- append the pixels that were holes in this view (tenExisting == 0) to the cloud: order-preserving stream compaction on the device
+        # (csrc/kb_compact.cu), one 4-byte host read for the new size (the reference's boolean-mask gathers synchronise too)
+        P = H_ * W_
+        existing = _f32(o['tenExisting']).reshape(-1)
+        lib().csb_cloud_append_scratch_ints.restype = C.c_longlong
+        scratch = torch.empty(int(lib().csb_cloud_append_scratch_ints(C.c_longlong(P))), device=self.device, dtype=torch.int32)
+        total = torch.empty(1, device=self.device, dtype=torch.int32)
+        check(lib().csb_cloud_append_count(ptr(existing), C.c_longlong(P), ptr(scratch), ptr(total), stream()), "csb_cloud_append_count")
+        srcs = [(_f32(o['tenImage']).reshape(3, P), 3), (_f32(o['tenDisparity']).reshape(1, P), 1), (_f32(depth).reshape(1, P), 1), (_f32(points).reshape(3, P), 3)]
+        olds = [_f32(objCommon.inpainted_img).reshape(3, -1), _f32(objCommon['tenInpaDisparity']).reshape(1, -1), _f32(objCommon['tenInpaDepth']).reshape(1, -1),
+                _f32(objCommon['tenInpaPoints']).reshape(3, -1)]
+        n_old = olds[0].shape[1]
+        n_new = n_old + int(total.item())
+        news = [torch.empty((1, c, n_new), device=self.device, dtype=torch.float32) for _, c in srcs]
+        plane = lambda t, c, n: [t.data_ptr() + 4 * n * k for k in range(c)]
+        sp = [a for (t, c) in srcs for a in plane(t, c, P)]
+        op = [a for t, (_, c) in zip(olds, srcs) for a in plane(t, c, n_old)]
+        dp = [a for t, (_, c) in zip(news, srcs) for a in plane(t, c, n_new)]
+        arr = lambda v: (C.c_void_p * len(v))(*v)
+        check(lib().csb_cloud_append(ptr(existing), C.c_longlong(P), ptr(scratch), arr(sp), arr(op), arr(dp), len(sp), C.c_longlong(n_old), stream()),
+              "csb_cloud_append")
+        objCommon.inpainted_img, objCommon['tenInpaDisparity'], objCommon['tenInpaDepth'], objCommon['tenInpaPoints'] = news
         return o
+
+    # ---- batched per-frame path (extension; the reference is a batch-1 loop over exactly these calls)
+    def render_frame_batch(self, imgs, shift_u: float = 40.0, shift_v: float = -25.0, depth_ratio: float = 0.8, crop_frac: float = 0.97,
+                           raw_disparity=None, segment: bool = True, warp: bool = True, out_host=None, det_sub: int = 32, zoe_sub: int = 16):
+        """One Ken-Burns frame per input frame, for a batch of equally sized frames -- per frame exactly the reference's sequence
+        `AnimeInsSeg.infer` body (:862-872, refine off) -> `_depth_est` (:563-581 / :812-818) -> `depth_adjustment_animesseg` (:604) ->
+        disparity -> cloud (:928-937) -> `process_shift` at camera offset (shift_u, shift_v) with the closest depth scaled by `depth_ratio`
+        (common.py:59-83) -> render + fill + uint8 pack (:1028-1040) -> centre crop `crop_frac` + resize (:1069-1070) -- with the networks run over
+        the whole batch and no host synchronisation besides the instance counts.
+
+        imgs: uint8 [B,H,W,3] BGR -- a CUDA tensor (inputs resident in HBM) or a (pinned) host tensor / ndarray, uploaded here.
+        raw_disparity: optional [B,H,W] fp32 CUDA tensor replacing the depth estimator.  out_host: optional pinned uint8 [B,H,W,3]; every
+        finished frame is copied into it and the call returns after the last copy.
+        -> dict(frames=[B,H,W,3] uint8 CUDA tensor, num_instances=list[int] or None)"""
+        cfg = self.cfg
+        dev = self.device
+        if isinstance(imgs, np.ndarray):
+            imgs = torch.from_numpy(imgs)
+        B, H, W = imgs.shape[:3]
+        st = getattr(self, '_rfb', None)
+        if st is None or st['key'] != (B, H, W):
+            st = self._rfb = {
+                'key': (B, H, W), 'stage': torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8), 'scratch': FrameScratch(H, W, dev),
+                'clouds': [{k: torch.empty((1, c, H, W), device=dev) for k, c in (('disparity', 1), ('depth', 1), ('valid', 1), ('points', 3), ('unaltered', 3))}
+                           for _ in range(2)],
+                'data': [torch.empty((1, 4, H * W), device=dev) for _ in range(2)], 'scalars': torch.empty(8, device=dev),
+                'd2c': torch.empty(64, device=dev, dtype=torch.int64), 'shift': torch.empty(3, device=dev),
+                'out': torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8)}
+        if imgs.is_cuda:
+            batch = imgs
+        else:                                                        # H2D of this call's inputs (asynchronous from pinned memory)
+            batch = st['stage']
+            batch.copy_(imgs, non_blocking=True)
+        cd = C.c_double
+        focal, baseline = float(cfg.focal), float(cfg.baseline)
+        # ---- depth: LeReS is enqueued first, so that its (device-side) tail overlaps nothing on the host; ZoeDepth in sub-batches
+        disp = raw_disparity
+        handle = None
+        if disp is None:
+            if cfg.depth_est == 'leres':
+                handle = self.leres_enqueue(None, imgs_dev=batch)
+            elif cfg.depth_est == 'zoe':
+                disp = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+                for s0 in range(0, B, zoe_sub):
+                    d = self.depth_zoe.infer_batch(batch[s0:s0 + zoe_sub])
+                    for i in range(d.shape[0]):                               # :815-817 is per image (min positive)
+                        self.depth_zoe.disparity(d[i], focal, baseline, out=disp[s0 + i])
+            else:
+                raise NotImplementedError(f"render_frame_batch: depth_est '{cfg.depth_est}' (pass raw_disparity=)")
+        # ---- segmentation (A1-A9): detector forward + post-process per sub-batch
+        masks, nums_dev = [], []
+        if segment:
+            from ..animeinsseg import rtmdet_postprocess
+            seg = self.animeinsseg
+            test_cfg = seg.model.bbox_head.test_cfg
+            for s0 in range(0, B, det_sub):
+                cls, reg, ker, mf = seg.model.net.forward(batch[s0:s0 + det_sub])
+                o = rtmdet_postprocess(cls, reg, ker, mf, (H, W), test_cfg)
+                masks.append(o['masks']); nums_dev.append(o['num'])
+        if handle is not None:
+            disp = self.leres_finish_batch(handle)
+        disp = disp.reshape(B, H, W)
+        nums = None
+        if segment:
+            nums = [int(v) for t in nums_dev for v in t.cpu().tolist()]          # the one host read: instance counts for the caller
+            for j, s0 in enumerate(range(0, B, det_sub)):                      # instance-guided depth flattening (C2), in place
+                depth_adjust_batch(disp[s0:s0 + det_sub], masks[j], nums_dev[j])
+        if not warp:
+            return dict(frames=None, num_instances=nums, disparity=disp)
+        pw, ph = int(math.floor(crop_frac * W)), int(math.floor(crop_frac * H))
+        fs = st['scratch']
+        copy_stream = None
+        if out_host is not None:
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            copy_stream = self._copy_stream
+        for b in range(B):
+            c, data = st['clouds'][b & 1], st['data'][b & 1]
+            check(lib().csb_disparity_to_cloud(ptr(disp[b]), H, W, cd(focal), cd(baseline), ptr(c['disparity']), ptr(c['depth']), ptr(c['valid']),
+                                               ptr(c['points']), ptr(c['unaltered']), ptr(st['scalars']), ptr(st['d2c']), ptr(batch[b]), ptr(data), stream()),
+                  "csb_disparity_to_cloud")
+            check(lib().csb_shift_from_scalars(ptr(st['scalars']), W, H, cd(focal), cd(shift_u), cd(shift_v), cd(depth_ratio), ptr(st['shift']), stream()),
+                  "csb_shift_from_scalars")
+            check(lib().csb_kenburns_frame(ptr(c['points']), ptr(data), H * W, H, W, cd(focal), cd(baseline), None, ptr(st['shift']), pw, ph,
+                                           cd(W / 2.0), cd(H / 2.0), ptr(fs.zkey), ptr(fs.zee), ptr(fs.acc), ptr(fs.packed), ptr(st['out'][b]), None, stream()),
+                  "csb_kenburns_frame")
+            if copy_stream is not None:                                        # D2H of frame b overlaps the render of frame b+1
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    out_host[b].copy_(st['out'][b], non_blocking=True)
+        if copy_stream is not None:
+            copy_stream.synchronize()                                          # the caller receives this batch's frames
+        return dict(frames=st['out'], num_instances=nums, disparity=disp)
 
     # ---- reference :979-1081
     def process_kenburns(self, objSettings, objCommon: KenBurnsConfig, inpaint: bool = True, verbose: bool = False):
@@ -550,22 +667,48 @@ class KenBurnsPipeline:
                 ins = objCommon.instances
                 masks = None if ins is None or ins.is_empty else ins.masks
                 bokeh = fx.BokehScratch(H, W, 0 if masks is None else int(masks.shape[0]), pts.device, objCommon.lightness_factor)
-            for i, fltStep in enumerate(steps):                                    # the reference frame loop, :1015-1072
+            if bokeh is None:                                                      # the reference frame loop, :1015-1072, as ONE library call
+                shifts = np.ascontiguousarray(np.stack([np.array(shift_scalars(camera(t), objCommon), np.float32) for t in steps]), np.float32)
+                if getattr(self, '_copy_stream', None) is None:
+                    self._copy_stream = torch.cuda.Stream(device=pts.device)
+                fs = self._frame_scratch
+                self._copy_stream.wait_stream(torch.cuda.current_stream())         # out_host / out_dev were allocated on the current stream
+                check(lib().csb_kenburns_frames(ptr(_f32(pts)), ptr(_f32(data)), N, H, W, C.c_double(objCommon['fltFocal']), C.c_double(objCommon['fltBaseline']),
+                                                shifts.ctypes.data_as(C.POINTER(C.c_float)), len(steps), int(pw), int(ph), C.c_double(W / 2.0), C.c_double(H / 2.0),
+                                                ptr(fs.zkey), ptr(fs.zee), ptr(fs.acc), ptr(fs.packed), ptr(out_dev), C.c_void_p(out_host.data_ptr()),
+                                                C.c_void_p(self._copy_stream.cuda_stream), stream()), "csb_kenburns_frames")
+                out_dev.record_stream(self._copy_stream)
+            for i, fltStep in (enumerate(steps) if bokeh is not None else ()):    # depth of field (:1042-1067): the bokeh stage sits between pack and crop
                 sh = np.array(shift_scalars(camera(fltStep), objCommon), np.float32)
-                if bokeh is None:
-                    kenburns_frame(pts, data, W, H, objCommon['fltFocal'], objCommon['fltBaseline'], sh, pw, ph, W / 2.0, H / 2.0,
-                                   scratch=self._frame_scratch, out=out_dev[i])
-                else:
-                    _, depth = kenburns_frame(pts, data, W, H, objCommon['fltFocal'], objCommon['fltBaseline'], sh, pw, ph, W / 2.0, H / 2.0,
-                                              scratch=self._frame_scratch, out=False, want_depth=True)
-                    d8 = fx.colorize_gray_r(depth, bokeh)                          # colorize(depth_rendered, cmap='gray_r')[..., 0]
-                    if i == 0:
-                        fx.focal_plane_range(d8, masks, bokeh)                     # focalplane_start / _end, :1045-1059
-                    blurred = fx.bokeh_blur(self._frame_scratch.packed, d8, 32, objCommon.lightness_factor, objCommon.depth_factor, True,
-                                            scratch=bokeh, focal_int=fx.focal_interp(fltStep, objCommon.dof_speed))
-                    check(lib().csb_frame_crop_resize(ptr(blurred), H, W, int(pw), int(ph), C.c_double(W / 2.0), C.c_double(H / 2.0),
-                                                      ptr(out_dev[i]), stream()), "csb_frame_crop_resize")
+                _, depth = kenburns_frame(pts, data, W, H, objCommon['fltFocal'], objCommon['fltBaseline'], sh, pw, ph, W / 2.0, H / 2.0,
+                                          scratch=self._frame_scratch, out=False, want_depth=True)
+                d8 = fx.colorize_gray_r(depth, bokeh)                              # colorize(depth_rendered, cmap='gray_r')[..., 0]
+                if i == 0:
+                    fx.focal_plane_range(d8, masks, bokeh)                         # focalplane_start / _end, :1045-1059
+                blurred = fx.bokeh_blur(self._frame_scratch.packed, d8, 32, objCommon.lightness_factor, objCommon.depth_factor, True,
+                                        scratch=bokeh, focal_int=fx.focal_interp(fltStep, objCommon.dof_speed))
+                check(lib().csb_frame_crop_resize(ptr(blurred), H, W, int(pw), int(ph), C.c_double(W / 2.0), C.c_double(H / 2.0),
+                                                  ptr(out_dev[i]), stream()), "csb_frame_crop_resize")
                 out_host[i].copy_(out_dev[i], non_blocking=True)                   # D2H overlaps the next frame's render
             torch.cuda.current_stream().synchronize()
             frames = [out_host[i].numpy() for i in range(len(steps))]
             return [frames, objCommon]
+
+
+def npyframes2video(npy_frame_list, video_save_path: str, playback: bool = False, fps: int = 25):
+    """reference :1086-1090: write the BGR uint8 frames as a 25 fps video; `playback` appends the reversed sequence without its two end frames
+    (forward + back loop).  The reference goes through moviepy (libx264, RGB frames); here OpenCV's writer takes the BGR frames directly."""
+    import cv2
+    sequence = list(npy_frame_list)
+    if playback:
+        sequence += sequence[::-1][1:-1]
+    if not sequence:
+        raise ValueError("npyframes2video: empty frame list")
+    h, w = sequence[0].shape[:2]
+    writer = cv2.VideoWriter(video_save_path, cv2.VideoWriter_fourcc(*'mp4v'), float(fps), (w, h))
+    if not writer.isOpened():
+        raise RuntimeError(f"npyframes2video: cannot open {video_save_path} for writing")
+    for frame in sequence:
+        writer.write(np.ascontiguousarray(frame))
+    writer.release()
+    return len(sequence)

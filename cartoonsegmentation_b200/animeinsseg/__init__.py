@@ -63,11 +63,9 @@ class AnimeInsSeg:
             raise RuntimeError("cartoonsegmentation_b200 has no CPU path (the reference's device='cpu' mode is the oracle's job)")
         if ckpt is None:
             sd = synthetic_state_dict(0)
-        elif isinstance(ckpt, str):
-            obj = torch.load(ckpt, map_location='cpu')
-            sd = obj.get('state_dict', obj)
-        else:
-            sd = ckpt
+        else:                                      # a checkpoint path in the reference's format ({'state_dict', 'meta': {'cfg'}}, :196-208) or a state_dict
+            from ..utils.checkpoints import detector_state_dict
+            sd = detector_state_dict(ckpt)
         net = RTMDetIns(sd, self.device)
         test_cfg = dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_threshold=0.6), max_per_img=100, min_bbox_size=0, mask_thr_binary=0.5)
         self.model = SimpleNamespace(net=net, bbox_head=SimpleNamespace(test_cfg=test_cfg, prior_generator=SimpleNamespace(strides=[(s, s) for s in STRIDES])))
@@ -94,8 +92,9 @@ class AnimeInsSeg:
             if self.refinenet is None:
                 from .isnet import ISNetDIS
                 sd = None
-                if refine_ckpt is not None:
-                    sd = torch.load(refine_ckpt, map_location='cpu')
+                if refine_ckpt is not None:            # models/AnimeInstanceSegmentation/refine_last.ckpt: a plain state_dict (animeseg_refine/__init__.py:161-165)
+                    from ..utils.checkpoints import plain_state_dict
+                    sd = plain_state_dict(refine_ckpt)
                 self.refinenet = ISNetDIS(sd, self.device)
             self.refine_size = refine_size
             self.postprocess_refine = self._postprocess_refine

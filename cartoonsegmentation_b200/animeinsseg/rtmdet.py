@@ -346,8 +346,17 @@ class RTMDetIns:
         return t
 
     def forward(self, img_u8):
+        """[N,H,W,3] uint8 BGR -> (cls, reg, ker per level NHWC fp32, mask_feat).  Batches of up to 4 images (launch-bound: ~200 launches of a few us
+        each) are replayed from a CUDA graph per input shape (utils/graphs.py); the returned tensors are then the graph's static outputs, valid until
+        the next forward of the same shape."""
         if img_u8.dim() == 3:
             img_u8 = img_u8[None]
+        if getattr(self, '_graphed', None) is None:
+            from ..utils.graphs import GraphedForward
+            self._graphed = GraphedForward(self._forward_impl)
+        return self._graphed(img_u8.contiguous())
+
+    def _forward_impl(self, img_u8):
         N, H, W, _ = img_u8.shape
         assert H % 32 == 0 and W % 32 == 0, "detector input must be padded to a multiple of 32 (Pad to det_size)"
         dev, f16 = img_u8.device, torch.float16

@@ -245,12 +245,19 @@ EncodeTiledFn encode_fn() {
 
 template <int K, bool STATS>
 int launch(const CUtensorMap& tm, const DwHaloParams& p, cudaStream_t st) {
-    // the attribute belongs to the current device: set it on every launch (cheap) rather than once per process
-    cudaFuncSetAttribute(k_dwconv_halo<K, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Geo<K>::kSmem);
-    const long long total = p.ntiles * p.chunks;
-    int dev = 0, sms = 0;
+    // the attribute belongs to the device that is current when it is set: once per (instantiation, device), outside any stream capture
+    static bool attr_done[64] = {};
+    static int sm_count[64] = {};
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dev = dev < 0 || dev >= 64 ? 0 : dev;
+    if (!attr_done[dev]) {
+        cudaFuncSetAttribute(k_dwconv_halo<K, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Geo<K>::kSmem);
+        cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+        attr_done[dev] = true;
+    }
+    const long long total = p.ntiles * p.chunks;
+    const int sms = sm_count[dev] > 0 ? sm_count[dev] : 148;
     const int grid = (int) (total < sms ? total : sms);
     k_dwconv_halo<K, STATS><<<grid, kThreads, Geo<K>::kSmem, st>>>(tm, p);
     return csb::launched("k_dwconv_halo", st);

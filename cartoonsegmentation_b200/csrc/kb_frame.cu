@@ -277,3 +277,38 @@ extern "C" int csb_kenburns_frame(const float* points, const float* data, int N,
     else k_crop_resize<false><<<csb::wave_grid((long long) H * W, 256, 8), 256, 0, st>>>(packed, H, W, p, H, W, out);
     return csb::launched("k_crop_resize", st);
 }
+
+// The reference's whole frame loop (kenburns_effect.py:1015-1072) in ONE call: F frames of csb_kenburns_frame with per-frame camera shifts, written
+// to out [F,H,W,3] on the device; if `host_out` (pinned) and `copy_stream` are given, frame f is copied to the host on `copy_stream` as soon as it
+// is finished (one reusable event orders the copy after the frame), so the D2H of frame f overlaps the render of frame f+1 and the Python side
+// issues one call instead of 6 launches + 1 copy per frame.
+extern "C" int csb_kenburns_frames(const float* points, const float* data, int N, int H, int W, double focal, double baseline, const float* shifts, int F,
+                                   int pw, int ph, double cx, double cy, int32_t* zkey, float* zee, float* acc, uint8_t* packed, uint8_t* out,
+                                   uint8_t* host_out, void* copy_stream, void* stream) {
+    CSB_REQUIRE(shifts && out && F > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t) stream, cs = (cudaStream_t) copy_stream;
+    const size_t frame_bytes = (size_t) H * W * 3;
+    cudaEvent_t ev = nullptr;
+    if (host_out) {
+        CSB_REQUIRE(copy_stream != nullptr && copy_stream != stream, "host_out needs a separate copy stream");
+        CSB_TRY(csb::cuda_ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate"));
+    }
+    int rc = CSB_OK;
+    for (int f = 0; f < F && rc == CSB_OK; ++f) {
+        rc = csb_kenburns_frame(points, data, N, H, W, focal, baseline, shifts + 3 * f, nullptr, pw, ph, cx, cy, zkey, zee, acc, packed,
+                                out + (size_t) f * frame_bytes, nullptr, stream);
+        if (rc == CSB_OK && host_out) {
+            cudaEventRecord(ev, st);
+            cudaStreamWaitEvent(cs, ev, 0);
+            rc = csb::cuda_ok(cudaMemcpyAsync(host_out + (size_t) f * frame_bytes, out + (size_t) f * frame_bytes, frame_bytes, cudaMemcpyDeviceToHost, cs), "D2H");
+        }
+    }
+    if (ev) {
+        if (rc == CSB_OK) {                        // the caller's stream continues only after the last copy (it may reuse `out`)
+            cudaEventRecord(ev, cs);
+            cudaStreamWaitEvent(st, ev, 0);
+        }
+        cudaEventDestroy(ev);
+    }
+    return rc;
+}

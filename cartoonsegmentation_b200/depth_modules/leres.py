@@ -179,6 +179,14 @@ class LeReS:
         """img_u8 [N,H,W,3] uint8 (BGR unless rgb_input), H and W multiples of 32 -> depth logits [N,H,W] fp32."""
         if img_u8.dim() == 3:
             img_u8 = img_u8[None]
+        if rgb_input:
+            return self._forward_impl(img_u8, True)
+        if getattr(self, '_graphed', None) is None:                # batches <= 4 replay a CUDA graph per input shape (utils/graphs.py)
+            from ..utils.graphs import GraphedForward
+            self._graphed = GraphedForward(self._forward_impl)
+        return self._graphed(img_u8.contiguous())
+
+    def _forward_impl(self, img_u8, rgb_input=False):
         N, H, W, _ = img_u8.shape
         assert H % 32 == 0 and W % 32 == 0
         # estimateleres: BGR -> RGB (depthmap.py:35), ToTensor on float (no /255 again), Normalize(ImageNet) (:26) on img/255

@@ -411,9 +411,9 @@ class ZoeDepth:
             check(lib().csb_zoe_finish(ptr(metric[i * nb:]), int(with_flip_aug), Hn, Wn, H, W, ph, pw, ptr(out[i]), stream()), "csb_zoe_finish")
         return out
 
-    def disparity(self, depth, focal, baseline):
+    def disparity(self, depth, focal, baseline, out=None):
         """`_depth_est_zoe` tail (kenburns_effect.py:815-817)"""
-        out = torch.empty_like(depth)
+        out = torch.empty_like(depth) if out is None else out
         check(lib().csb_zoe_disparity(ptr(depth), C.c_longlong(depth.numel()), C.c_double(focal), C.c_double(baseline), ptr(out), ptr(self._scratch), stream()),
               "csb_zoe_disparity")
         return out

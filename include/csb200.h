@@ -156,6 +156,15 @@ CSB_API int csb_masks_area_resize(const uint8_t* masks, int K, int H0, int W0, u
 /* AnimeInstances.compose_masks (anime_instances.py:282-298): logical OR of K masks of P = H*W bool bytes -> out [P]. */
 CSB_API int csb_masks_compose(const uint8_t* masks, int K, long long P, uint8_t* out, void* stream);
 
+/* Point-cloud growth after an inpaint pass (kenburns_effect.py:462-512): dst[c] = concat(old[c][0..n_old), src[c][existing == 0]) for up to 8 fp32
+ * planes, element order = the boolean-mask gather's (ascending pixel index): an order-preserving stream compaction on the device.
+ *   csb_cloud_append_scratch_ints(P)  ints of scratch;   csb_cloud_append_count: phase 1, the hole count lands in *total_out (device int);
+ *   csb_cloud_append: phase 2 (dst planes hold n_old + total floats). */
+CSB_API long long csb_cloud_append_scratch_ints(long long P);
+CSB_API int csb_cloud_append_count(const float* existing, long long P, int* scratch, int* total_out, void* stream);
+CSB_API int csb_cloud_append(const float* existing, long long P, const int* scratch, const float* const* src, const float* const* old_planes, float* const* dst,
+                             int planes, long long n_old, void* stream);
+
 /* ZoeDepth / MiDaS DPT-BEiT-L encoder pieces (the encoder is torch.hub `intel-isl/MiDaS` `DPT_BEiT_L_384`, loaded at
  * depth_modules/zoedepth/models/base_models/midas.py:341 and NOT vendored in the reference: restated from timm's BEiT + MiDaS v3.1's DPT).
  * Every Linear / Conv runs on csb_conv2d_nhwc; these are the remaining ops (csrc/zoe_attn.cu, csrc/zoe_io.cu).
@@ -211,6 +220,13 @@ CSB_API int csb_bokeh_blur(const uint8_t* frame, const uint8_t* depth8, int H, i
 CSB_API int csb_kenburns_frame(const float* points, const float* data, int N, int H, int W, double focal, double baseline,
                        const float* shift, const float* shift_dev, int pw, int ph, double cx, double cy,
                        int32_t* zkey, float* zee, float* acc, uint8_t* packed, uint8_t* out, float* depth_out, void* stream);
+
+/* The whole frame loop of kenburns_effect.py:1015-1072 in one call: F frames with per-frame camera shifts `shifts` [F,3] (host floats) -> out
+ * [F,H,W,3] u8 (device).  host_out (pinned, optional) + copy_stream: each finished frame is copied to the host on copy_stream, overlapping the
+ * next frame's render; `stream` waits for the last copy. */
+CSB_API int csb_kenburns_frames(const float* points, const float* data, int N, int H, int W, double focal, double baseline, const float* shifts, int F,
+                                int pw, int ph, double cx, double cy, int32_t* zkey, float* zee, float* acc, uint8_t* packed, uint8_t* out,
+                                uint8_t* host_out, void* copy_stream, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense contractions on the tcgen05 tensor cores (csrc/tc_conv.cu).  In the reference every conv / linear layer of
