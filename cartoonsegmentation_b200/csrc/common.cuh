@@ -57,15 +57,30 @@ inline int cuda_ok(cudaError_t e, const char* what) {
         if (_st != CSB_OK) return _st; \
     } while (0)
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs, e.g. depth_est_device != device)
 inline int num_sms() {
-    static int n = 0;
+    static int cache[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev] = n;
     }
     return n;
+}
+
+// true exactly once per device: guards per-device one-time setup such as cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which applies only to
+// the device that is current when it runs.  `flags` is a zero-initialised static array of 64 entries owned by the call site.
+inline bool first_use_on_device(unsigned char* flags) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (flags[dev]) return false;
+    flags[dev] = 1;
+    return true;
 }
 
 // Grid for a grid-stride kernel: a whole number of waves (multiple of the SM count), capped by the work.

@@ -438,11 +438,11 @@ extern "C" int csb_rtmdet_select(const float* const* cls, const float* const* re
     while (p2 < maxloc) p2 <<= 1;
     CSB_REQUIRE((size_t) p2 * 8 <= 200 * 1024, "level too large for the shared-memory sort: the location count is padded to a power of two and must be <= 16384 per level (det_size <= 1024)");
     cudaStream_t st = (cudaStream_t) stream;
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static unsigned char attr_done[64] = {};
+    if (csb::first_use_on_device(attr_done)) {          // per device, not per process
         cudaFuncSetAttribute(k_select_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    });
+    }
     k_select_level<<<N * L, 1024, (size_t) p2 * 8, st>>>(lv, N, score_thr, nms_pre, img_h, img_w, cand, cand_count);
     CSB_TRY(csb::launched("k_select_level", st));
     const int cap = L * nms_pre;

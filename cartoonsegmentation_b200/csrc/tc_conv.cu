@@ -102,9 +102,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// CG = 2 (CTA pair, tcgen05 cta_group::2): the load lands in THIS CTA's shared memory but signals the mbarrier of the pair's leader CTA
+// (`bar` is then a shared::cluster address obtained with mapa), which the .cta_group::2 form of the instruction permits.
+template <int CG>
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    if constexpr (CG == 1)
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -116,18 +135,35 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    if constexpr (CG == 1)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// CG = 2: ONE instruction issued by the leader CTA drives the tensor cores of both SMs of the pair: M = 256 (128 rows per CTA, each from its own
+// shared memory at the same offset), B = block_n rows of which each CTA holds half, accumulators in both CTAs' TMEM at the same column.
+template <int CG>
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    if constexpr (CG == 1)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// CG = 2: the arrival is multicast to the barrier at the same offset in both CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if constexpr (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t) 3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -354,23 +390,32 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
 }
 
 // Epilogue role: EG groups of 4 warps; warp w owns TMEM lane quarter (w & 3) and the 32-column chunks with chunk % EG == (w - 4) / 4.
-template <class T, int ACT, bool LN = false, int GM = kGeluMufuPairs>
+// CG = 2: `total_tiles` counts PAIR tiles (two m-tiles that share an n-tile); this CTA owns m-tile 2 * pair + rank (an m-tile past the end is
+// computed on zero-filled operands and never stored), and hands its accumulator stage back on the LEADER's tmem_empty barrier.
+template <class T, int ACT, int CG, bool LN = false, int GM = kGeluMufuPairs>
 __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
                                               const CUtensorMap* tmC) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int EG = (int) (blockDim.x >> 7) - 1;
     const int q = warp & 3, half = (warp - 4) >> 2;
     const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && (!p.bias || ((uintptr_t) p.bias % 16 == 0));
+    const int rank = CG == 2 ? (int) cluster_ctarank() : 0;
+    const int cta = CG == 2 ? (int) (blockIdx.x >> 1) : (int) blockIdx.x, ncta = CG == 2 ? (int) (gridDim.x >> 1) : (int) gridDim.x;
+    const uint32_t tempty_lead = CG == 2 ? mapa_u32(tempty0, 0) : tempty0;
+    auto release = [&](int s) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty_lead + 8u * s);
+        else mbar_arrive(tempty0 + 8u * s);
+    };
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+    for (int tile = cta; tile < total_tiles; tile += ncta) {
+        const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + rank;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
         const int m = q * 32 + lane;
         const int oh = th * p.bh + m / p.bw, ow = tw * p.bw + m % p.bw;
-        const bool row_ok = oh < p.H && ow < p.W;
+        const bool row_ok = oh < p.H && ow < p.W && img < p.N;
         // rows outside the image still run the arithmetic on the TMA-store path (the store clips them): keep their residual address in bounds
-        const size_t pix = ((size_t) img * p.H + (oh < p.H ? oh : p.H - 1)) * p.W + (ow < p.W ? ow : p.W - 1);
+        const size_t pix = ((size_t) (img < p.N ? img : p.N - 1) * p.H + (oh < p.H ? oh : p.H - 1)) * p.W + (ow < p.W ? ow : p.W - 1);
         const uint32_t stage = p.tma_store ? stage_base + (uint32_t) (warp - 4) * 2048u : 0u;
         const int row0 = q * 32;
         const int cw = tw * p.bw + row0 % p.bw, chh = th * p.bh + row0 / p.bw;
@@ -393,7 +438,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
         if (last < 0) {                                    // nothing to read for this warp in this tile: release immediately
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8u * as);
+            if (lane == 0) release(as);
         }
         for (int ch = half; ch < nchunks; ch += EG) {
             const int n0 = nt * p.block_n + ch * 32;
@@ -403,7 +448,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
             if (ch == last) {                              // accumulator rows of this warp fully read: hand the TMEM stage back
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty0 + 8u * as);
+                if (lane == 0) release(as);
             }
             epilogue_chunk<T, ACT, LN, GM>(p, acc, pix, n0, row_ok, fast, stage, tmC, cw, chh, img, neg_mean, rstd);
         }
@@ -412,33 +457,38 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
     if (p.tma_store && lane == 0) tma_store_wait_all();           // every tile store of this warp has completed before the CTA may exit
 }
 
-template <class T>
+template <class T, int CG>
 __device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
                                                   const CUtensorMap* tmC) {
     if (p.ln_stats) {     // LayerNorm-folded 1x1 conv: only the activations that follow a LayerNorm on this path
-        if (p.act == CSB_ACT_GELU) epilogue_role<T, CSB_ACT_GELU, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
-        else epilogue_role<T, CSB_ACT_NONE, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
+        if (p.act == CSB_ACT_GELU) epilogue_role<T, CSB_ACT_GELU, CG, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
+        else epilogue_role<T, CSB_ACT_NONE, CG, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
         return;
     }
     switch (p.act) {      // hoisted out of every loop: each instantiation is straight-line code
-        case CSB_ACT_RELU: epilogue_role<T, CSB_ACT_RELU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
-        case CSB_ACT_SILU: epilogue_role<T, CSB_ACT_SILU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
-        case CSB_ACT_GELU: epilogue_role<T, CSB_ACT_GELU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
-        case CSB_ACT_PRELU: epilogue_role<T, CSB_ACT_PRELU>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
-        case CSB_ACT_SIGMOID: epilogue_role<T, CSB_ACT_SIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
-        case CSB_ACT_SOFTPLUS: epilogue_role<T, CSB_ACT_SOFTPLUS>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
-        case CSB_ACT_HARDSIGMOID: epilogue_role<T, CSB_ACT_HARDSIGMOID>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
-        default: epilogue_role<T, CSB_ACT_NONE>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_RELU: epilogue_role<T, CSB_ACT_RELU, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_SILU: epilogue_role<T, CSB_ACT_SILU, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_GELU: epilogue_role<T, CSB_ACT_GELU, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_PRELU: epilogue_role<T, CSB_ACT_PRELU, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_SIGMOID: epilogue_role<T, CSB_ACT_SIGMOID, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_SOFTPLUS: epilogue_role<T, CSB_ACT_SOFTPLUS, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        case CSB_ACT_HARDSIGMOID: epilogue_role<T, CSB_ACT_HARDSIGMOID, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
+        default: epilogue_role<T, CSB_ACT_NONE, CG>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC); break;
     }
 }
 
-template <int EG>
+// CG = 1: one CTA per SM, every CTA an independent pipeline.  CG = 2: clusters of two CTAs (one TPC) work on two m-tiles that share an n-tile; each
+// CTA's producer loads its own activation tile and HALF of the weight tile, the leader's MMA warp issues tcgen05.mma.cta_group::2 (M = 256), so the
+// weight tile crosses the L2 -> SM fabric once per pair instead of once per CTA (the 128 x 256 x 64 k-block drops from 48 KiB to 32 KiB per SM).
+// Barriers: full[s] lives in the leader (one expect_tx arrival of the leader's producer + the bytes of both CTAs' loads), empty[s] and tmem_full[a]
+// exist in both CTAs and are signalled by multicast commits, tmem_empty[a] lives in the leader and counts the epilogue warps of both CTAs.
+template <int EG, int CG>
 __global__ void __launch_bounds__(128 * (EG + 1), 1) k_conv_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmC, const ConvKernelParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t row_bytes = (uint32_t) p.bk * 2u;
-    const uint32_t a_bytes = kBlockM * row_bytes, b_bytes = (uint32_t) p.block_n * row_bytes;
+    const uint32_t a_bytes = kBlockM * row_bytes, b_bytes = (uint32_t) (p.block_n / CG) * row_bytes;       // per CTA
     const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + (uint32_t) p.stages * stage_bytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -449,6 +499,8 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_conv_tc(const __grid_cons
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CG == 2 ? (int) cluster_ctarank() : 0;
+    const int cta = CG == 2 ? (int) (blockIdx.x >> 1) : (int) blockIdx.x, ncta = CG == 2 ? (int) (gridDim.x >> 1) : (int) gridDim.x;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -457,58 +509,64 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_conv_tc(const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * EG); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * EG * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int total_tiles = p.tiles_m * p.tiles_n;
+    const int total_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n;     // CG = 2: pair tiles
     const int kblocks = p.R * p.S * p.kchunks;
 
-    if constexpr (EG == 3) {
+    if (warp < 4) {
         // 16 warps are compiled for 128 registers; the TMA / MMA / alloc warpgroup needs ~40, so it hands its share to the three epilogue
         // warpgroups (4 x 32 x 40 + 12 x 32 x 152 = 63488 <= 65536): 12 epilogue warps run with the register budget of the 8-warp build.
-    }
-    if (warp < 4) {
         if constexpr (EG == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
-        // ===================================================== TMA producer
+        // ===================================================== TMA producer (one per CTA; in a pair both signal the leader's full barrier)
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
+            const uint32_t full_lead0 = CG == 2 ? mapa_u32(full_bar(0), 0) : full_bar(0);
+            for (int tile = cta; tile < total_tiles; tile += ncta) {
+                const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + rank;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);     // img >= N: zero-filled by TMA
                 const int oh0 = th * p.bh, ow0 = tw * p.bw, n0 = nt * p.block_n;
                 for (int r = 0; r < p.R; ++r)
                     for (int s = 0; s < p.S; ++s)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
                             const uint32_t a_dst = smem_base + (uint32_t) stage * stage_bytes, b_dst = a_dst + a_bytes;
-                            mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
-                            tma_load_4d(a_dst, &tmA, full_bar(stage), p.in_coff + (p.grouped ? n0 : kc * p.bk), ow0 * p.stride + s * p.dil - p.pad,
-                                        oh0 * p.stride + r * p.dil - p.pad, img);
-                            tma_load_2d(b_dst, &tmB, full_bar(stage), ((r * p.S + s) * p.kchunks + kc) * p.bk, n0);
+                            if (rank == 0) mbar_expect_tx(full_bar(stage), CG * (a_bytes + b_bytes));
+                            const uint32_t fb = full_lead0 + 8u * stage;
+                            tma_load_4d<CG>(a_dst, &tmA, fb, p.in_coff + (p.grouped ? n0 : kc * p.bk), ow0 * p.stride + s * p.dil - p.pad,
+                                            oh0 * p.stride + r * p.dil - p.pad, img);
+                            tma_load_2d<CG>(b_dst, &tmB, fb, ((r * p.S + s) * p.kchunks + kc) * p.bk, n0 + rank * (p.block_n / CG));
                             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                         }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================== MMA issuer
+    } else if (warp == 1 && rank == 0) {
+        // ===================================================== MMA issuer (the leader CTA of a pair)
         // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B fp16 or bf16, both K-major, N>>3 @17, M>>4 @24
         const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.block_n >> 3) << 17) | ((uint32_t) (kBlockM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.block_n >> 3) << 17) | ((uint32_t) ((kBlockM * CG) >> 4) << 24);
         int stage = 0, as = 0;
         uint32_t phase = 0, aphase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = cta; tile < total_tiles; tile += ncta) {
             mbar_wait(tempty_bar(as), aphase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t) as * 256u;
@@ -519,9 +577,9 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_conv_tc(const __grid_cons
                     const uint32_t a_addr = smem_base + (uint32_t) stage * stage_bytes, b_addr = a_addr + a_bytes;
                     const uint64_t adesc = make_desc(a_addr, row_bytes), bdesc = make_desc(b_addr, row_bytes);
                     for (int k = 0; k < p.bk / kUmmaK; ++k)   // advance 16 elements = 32 B = 2 descriptor units inside the swizzle atom
-                        umma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(empty_bar(stage));
-                    if (kb == kblocks - 1) umma_commit(tfull_bar(as));
+                        umma_f16<CG>(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit<CG>(empty_bar(stage));
+                    if (kb == kblocks - 1) umma_commit<CG>(tfull_bar(as));
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -532,14 +590,16 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_conv_tc(const __grid_cons
     } else {
         // ===================================================== epilogue (TMEM -> registers -> global), 4 * EG warps
         if constexpr (EG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-        if (p.is_bf16) epilogue_dispatch<__nv_bfloat16>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
-        else epilogue_dispatch<__half>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
+        if (p.is_bf16) epilogue_dispatch<__nv_bfloat16, CG>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
+        else epilogue_dispatch<__half, CG>(p, tmem_base, tfull_bar(0), tempty_bar(0), total_tiles, smem_base + p.stage_off, &tmC);
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();          // neither CTA leaves (or frees TMEM) while its peer may still signal it / read its shared memory
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
     }
 }
 
@@ -561,7 +621,12 @@ EncodeTiledFn encode_fn() {
 
 CUtensorMapSwizzle swizzle_of(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); }
 
+std::atomic<int> g_pair_mode{[] { const char* e = getenv("CSB_CTA_PAIR"); return e ? atoi(e) : 1; }()};
+
 }  // namespace
+
+// A/B switch of the CTA-pair path for tests and benchmarks (same values as the CSB_CTA_PAIR environment variable); returns the previous mode.
+extern "C" int csb_conv_set_pair_mode(int mode) { return g_pair_mode.exchange(mode); }
 
 static int conv_impl(const csb_conv_desc* d, const void* x, const void* w, const float* bias, const float* act_param, const void* residual, void* y,
                      float* y_f32, const float* ln_stats, const float* ln_colsum, float ln_eps, void* stream) {
@@ -620,6 +685,11 @@ static int conv_impl(const csb_conv_desc* d, const void* x, const void* w, const
     p.tiles_h = (p.H + p.bh - 1) / p.bh; p.tiles_w = (p.W + p.bw - 1) / p.bw; p.tiles_m = p.N * p.tiles_h * p.tiles_w;
     p.block_n = p.grouped ? 64 : (d->Cout >= 256 ? 256 : ((d->Cout + 15) / 16) * 16);
     p.tiles_n = (d->Cout + p.block_n - 1) / p.block_n;
+    // CTA pairs (tcgen05 cta_group::2, see k_conv_tc): for the wide-N layers, whose k-blocks are bound by the L2 -> shared-memory fabric.
+    // CSB_CTA_PAIR: 0 never, 1 (default) when block_n >= 128 and there are at least two m-tiles, 2 whenever the shape allows it.
+    const int pair_mode = g_pair_mode.load(std::memory_order_relaxed);
+    static const int eg = [] { const char* e = getenv("CSB_EPI_GROUPS"); return e && atoi(e) == 2 ? 2 : 3; }();      // 12 (default) or 8 epilogue warps
+    const int cg = (eg == 3 && pair_mode > 0 && !p.grouped && p.block_n % 32 == 0 && p.tiles_m >= 2 && (pair_mode == 2 || p.block_n >= 128)) ? 2 : 1;
     box[0] = (cuuint32_t) p.bk; box[1] = (cuuint32_t) (p.bw * d->stride); box[2] = (cuuint32_t) (p.bh * d->stride); box[3] = 1;
     estr[0] = 1; estr[1] = (cuuint32_t) d->stride; estr[2] = (cuuint32_t) d->stride; estr[3] = 1;
     const CUtensorMapDataType dt = d->dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -629,12 +699,12 @@ static int conv_impl(const csb_conv_desc* d, const void* x, const void* w, const
     if (r != CUDA_SUCCESS) return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_conv2d_nhwc", "cuTensorMapEncodeTiled(A) failed");
     const cuuint64_t ktot = (cuuint64_t) d->R * d->S * (p.grouped ? 64 : d->Cin);
     cuuint64_t wdim[2] = {ktot, (cuuint64_t) d->Cout}, wstr[1] = {ktot * esz};
-    cuuint32_t wbox[2] = {(cuuint32_t) p.bk, (cuuint32_t) p.block_n}, westr[2] = {1, 1};
+    cuuint32_t wbox[2] = {(cuuint32_t) p.bk, (cuuint32_t) (p.block_n / cg)}, westr[2] = {1, 1};      // a pair's CTAs load half of the weight tile each
     r = enc(&tmB, dt, 2, const_cast<void*>(w), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(p.bk),
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_conv2d_nhwc", "cuTensorMapEncodeTiled(B) failed");
 
-    const uint32_t row_bytes = p.bk * 2, stage_bytes = ((kBlockM + p.block_n) * row_bytes + 1023u) & ~1023u;
+    const uint32_t row_bytes = p.bk * 2, stage_bytes = ((kBlockM + p.block_n / cg) * row_bytes + 1023u) & ~1023u;
     const int kblocks = p.R * p.S * p.kchunks;
     int stages = (int) ((200u * 1024u) / stage_bytes);
     stages = stages > kMaxStages ? kMaxStages : stages;
@@ -661,18 +731,32 @@ static int conv_impl(const csb_conv_desc* d, const void* x, const void* w, const
                 store_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r == CUDA_SUCCESS) p.tma_store = store_mode == 1 ? 1 : 2;
     }
-    static std::once_flag attr_once;
-    std::call_once(attr_once, [] {
-        cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_conv_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    });
-    const int total = p.tiles_m * p.tiles_n;
-    const int grid = total < csb::num_sms() ? total : csb::num_sms();
+    // the opt-in to > 48 KiB of dynamic shared memory is per device: set it once per (device, kernel)
+    static unsigned char attr_done[64] = {};
+    if (csb::first_use_on_device(attr_done)) {
+        cudaFuncSetAttribute(k_conv_tc<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_conv_tc<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_conv_tc<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
     // 12 epilogue warps (EG = 3, registers re-balanced with setmaxnreg) by default: -1.1 ms on the detector's convs and -0.7 ms on LeReS' per 32
     // frames against the 8-warp build, which stays selectable (CSB_EPI_GROUPS=2) for A/B runs
-    static const int eg = [] { const char* e = getenv("CSB_EPI_GROUPS"); return e && atoi(e) == 2 ? 2 : 3; }();
-    if (eg == 3) k_conv_tc<3><<<grid, 512, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
-    else k_conv_tc<2><<<grid, 384, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
+    const int sms = csb::num_sms();
+    if (cg == 2) {
+        const int pairs = ((p.tiles_m + 1) / 2) * p.tiles_n;
+        const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned) grid); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t) stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_conv_tc<3, 2>, tmA, tmB, tmC, p);
+    } else {
+        const int total = p.tiles_m * p.tiles_n;
+        const int grid = total < sms ? total : sms;
+        if (eg == 3) k_conv_tc<3, 1><<<grid, 512, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
+        else k_conv_tc<2, 1><<<grid, 384, smem, (cudaStream_t) stream>>>(tmA, tmB, tmC, p);
+    }
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {           // detailed profile: one key per layer shape
         char label[160];
         snprintf(label, sizeof label, "k_conv_tc[%dx%dx%dx%d->%d k%dx%d s%d d%d g%d act%d res%d]", d->N, d->Hin, d->Win, d->Cin, d->Cout, d->R, d->S, d->stride,

@@ -421,8 +421,8 @@ extern "C" int csb_attention_bias_tc(const void* qkv, int B, int T, int heads, i
     p.B = B; p.T = T; p.heads = heads; p.Tp = Tp; p.nqb = (T + kBQ - 1) / kBQ; p.nkb = Tkp / kBK;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.bias = (const __half*) bias; p.out = (__half*) out;
-    static std::once_flag attr_once;
-    std::call_once(attr_once, [] { cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes); });
+    static unsigned char attr_done[64] = {};
+    if (csb::first_use_on_device(attr_done)) cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
     const long long grid = (long long) B * p.nqb * heads;
     k_attention_tc<<<(unsigned) grid, kThreadsAttn, kSmemBytes, st>>>(tmQKV, tmK, tmVT, tmBias, p);
     return csb::launched("k_attention_tc", st);

@@ -267,6 +267,11 @@ typedef struct csb_conv_desc {
 CSB_API int csb_conv2d_nhwc(const csb_conv_desc* desc, const void* x, const void* w, const float* bias, const float* act_param,
                     const void* residual, void* y, float* y_f32, void* stream);
 
+/* Tuning / A-B switch of the conv engine's CTA-pair path (tcgen05 cta_group::2: two SMs share one weight tile): 0 never, 1 (default) for the
+ * wide-N layers, 2 whenever the shape allows it.  Same values as the CSB_CTA_PAIR environment variable; returns the previous mode.  Results do not
+ * depend on the mode beyond fp32 accumulation order (identical: the k-order is unchanged). */
+CSB_API int csb_conv_set_pair_mode(int mode);
+
 /* LayerNorm folded into the 1x1 conv that consumes it (the ConvNeXt block: depthwise 7x7 -> LayerNorm -> Linear C->4C -> GELU, mmpretrain
  * ConvNeXtBlock).  csb_dwconv_stats_nhwc is csb_dwconv_nhwc (K = 7, no activation) that also writes, per pixel and
  * per 64-channel chunk, (sum, sum of squares) of its fp16 outputs: stats [N*H*W][C/64][2] fp32.  csb_conv2d_ln_nhwc then computes

@@ -129,3 +129,40 @@ def test_convnext_block_head_ln_folded(eng, N, H, W, C, mean_shift):
     y2 = eng.conv2d_nhwc(u2, eng.pack_conv_weight(w1[:, :, None, None]), b1, act='gelu').float()
     assert (y2 - ref).abs().max() <= tol
     assert ((y - ref) ** 2).mean().sqrt() <= 1.5 * ((y2 - ref) ** 2).mean().sqrt() + 1e-4          # folding does not cost accuracy
+
+
+PAIR_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad, act: shapes that take the CTA-pair path (tcgen05 cta_group::2) in mode 2
+    (2, 24, 40, 128, 256, 1, 1, 0, 'silu'),       # flat, 15 m-tiles: the last pair has a peer tile past the end
+    (1, 64, 64, 512, 2048, 1, 1, 0, 'gelu'),      # ConvNeXt fc1: 8 n-tiles, 32 m-tiles
+    (1, 32, 32, 2048, 512, 1, 1, 0, None),        # ConvNeXt fc2: 32 k-blocks
+    (2, 36, 28, 256, 256, 3, 1, 1, 'relu'),       # 3x3 with ragged spatial tiles, 2 images
+    (1, 33, 47, 64, 64, 3, 2, 1, 'relu'),         # stride 2, block_n 64 (pairs only in mode 2)
+    (3, 20, 20, 128, 96, 3, 1, 1, 'silu'),        # block_n 96: a 48-row weight half per CTA
+    (1, 16, 16, 1024, 4096, 1, 1, 0, 'gelu'),     # more n-tiles than m-tiles
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad,act", PAIR_CASES)
+def test_conv_cta_pair_matches_single_cta(eng, N, H, W, Cin, Cout, k, stride, pad, act):
+    """tcgen05 cta_group::2 (two SMs share one weight tile) against the single-CTA kernel: the k-order of the accumulation is the same, so
+    the results are bit-identical; both are also checked against PyTorch fp32."""
+    from cartoonsegmentation_b200._lib import lib
+    g = torch.Generator(device='cuda').manual_seed(H * 77 + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, device='cuda', generator=g).half()
+    w = (torch.randn(Cout, Cin, k, k, device='cuda', generator=g) / (Cin * k * k) ** 0.5)
+    b = torch.randn(Cout, device='cuda', generator=g) * 0.1
+    res = torch.randn(N, (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1, Cout, device='cuda', generator=g).half()
+    wp = eng.pack_conv_weight(w)
+    outs = {}
+    prev = lib().csb_conv_set_pair_mode(0)
+    try:
+        for mode in (0, 2):
+            lib().csb_conv_set_pair_mode(mode)
+            outs[mode] = eng.conv2d_nhwc(x, wp, b, stride=stride, pad=pad, act=act, residual=res, res_mode=2).clone()
+    finally:
+        lib().csb_conv_set_pair_mode(prev)
+    torch.cuda.synchronize()
+    r = ref_conv(x, w, b, stride, pad, 1, act, residual=res, res_mode=2)
+    assert (outs[0].float() - r).abs().max().item() <= 2e-3 * r.abs().max().item() + 1e-3
+    assert torch.equal(outs[0], outs[2]), f"pair path differs: max {(outs[0].float() - outs[2].float()).abs().max().item()}"
