@@ -57,6 +57,10 @@ inline int cuda_ok(cudaError_t e, const char* what) {
         if (_st != CSB_OK) return _st; \
     } while (0)
 
+// tc_halo.cu: launch of the halo-tile conv kernel (also reached from csb_conv2d_nhwc for the dense shapes it suits)
+int conv_halo_launch(const csb_conv_desc* d, const void* x, const void* w, const float* bias, const float* act_param, const void* residual, void* y, float* y_f32,
+                     float* stats, void* stream);
+
 // SM count of the CURRENT device (cached per device: one process may drive several GPUs, e.g. depth_est_device != device)
 inline int num_sms() {
     static int cache[64] = {};

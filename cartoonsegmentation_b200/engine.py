@@ -43,6 +43,56 @@ def pack_grouped_weight(w, groups, dtype=torch.float16):
     return out.contiguous().to(dtype)
 
 
+def pack_grouped_weight_compact(w, groups, dtype=torch.float16):
+    """torch grouped conv weight [Cout, Cin/groups, R, S] (Cin == Cout) -> [Cout, R, S, gk], gk = max(16, Cin/groups): per output channel the
+    gk input channels of the gk-aligned block that holds its group (zeros outside the group when a block holds several groups) -- the compact
+    block-diagonal form of csb_conv2d_halo_nhwc(groups > 1)."""
+    Cout, cpg, R, S = w.shape
+    assert Cout // groups == cpg and (cpg >= 16 and 64 % cpg == 0 or 16 % cpg == 0)
+    gk = max(16, cpg)
+    if cpg >= 16:
+        return w.permute(0, 2, 3, 1).contiguous().to(dtype)
+    out = torch.zeros((Cout, R * S, gk), device=w.device, dtype=torch.float32)
+    co = torch.arange(Cout, device=w.device)
+    base = ((co // cpg) * cpg) % gk                                           # first input channel of the group inside its 16-channel block
+    idx = base[:, None] + torch.arange(cpg, device=w.device)[None]          # [Cout, cpg]
+    out.scatter_(2, idx[:, None, :].expand(Cout, R * S, cpg), w.permute(0, 2, 3, 1).reshape(Cout, R * S, cpg).float())
+    return out.view(Cout, R, S, gk).contiguous().to(dtype)
+
+
+def pack_dw_weight_compact(w, dtype=torch.float16):
+    """depthwise weight [K, K, C] (the layout of dwconv_nhwc) -> compact block-diagonal [C, K, K, 16] for csb_conv2d_halo_nhwc(groups = C)."""
+    K, _, Cc = w.shape
+    return pack_grouped_weight_compact(w.permute(2, 0, 1)[:, None].contiguous(), Cc, dtype)
+
+
+def halo_supported(N, H, W, Cin, Cx, in_coff, Cout, R, S, stride, pad, dil, groups=1):
+    d = ConvDesc(N, H, W, Cin, Cx, in_coff, Cout, R, S, stride, pad, dil, Cout, 0, 0, 0, 0, 0, 0, groups)
+    return bool(lib().csb_conv_halo_supported(C.byref(d)))
+
+
+def conv2d_halo_nhwc(x, w, bias=None, pad=0, dil=1, act=None, act_param=None, residual=None, res_mode=0, out=None, out_coff=0, in_coff=0,
+                     res_coff=0, out_f32=False, groups=1, stats=False):
+    """Stride-1 RxS conv on the halo-tile kernel (csrc/tc_halo.cu).  groups <= 1: w packed [Cout,R,S,Cin]; groups > 1: w from
+    pack_grouped_weight_compact / pack_dw_weight_compact ([Cout,R,S,gk]), Cin == Cout.  stats=True (grouped): also returns the per-pixel,
+    per-64-channel (sum, sum of squares) of the rounded outputs for conv2d_ln_nhwc."""
+    N, H, W, Cx = x.shape
+    Cout, R, S, Kw = w.shape
+    Cin = Cout if groups > 1 else Kw
+    Ho, Wo = out_hw(H, W, R, S, 1, pad, dil)
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), device=x.device, dtype=torch.float32 if out_f32 else x.dtype)
+    if residual is not None and res_mode == 0:
+        res_mode = 1
+    d = ConvDesc(N, H, W, Cin, Cx, in_coff, Cout, R, S, 1, pad, dil, out.shape[3], out_coff, ACT[act], res_mode,
+                 residual.shape[3] if residual is not None else 0, res_coff, 1 if x.dtype == torch.bfloat16 else 0, groups)
+    st = torch.empty((N * Ho * Wo, Cout // 64, 2), device=x.device, dtype=torch.float32) if stats else None
+    is_f32 = out.dtype == torch.float32
+    check(lib().csb_conv2d_halo_nhwc(C.byref(d), ptr(x), ptr(w), ptr(bias), ptr(act_param), ptr(residual), None if is_f32 else ptr(out),
+                                     ptr(out) if is_f32 else None, ptr(st), stream()), "csb_conv2d_halo_nhwc")
+    return (out, st) if stats else out
+
+
 def conv2d_nhwc(x, w, bias=None, stride=1, pad=0, dil=1, act=None, act_param=None, residual=None, res_mode=0, out=None, out_coff=0,
                 in_coff=0, cin=None, res_coff=0, out_f32=False, groups=1):
     """x: [N,H,W,Cx] NHWC fp16/bf16 (channels in_coff..in_coff+cin used); w: packed [Cout,R,S,Cin]; -> y [N,Ho,Wo,Cout] (or `out`

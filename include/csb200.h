@@ -272,6 +272,23 @@ CSB_API int csb_conv2d_nhwc(const csb_conv_desc* desc, const void* x, const void
  * depend on the mode beyond fp32 accumulation order (identical: the k-order is unchanged). */
 CSB_API int csb_conv_set_pair_mode(int mode);
 
+/* Halo-tile path of the conv engine (csrc/tc_halo.cu) for stride-1 RxS convolutions: ONE activation halo box per 64-channel chunk feeds all R*S
+ * taps through shifted tcgen05 shared-memory descriptors (the per-tap path moves R*S x the activation bytes from L2 to shared memory).
+ *   desc->groups <= 1: w = [Cout][R][S][Cin] as for csb_conv2d_nhwc (which routes its eligible shapes with Cout <= 128 here by itself);
+ *   desc->groups  > 1: Cin == Cout, w COMPACT = [Cout][R][S][gk], gk = max(16, Cin / groups): per output channel the gk input channels of the
+ *                      gk-aligned block that holds its group (zeros outside the group when Cin / groups < 16).  groups == Cin is a depthwise conv
+ *                      (ConvNeXt 7x7, mmpretrain ConvNeXtBlock; CSPNeXt 5x5), ResNeXt-101 32x8d gives gk = 16 / 16 / 32 / 64
+ *                      (depth_modules/leres/leres/Resnext_torch.py:70-118).
+ * act: none / relu / silu / prelu.  stats (optional, grouped only): [N*H*W][Cout/64][2] fp32 (sum, sum of squares) of the rounded outputs per
+ * pixel and 64-channel slice -- the input csb_conv2d_ln_nhwc expects after a depthwise conv.
+ * csb_conv_halo_supported: 1 if the shape can take this path (stride 1, R, S >= 2, (S-1) * dil <= 8, Cin % 64 == 0, dense Cout <= 256).
+ * csb_conv_set_halo_mode: 0 off, 1 on (default; CSB_CONV_HALO), 2 on with a non-zero descriptor base offset (diagnostic: the B200 applies the
+ * swizzle to absolute shared-memory address bits, mode 2 gives wrong results and exists to document that); returns the previous mode. */
+CSB_API int csb_conv_halo_supported(const csb_conv_desc* desc);
+CSB_API int csb_conv_set_halo_mode(int mode);
+CSB_API int csb_conv2d_halo_nhwc(const csb_conv_desc* desc, const void* x, const void* w, const float* bias, const float* act_param, const void* residual,
+                         void* y, float* y_f32, float* stats, void* stream);
+
 /* LayerNorm folded into the 1x1 conv that consumes it (the ConvNeXt block: depthwise 7x7 -> LayerNorm -> Linear C->4C -> GELU, mmpretrain
  * ConvNeXtBlock).  csb_dwconv_stats_nhwc is csb_dwconv_nhwc (K = 7, no activation) that also writes, per pixel and
  * per 64-channel chunk, (sum, sum of squares) of its fp16 outputs: stats [N*H*W][C/64][2] fp32.  csb_conv2d_ln_nhwc then computes
