@@ -485,6 +485,7 @@ class KenBurnsPipeline:
             cfg['tenInpaDepth'] = cfg['tenRawDepth'].view(1, 1, -1)
             cfg['tenInpaPoints'] = cfg['tenRawPoints'].view(1, 3, -1)
             cfg._render_data = c['data']                       # [1,4,N] = image ++ depth, the frame loop's payload (:1036)
+            cfg._render_key = (cfg.inpainted_img.data_ptr(), cfg['tenInpaDepth'].data_ptr())     # the tensors the payload was built from
             cfg.instances = instances
             cfg.original_img_nparray = img
             return cfg
@@ -653,15 +654,18 @@ class KenBurnsPipeline:
                     self.inpaint(1.1 * sh, None, objCommon, verbose)
             pts = objCommon['tenInpaPoints']
             N = pts.shape[2]
+            # the cached payload is only valid for the very tensors it was built from (a caller may have replaced inpainted_img / tenInpaDepth by
+            # same-sized ones, e.g. a repainted image): identity check, else rebuild as the reference does every frame (:1036)
             data = getattr(objCommon, '_render_data', None)
-            if data is None or data.shape[2] != N:
+            key = (objCommon.inpainted_img.data_ptr(), objCommon['tenInpaDepth'].data_ptr())
+            if data is None or data.shape[2] != N or getattr(objCommon, '_render_key', None) != key:
                 data = torch.cat([objCommon.inpainted_img, objCommon['tenInpaDepth']], 1).view(1, 4, -1).contiguous()       # :1036
             pw, ph = max(oF['intCropWidth'], oT['intCropWidth']), max(oF['intCropHeight'], oT['intCropHeight'])
             steps = objSettings['fltSteps']
             if self._frame_scratch is None or self._frame_scratch.key[2:4] != (H, W):
                 self._frame_scratch = FrameScratch(H, W, pts.device)
             out_dev = torch.empty((len(steps), H, W, 3), device=pts.device, dtype=torch.uint8)
-            out_host = torch.empty((len(steps), H, W, 3), dtype=torch.uint8).pin_memory()
+            out_host = torch.empty((len(steps), H, W, 3), dtype=torch.uint8, pin_memory=True)     # straight from torch's pinned-block cache (no pageable staging copy)
             bokeh = None
             if objCommon.depth_field:                                              # :1042-1067, all on the device (utils/effects.py)
                 ins = objCommon.instances

@@ -26,6 +26,11 @@ DEPTHS, DIMS = (3, 3, 27, 3), (128, 256, 512, 1024)
 STRIDES = (8, 16, 32)
 NUM_GEN_PARAMS = 169
 import os as _os
+# Depthwise convs as diagonal-block MMAs on the halo-tile kernel (csrc/tc_halo.cu).  Measured on B200 (tools/halo_bench.py): the neck's 5x5 + SiLU
+# gains 1.3x over the FFMA kernel (491 vs 377 G outputs/s), the backbone's 7x7 loses (246 vs 358: 49 taps x 4 MMAs of N = 16 per 64-channel
+# tile are bound by MMA issue and the re-read of the A tile per tap), so the 7x7 stays on k_dwconv_halo unless CSB_DW_TC=1.
+DW_TC = _os.environ.get("CSB_DW_TC", "0") != "0"
+DW5_TC = _os.environ.get("CSB_DW5_TC", "1") != "0"
 FOLD_LN = _os.environ.get("CSB_FOLD_LN", "1") != "0"        # ConvNeXt block: LayerNorm applied in the fc1 GEMM epilogue (engine.fold_layernorm)
 
 
@@ -204,6 +209,8 @@ class _CSP:
             c1 = _Conv(*_fold_bn(sd, f"{name}.blocks.{b}.conv1", eps), dev, pad=1, act='silu')
             wd, bd = _fold_bn(sd, f"{name}.blocks.{b}.conv2.depthwise_conv", eps)
             dw = (wd[:, 0].permute(1, 2, 0).contiguous().to(dev), bd.contiguous().to(dev))            # [K,K,C] fp32
+            if DW5_TC and dw[0].shape[2] % 64 == 0:
+                dw = dw + (E.pack_dw_weight_compact(dw[0]),)
             pw = _Conv(*_fold_bn(sd, f"{name}.blocks.{b}.conv2.pointwise_conv", eps), dev, act='silu')
             self.blocks.append((c1, dw, pw))
             b += 1
@@ -212,7 +219,10 @@ class _CSP:
         y = self.ms(x)                                        # [.., 2*mid] = [main | short]
         for c1, dw, pw in self.blocks:                        # CSPNeXtBlock
             a = E.conv2d_nhwc(y, c1.w, c1.b, pad=1, act='silu', in_coff=0)
-            d = E.dwconv_nhwc(a, dw[0], dw[1], act='silu')
+            if len(dw) == 3:
+                d = E.conv2d_halo_nhwc(a, dw[2], dw[1], pad=dw[0].shape[0] // 2, act='silu', groups=a.shape[3])
+            else:
+                d = E.dwconv_nhwc(a, dw[0], dw[1], act='silu')
             if self.add_identity:                             # out + identity: the block input is the main half itself (read, then overwritten per element)
                 E.conv2d_nhwc(d, pw.w, pw.b, act='silu', out=y, out_coff=0, residual=y, res_mode=2, res_coff=0)
             else:
@@ -294,7 +304,7 @@ class RTMDetIns:
                 dw = f32(sd[f"{p}.depthwise_conv.weight"][:, 0].permute(1, 2, 0))                  # [7,7,C]
                 # LayerNorm folded into fc1 (csb_conv2d_ln_nhwc): W' = W diag(gamma), b' = b + W beta, column sums of the rounded W'
                 wl, bl, cs = E.fold_layernorm(sd[f"{p}.pointwise_conv1.weight"], sd[f"{p}.pointwise_conv1.bias"], sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"])
-                st.append(dict(dw=dw, fc1_ln=(wl.to(dev), bl.to(dev), cs.to(dev)), dwb=f32(sd[f"{p}.depthwise_conv.bias"]), ln=(f32(sd[f"{p}.norm.weight"]), f32(sd[f"{p}.norm.bias"])),
+                st.append(dict(dw=dw, dw_tc=E.pack_dw_weight_compact(dw), fc1_ln=(wl.to(dev), bl.to(dev), cs.to(dev)), dwb=f32(sd[f"{p}.depthwise_conv.bias"]), ln=(f32(sd[f"{p}.norm.weight"]), f32(sd[f"{p}.norm.bias"])),
                                fc1=_Conv(sd[f"{p}.pointwise_conv1.weight"][:, :, None, None], sd[f"{p}.pointwise_conv1.bias"], dev, act='gelu'),
                                # layer scale folded: gamma * (W2 h + b2)
                                fc2=_Conv(sd[f"{p}.pointwise_conv2.weight"][:, :, None, None] * gamma.view(-1, 1, 1, 1), sd[f"{p}.pointwise_conv2.bias"] * gamma, dev)))
@@ -334,7 +344,10 @@ class RTMDetIns:
                 t = conv(E.layernorm_nhwc(t, *ln))
             for blk in self.blocks[i]:
                 if FOLD_LN and t.shape[3] % 64 == 0:
-                    u, stats = E.dwconv_stats_nhwc(t, blk['dw'], blk['dwb'])
+                    if DW_TC:       # tensor-core depthwise (fp16 taps, fp32 accumulate) emitting the LayerNorm partial sums
+                        u, stats = E.conv2d_halo_nhwc(t, blk['dw_tc'], blk['dwb'], pad=3, groups=t.shape[3], stats=True)
+                    else:
+                        u, stats = E.dwconv_stats_nhwc(t, blk['dw'], blk['dwb'])
                     h = E.conv2d_ln_nhwc(u, stats, *blk['fc1_ln'], eps=1e-6, act='gelu')
                 else:
                     u = E.dwconv_nhwc(t, blk['dw'], blk['dwb'], ln=blk['ln'], eps=1e-6)

@@ -47,6 +47,7 @@ struct HaloParams {
     uint32_t b_row_bytes, b_tile_bytes;
     int b_slots, b_resident;
     int a_stages;
+    int n_iss;                   // MMA-issuing warps (resident weights only)
     uint32_t halo_bytes;
     int acc_stages, acc_stride;
     int base_off;                // 0 (correct on sm_100a): descriptor base offset 0; 1: (start >> 7) & 7 (diagnostic mode, see the header comment)
@@ -70,31 +71,42 @@ __device__ __forceinline__ uint64_t make_desc_ex(uint32_t saddr, uint32_t sbo_by
            (layout << 61);
 }
 
-template <class T>
-__device__ __forceinline__ void halo_epilogue(const HaloParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int t0, int t1) {
+template <int ACT>
+__device__ __forceinline__ float halo_act(float t, float slope) {
+    if constexpr (ACT == CSB_ACT_RELU) return fmaxf(t, 0.f);
+    else if constexpr (ACT == CSB_ACT_SILU) return __fdividef(t, 1.0f + __expf(-t));
+    else if constexpr (ACT == CSB_ACT_PRELU) return t > 0.f ? t : t * slope;
+    else return t;
+}
+
+// Epilogue of the halo kernel.  The layers on this path are thin (<= 128 output channels, often 9..36 MMAs per tile), so the conversion of a
+// tile must be as cheap as the MMAs that produced it: activation and residual mode are template parameters, bias / residual are 16 B loads,
+// a full 32-column chunk is straight-line code (the tail path handles Cout % 32 != 0, fp32 outputs and unaligned slices).
+template <class T, int ACT>
+__device__ __forceinline__ void halo_epilogue(const HaloParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int nt, int m0, int m1) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, grp = (warp - 4) >> 2;
-    const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && !p.out_f32;
+    const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && !p.out_f32 &&
+                         (!p.bias || ((uintptr_t) p.bias % 16 == 0));
     int as = 0, rot = grp;
     uint32_t aphase = 0;
-    for (int tile = t0; tile < t1; ++tile) {
+    for (int mt = m0; mt < m1; ++mt) {
         const int turn = rot;                               // see tc_conv.cu: the groups' starting chunk rotates from tile to tile
         if (++rot == kEpiGroups) rot = 0;
-        const int nt = tile / p.tiles_m, mt = tile % p.tiles_m;
         const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
         const int m = q * 32 + lane;
         const int oh = th * kTileH + (m >> 3), ow = tw * kTileW + (m & 7);
         const bool row_ok = oh < p.H && ow < p.W;
         const size_t pix = ((size_t) img * p.H + (oh < p.H ? oh : p.H - 1)) * p.W + (ow < p.W ? ow : p.W - 1);
-        mbar_wait(tfull0 + 8u * as, aphase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * p.acc_stride);
         const int ncols = min(p.block_n, p.Cout - nt * p.block_n);
         const int nchunks = (ncols + 31) / 32;
         // statistics mode: ONE group converts the whole tile (it owns complete rows of the 64-channel slice); otherwise chunks go round-robin
         const int first = p.stats ? (turn == 0 ? 0 : nchunks) : turn, step = p.stats ? 1 : kEpiGroups;
         int last = -1;
         for (int ch = first; ch < nchunks; ch += step) last = ch;
+        mbar_wait(tfull0 + 8u * as, aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (as * p.acc_stride);
         if (last < 0) {
             tc_fence_before();
             __syncwarp();
@@ -112,16 +124,19 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, uint32_t tmem
                 if (lane == 0) mbar_arrive(tempty0 + 8u * as);
             }
             if (!row_ok) continue;
-            float y[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(acc[j]);
-            const bool vec = aligned && (nv % 8 == 0);
-            if (vec) {
+            if (aligned && nv % 8 == 0) {
                 const T* res = p.res_mode ? reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0 : nullptr;
                 T* o = reinterpret_cast<T*>(p.out) + pix * p.out_ld + p.out_coff + n0;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     if (g * 8 >= nv) break;
+                    float y[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(acc[g * 8 + e]);
+                    if (p.bias) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * g), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * g + 1);
+                        y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w; y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
+                    }
                     float r[8];
                     if (p.res_mode) {
                         const uint4 u = *reinterpret_cast<const uint4*>(res + g * 8);
@@ -130,30 +145,39 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, uint32_t tmem
                         f = unpack2<T>(u.y); r[2] = f.x; r[3] = f.y;
                         f = unpack2<T>(u.z); r[4] = f.x; r[5] = f.y;
                         f = unpack2<T>(u.w); r[6] = f.x; r[7] = f.y;
-                    }
-                    uint32_t pk[4];
+                        if (p.res_mode == 1) {
 #pragma unroll
-                    for (int e = 0; e < 8; e += 2) {
-                        float v[2];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int c = n0 + g * 8 + e + h;
-                            float t = y[g * 8 + e + h] + (p.bias ? __ldg(p.bias + c) : 0.f);
-                            if (p.res_mode == 1) t += r[e + h];
-                            if (p.act == CSB_ACT_RELU) t = fmaxf(t, 0.f);
-                            else if (p.act == CSB_ACT_SILU) t = __fdividef(t, 1.0f + __expf(-t));
-                            else if (p.act == CSB_ACT_PRELU) t = t > 0.f ? t : t * (p.act_param ? __ldg(p.act_param + c) : 0.25f);
-                            if (p.res_mode == 2) t += r[e + h];
-                            v[h] = t;
-                        }
-                        pk[e >> 1] = pack2<T>(v[0], v[1]);
-                        if (p.stats) {                      // statistics of the ROUNDED values, i.e. of what the consumer will read
-                            const float2 f = unpack2<T>(pk[e >> 1]);
-                            s1 += f.x + f.y;
-                            s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+                            for (int e = 0; e < 8; ++e) y[e] += r[e];
                         }
                     }
-                    *reinterpret_cast<uint4*>(o + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if constexpr (ACT == CSB_ACT_PRELU) {
+                        float sl[8];
+                        if (p.act_param) {
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.act_param + n0) + 2 * g), a1 = __ldg(reinterpret_cast<const float4*>(p.act_param + n0) + 2 * g + 1);
+                            sl[0] = a0.x; sl[1] = a0.y; sl[2] = a0.z; sl[3] = a0.w; sl[4] = a1.x; sl[5] = a1.y; sl[6] = a1.z; sl[7] = a1.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) sl[e] = 0.25f;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) y[e] = halo_act<ACT>(y[e], sl[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) y[e] = halo_act<ACT>(y[e], 0.f);
+                    }
+                    if (p.res_mode == 2) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) y[e] += r[e];
+                    }
+                    const uint4 pk = make_uint4(pack2<T>(y[0], y[1]), pack2<T>(y[2], y[3]), pack2<T>(y[4], y[5]), pack2<T>(y[6], y[7]));
+                    if (p.stats) {                          // statistics of the ROUNDED values, i.e. of what the consumer will read
+                        float2 f;
+                        f = unpack2<T>(pk.x); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+                        f = unpack2<T>(pk.y); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+                        f = unpack2<T>(pk.z); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+                        f = unpack2<T>(pk.w); s1 += f.x + f.y; s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, s2));
+                    }
+                    *reinterpret_cast<uint4*>(o + g * 8) = pk;
                 }
             } else {
                 const T* res = p.res_mode ? reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0 : nullptr;
@@ -161,11 +185,9 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, uint32_t tmem
                 for (int j = 0; j < 32; ++j) {
                     if (j >= nv) break;
                     const int c = n0 + j;
-                    float t = y[j] + (p.bias ? __ldg(p.bias + c) : 0.f);
+                    float t = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
                     if (p.res_mode == 1) t += to_f<T>(res[j]);
-                    if (p.act == CSB_ACT_RELU) t = fmaxf(t, 0.f);
-                    else if (p.act == CSB_ACT_SILU) t = __fdividef(t, 1.0f + __expf(-t));
-                    else if (p.act == CSB_ACT_PRELU) t = t > 0.f ? t : t * (p.act_param ? __ldg(p.act_param + c) : 0.25f);
+                    t = halo_act<ACT>(t, ACT == CSB_ACT_PRELU && p.act_param ? __ldg(p.act_param + c) : 0.25f);
                     if (p.res_mode == 2) t += to_f<T>(res[j]);
                     if (p.out_f32) p.out_f32[pix * p.out_ld + p.out_coff + c] = t;
                     else {
@@ -179,6 +201,90 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, uint32_t tmem
         if (p.stats && last >= 0 && row_ok) reinterpret_cast<float2*>(p.stats)[pix * p.stats_nchunk + nt] = make_float2(s1, s2);
         if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
     }
+}
+
+template <class T>
+__device__ __forceinline__ void halo_epilogue_dispatch(const HaloParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int nt, int m0, int m1) {
+    switch (p.act) {
+        case CSB_ACT_RELU: halo_epilogue<T, CSB_ACT_RELU>(p, tmem_base, tfull0, tempty0, nt, m0, m1); break;
+        case CSB_ACT_SILU: halo_epilogue<T, CSB_ACT_SILU>(p, tmem_base, tfull0, tempty0, nt, m0, m1); break;
+        case CSB_ACT_PRELU: halo_epilogue<T, CSB_ACT_PRELU>(p, tmem_base, tfull0, tempty0, nt, m0, m1); break;
+        default: halo_epilogue<T, CSB_ACT_NONE>(p, tmem_base, tfull0, tempty0, nt, m0, m1); break;
+    }
+}
+
+// (The issuers' barrier waits are keyed by index parity; the host limits n_iss so that they stay unambiguous, see conv_halo_launch.)
+// MMA issue loop.  With N <= 128 an MMA occupies the tensor pipe for only 8..64 cycles, so the ISSUE rate is the critical path of this kernel
+// (measured: ~350 cycles per tap for one issuing warp).  Two measures:
+//   * the loop is specialised (RESIDENT, NSUB x KSTEPS) and advances descriptor start addresses by additions -- no divisions, no table loads;
+//   * when the weights are resident, `n_iss` (up to 3) warps issue for DIFFERENT tiles (tile i -> warp i % n_iss, accumulator stage i % 4): their
+//     MMA series are independent (distinct TMEM columns), the shared-memory operands are read-only, and the ring slots of the halos are owned by
+//     one tile at a time, so no ordering between the issuers is needed.
+// NSUB x KSTEPS MMAs per tap: (1, 4) dense, N = block_n, K = 64; (2, 2) / (4, 1) grouped with 32 / 16-channel diagonal blocks.
+// a_stages and acc_stages are powers of two: slot = index & (stages - 1), phase = (index >> log2 stages) & 1.
+template <int NSUB, int KSTEPS, bool RESIDENT>
+__device__ __forceinline__ void mma_role(const HaloParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t b_base, uint32_t bar_base, int ntiles, int idx, int n_iss) {
+    const bool leader = elect_one();
+    const uint32_t afull0 = bar_base, aempty0 = bar_base + 8u * kMaxA, bfull0 = bar_base + 8u * (2 * kMaxA), bempty0 = bar_base + 8u * (2 * kMaxA + kMaxB);
+    const uint32_t tfull0 = bar_base + 8u * (2 * kMaxA + 2 * kMaxB), tempty0 = tfull0 + 8u * kMaxAcc;
+    const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.n_mma >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+    const uint64_t b_layout = p.b_row_bytes == 128 ? 2ull : (p.b_row_bytes == 64 ? 4ull : 6ull);
+    // descriptors with a zero start address: the per-MMA start (16 B units, < 2^14) is added into the low word
+    const uint64_t a_hi = make_desc_ex(0u, kSbo, 0u, 2ull), b_hi = make_desc_ex(0u, 8u * p.b_row_bytes, 0u, b_layout);
+    const uint32_t a_lo0 = (a_base & 0x3ffffu) >> 4, b_lo0 = (b_base & 0x3ffffu) >> 4;
+    const uint32_t a_step = p.halo_bytes >> 4, b_step = p.b_tile_bytes >> 4;
+    const uint32_t q_rows = ((uint32_t) p.gk * p.b_row_bytes) >> 4;      // start-address step between the diagonal blocks of a weight tile
+    const uint32_t col_step = ((uint32_t) p.dil * kRowB) >> 4;           // next tap in the row: dil pixels
+    const uint32_t row_step = ((uint32_t) (p.dil * kPitch) * kRowB >> 4) - (uint32_t) (p.S - 1) * col_step;   // first tap of the next filter row
+    const int taps = p.taps, S = p.S, kchunks = p.kchunks;
+    const int a_mask = p.a_stages - 1, a_log = p.a_stages == 4 ? 2 : 1, t_mask = p.acc_stages - 1, t_log = p.acc_stages == 4 ? 2 : 1;
+    int b_slot = 0;
+    uint32_t b_ph = 0;
+    bool wait_b = true;                                             // resident weights: awaited once, at the issuer's first tile
+    for (int i = idx; i < ntiles; i += n_iss) {
+        const int as = i & t_mask;
+        mbar_wait(tempty0 + 8u * as, (((uint32_t) i >> t_log) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t) (as * p.acc_stride);
+        uint32_t first = 0u;                                        // accumulate flag: 0 for the first MMA series of the tile
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int g = i * kchunks + kc, a_slot = g & a_mask;
+            mbar_wait(afull0 + 8u * a_slot, ((uint32_t) g >> a_log) & 1u);
+            tc_fence_after();
+            uint64_t ad = a_hi | (uint64_t) (a_lo0 + (uint32_t) a_slot * a_step);
+            uint32_t slot = RESIDENT ? (uint32_t) kc : (uint32_t) b_slot;
+            uint64_t bd = b_hi | (uint64_t) (b_lo0 + slot * b_step);
+            int sx = 0;
+            for (int tap = 0; tap < taps; ++tap) {
+                if (!RESIDENT || wait_b) { mbar_wait(bfull0 + 8u * slot, RESIDENT ? 0u : b_ph); tc_fence_after(); }
+                if (leader) {
+#pragma unroll
+                    for (int q = 0; q < NSUB; ++q)
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; ++k)
+                            umma_f16<1>(tmem_d + (uint32_t) (q * (64 / NSUB)), ad + (uint64_t) (2 * (q * KSTEPS + k)), bd + (uint64_t) (q * q_rows + 2 * k), idesc,
+                                        k == 0 ? first : 1u);
+                    if (!RESIDENT) umma_commit<1>(bempty0 + 8u * slot);
+                }
+                first = 1u;
+                if (++sx == S) { sx = 0; ad += row_step; } else ad += col_step;
+                if (RESIDENT) { slot += (uint32_t) kchunks; bd += (uint64_t) kchunks * b_step; }
+                else if (++b_slot == p.b_slots) { b_slot = 0; b_ph ^= 1u; slot = 0u; bd = b_hi | (uint64_t) b_lo0; }
+                else { ++slot; bd += b_step; }
+            }
+            if (leader) umma_commit<1>(aempty0 + 8u * a_slot);
+        }
+        wait_b = false;
+        if (leader) umma_commit<1>(tfull0 + 8u * as);
+        __syncwarp();
+    }
+}
+
+template <int NSUB, int KSTEPS>
+__device__ __forceinline__ void mma_dispatch(const HaloParams& p, uint32_t tmem_base, uint32_t a_base, uint32_t b_base, uint32_t bar_base, int ntiles, int idx, int n_iss) {
+    if (p.b_resident) mma_role<NSUB, KSTEPS, true>(p, tmem_base, a_base, b_base, bar_base, ntiles, idx, n_iss);
+    else mma_role<NSUB, KSTEPS, false>(p, tmem_base, a_base, b_base, bar_base, ntiles, idx, n_iss);
 }
 
 __global__ void __launch_bounds__(128 * (kEpiGroups + 1), 1) k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -216,113 +322,61 @@ __global__ void __launch_bounds__(128 * (kEpiGroups + 1), 1) k_conv_halo(const _
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    // contiguous tile range of this CTA in n-major order (tile = nt * tiles_m + mt): a CTA changes its weight set at most once or twice
-    const long long total = (long long) p.tiles_m * p.tiles_n;
-    const int t0 = (int) (total * blockIdx.x / gridDim.x), t1 = (int) (total * (blockIdx.x + 1) / gridDim.x);
+    // every CTA works on ONE n-tile (grid = tiles_n * ctas_per_n): its weight set is loaded once; the m-tiles of the n-tile are split evenly
+    const int ctas_per_n = (int) gridDim.x / p.tiles_n, nt = (int) blockIdx.x % p.tiles_n, part = (int) blockIdx.x / p.tiles_n;
+    const int m0 = (int) ((long long) p.tiles_m * part / ctas_per_n), m1 = (int) ((long long) p.tiles_m * (part + 1) / ctas_per_n);
+    const int ntiles = m1 - m0;
+    const int n_iss = p.n_iss;                                   // issuing warps (1, 2, 3): see mma_role
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 0) {
-            // ===================================================== TMA producer
+            // ===================================================== TMA producer (all ring positions are counters with wrap: no divisions)
             if (elect_one()) {
-                const long long nchunk = (long long) (t1 - t0) * p.kchunks;
-                auto issue_a = [&](long long g) {
-                    const int tile = t0 + (int) (g / p.kchunks), kc = (int) (g % p.kchunks);
-                    const int nt = tile / p.tiles_m, mt = tile % p.tiles_m;
-                    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, img = mt / (p.tiles_w * p.tiles_h);
-                    const int slot = (int) (g % p.a_stages);
-                    const uint32_t ph = (uint32_t) ((g / p.a_stages) & 1);
-                    mbar_wait(aempty(slot), ph ^ 1u);
-                    mbar_expect_tx(afull(slot), p.halo_bytes);
-                    tma_load_4d<1>(a_base + (uint32_t) slot * p.halo_bytes, &tmA, afull(slot), p.in_coff + (p.grouped ? nt * 64 : kc * 64),
-                                   tw * kTileW - p.pad, th * kTileH - p.pad, img);
-                };
-                if (nchunk > 0) issue_a(0);
-                long long bcount = 0;
-                int run = -1, prev_nt = -1, run_tile = -1;
-                for (long long g = 0; g < nchunk; ++g) {
-                    if (g + 1 < nchunk) issue_a(g + 1);             // the next halo is in flight while this chunk's weight tiles are issued
-                    const int tile = t0 + (int) (g / p.kchunks), kc = (int) (g % p.kchunks);
-                    const int nt = tile / p.tiles_m, n0 = nt * p.block_n;
-                    if (p.b_resident) {
-                        if (kc == 0 && nt != prev_nt) { ++run; prev_nt = nt; run_tile = tile; }
-                        if (tile != run_tile) continue;            // this weight set is already resident
+                const int n0 = nt * p.block_n;
+                if (p.b_resident)                                    // the whole weight set of this n-tile, once
+                    for (int kc = 0; kc < p.kchunks; ++kc)
                         for (int tap = 0; tap < p.taps; ++tap) {
                             const int slot = tap * p.kchunks + kc;
-                            mbar_wait(bempty(slot), ((uint32_t) run & 1u) ^ 1u);
                             mbar_expect_tx(bfull(slot), p.b_tile_bytes);
                             tma_load_2d<1>(b_base + (uint32_t) slot * p.b_tile_bytes, &tmB, bfull(slot), p.grouped ? tap * p.gk : (tap * p.kchunks + kc) * 64, n0);
                         }
-                    } else {
+                int a_slot = 0, b_slot = 0;
+                uint32_t a_ph = 0, b_ph = 0;
+                // halo of (tile, kc): one 4-D box; the halo of the NEXT chunk is issued before this chunk's weight tiles
+                int at = m0, akc = 0;                                // cursor of the next halo to issue
+                auto issue_a = [&]() {
+                    const int tw = at % p.tiles_w, th = (at / p.tiles_w) % p.tiles_h, img = at / (p.tiles_w * p.tiles_h);
+                    mbar_wait(aempty(a_slot), a_ph ^ 1u);
+                    mbar_expect_tx(afull(a_slot), p.halo_bytes);
+                    tma_load_4d<1>(a_base + (uint32_t) a_slot * p.halo_bytes, &tmA, afull(a_slot), p.in_coff + (p.grouped ? nt * 64 : akc * 64),
+                                   tw * kTileW - p.pad, th * kTileH - p.pad, img);
+                    if (++a_slot == p.a_stages) { a_slot = 0; a_ph ^= 1u; }
+                    if (++akc == p.kchunks) { akc = 0; ++at; }
+                };
+                if (at < m1) issue_a();
+                for (int mt = m0; mt < m1; ++mt)
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        if (at < m1) issue_a();
+                        if (p.b_resident) continue;
                         for (int tap = 0; tap < p.taps; ++tap) {
-                            const int slot = (int) (bcount % p.b_slots);
-                            const uint32_t ph = (uint32_t) ((bcount / p.b_slots) & 1);
-                            mbar_wait(bempty(slot), ph ^ 1u);
-                            mbar_expect_tx(bfull(slot), p.b_tile_bytes);
-                            tma_load_2d<1>(b_base + (uint32_t) slot * p.b_tile_bytes, &tmB, bfull(slot), p.grouped ? tap * p.gk : (tap * p.kchunks + kc) * 64, n0);
-                            ++bcount;
+                            mbar_wait(bempty(b_slot), b_ph ^ 1u);
+                            mbar_expect_tx(bfull(b_slot), p.b_tile_bytes);
+                            tma_load_2d<1>(b_base + (uint32_t) b_slot * p.b_tile_bytes, &tmB, bfull(b_slot), p.grouped ? tap * p.gk : (tap * p.kchunks + kc) * 64, n0);
+                            if (++b_slot == p.b_slots) { b_slot = 0; b_ph ^= 1u; }
                         }
                     }
-                }
             }
-        } else if (warp == 1) {
-            // ===================================================== MMA issuer
-            if (elect_one()) {
-                const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-                const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (p.n_mma >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
-                const uint64_t b_layout = p.b_row_bytes == 128 ? 2ull : (p.b_row_bytes == 64 ? 4ull : 6ull);
-                const uint32_t b_sbo = 8u * p.b_row_bytes;
-                const int ksteps = p.kq / 16;
-                long long g = 0, bcount = 0;
-                int run = -1, prev_nt = -1, as = 0;
-                uint32_t aphase = 0;
-                for (int tile = t0; tile < t1; ++tile) {
-                    const int nt = tile / p.tiles_m;
-                    const bool new_run = p.b_resident && nt != prev_nt;
-                    if (new_run) { ++run; prev_nt = nt; }
-                    const bool last_of_run = p.b_resident && (tile == t1 - 1 || (tile + 1) / p.tiles_m != nt);
-                    mbar_wait(tempty(as), aphase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t) (as * p.acc_stride);
-                    for (int kc = 0; kc < p.kchunks; ++kc, ++g) {
-                        const int aslot = (int) (g % p.a_stages);
-                        mbar_wait(afull(aslot), (uint32_t) ((g / p.a_stages) & 1));
-                        tc_fence_after();
-                        const uint32_t a_addr = a_base + (uint32_t) aslot * p.halo_bytes;
-                        for (int tap = 0; tap < p.taps; ++tap) {
-                            const int r = tap / p.S, s = tap - r * p.S;
-                            int slot;
-                            if (p.b_resident) {
-                                slot = tap * p.kchunks + kc;
-                                if (new_run) { mbar_wait(bfull(slot), (uint32_t) run & 1u); tc_fence_after(); }
-                            } else {
-                                slot = (int) (bcount % p.b_slots);
-                                mbar_wait(bfull(slot), (uint32_t) ((bcount / p.b_slots) & 1));
-                                tc_fence_after();
-                                ++bcount;
-                            }
-                            const uint32_t a_tap = a_addr + (uint32_t) ((r * p.dil) * kPitch + s * p.dil) * kRowB;
-                            const uint64_t adesc = make_desc_ex(a_tap, kSbo, p.base_off ? (a_tap >> 7) : 0u, 2ull);
-                            const uint32_t b_addr = b_base + (uint32_t) slot * p.b_tile_bytes;
-                            for (int q = 0; q < p.nsub; ++q) {
-                                const uint64_t bdesc = make_desc_ex(b_addr + (uint32_t) (q * p.gk) * p.b_row_bytes, b_sbo, 0u, b_layout);
-                                for (int k = 0; k < ksteps; ++k)
-                                    umma_f16<1>(tmem_d + (uint32_t) (q * p.gk), adesc + 2u * (uint32_t) (q * ksteps + k), bdesc + 2u * (uint32_t) k, idesc,
-                                                (kc | tap | k) != 0 ? 1u : 0u);
-                            }
-                            if (!p.b_resident || last_of_run) umma_commit<1>(bempty(slot));
-                        }
-                        umma_commit<1>(aempty(aslot));
-                    }
-                    umma_commit<1>(tfull(as));
-                    if (++as == p.acc_stages) { as = 0; aphase ^= 1u; }
-                }
-            }
+        } else if (warp - 1 < n_iss) {
+            // ===================================================== MMA issuers
+            if (p.nsub == 1) mma_dispatch<1, 4>(p, tmem_base, a_base, b_base, bar_base, ntiles, warp - 1, n_iss);
+            else if (p.nsub == 2) mma_dispatch<2, 2>(p, tmem_base, a_base, b_base, bar_base, ntiles, warp - 1, n_iss);
+            else mma_dispatch<4, 1>(p, tmem_base, a_base, b_base, bar_base, ntiles, warp - 1, n_iss);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-        if (p.is_bf16) halo_epilogue<__nv_bfloat16>(p, tmem_base, tfull(0), tempty(0), t0, t1);
-        else halo_epilogue<__half>(p, tmem_base, tfull(0), tempty(0), t0, t1);
+        if (p.is_bf16) halo_epilogue_dispatch<__nv_bfloat16>(p, tmem_base, tfull(0), tempty(0), nt, m0, m1);
+        else halo_epilogue_dispatch<__half>(p, tmem_base, tfull(0), tempty(0), nt, m0, m1);
     }
     tc_fence_before();
     __syncthreads();
@@ -417,9 +471,19 @@ int conv_halo_launch(const csb_conv_desc* d, const void* x, const void* w, const
         p.b_slots = slots;
     }
     const uint32_t b_bytes = (uint32_t) p.b_slots * p.b_tile_bytes;
-    int a_stages = (int) ((budget - bars - b_bytes) / p.halo_bytes);
-    p.a_stages = a_stages > kMaxA ? kMaxA : a_stages;
-    CSB_REQUIRE(p.a_stages >= 2, "halo tile too large");
+    const int a_stages = (int) ((budget - bars - b_bytes) / p.halo_bytes);
+    p.a_stages = a_stages >= 4 ? 4 : 2;                          // a power of two (slot = index & mask in the issue loop)
+    CSB_REQUIRE(a_stages >= 2, "halo tile too large");
+    // Issuers work on different tiles concurrently and find their ring slots by index parity: tile i may only start once tile i - n_iss is
+    // complete, so the halo ring must hold the chunks of n_iss tiles (a_stages >= n_iss * kchunks) and there must be n_iss accumulator stages --
+    // otherwise a wait could be satisfied by the slot's PREVIOUS phase (mbarrier parity is ambiguous two phases apart).
+    p.n_iss = 1;
+    if (p.b_resident) {
+        int n = p.a_stages / p.kchunks;
+        n = n > 3 ? 3 : n;
+        n = n > p.acc_stages ? p.acc_stages : n;
+        p.n_iss = n < 1 ? 1 : n;
+    }
     p.b_off = (uint32_t) p.a_stages * p.halo_bytes;              // halo_bytes is a multiple of 2 KiB: every region stays 1 KiB aligned
     p.bar_off = p.b_off + ((b_bytes + 1023u) & ~1023u);
     const size_t smem = (size_t) p.bar_off + bars + 1024 /*align*/;
@@ -449,9 +513,12 @@ int conv_halo_launch(const csb_conv_desc* d, const void* x, const void* w, const
 
     static unsigned char attr_done[64] = {};
     if (csb::first_use_on_device(attr_done)) cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    const long long total = (long long) p.tiles_m * p.tiles_n;
+    // one n-tile per CTA: grid = tiles_n * (CTAs per n-tile), at most one CTA per SM
     const int sms = csb::num_sms();
-    const int grid = (int) (total < sms ? total : sms);
+    CSB_REQUIRE(p.tiles_n <= sms, "too many 64-channel slices for the halo-tile kernel");
+    int per_n = sms / p.tiles_n;
+    per_n = per_n > p.tiles_m ? p.tiles_m : per_n;
+    const int grid = p.tiles_n * per_n;
     k_conv_halo<<<grid, 128 * (kEpiGroups + 1), smem, (cudaStream_t) stream>>>(tmA, tmB, p);
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {
         char label[160];

@@ -93,9 +93,17 @@ class _C:
     def __init__(self, w, b, dev, groups=1, cin_pad=None):
         self.groups = groups
         self.w = E.pack_grouped_weight(w.to(dev), groups) if groups > 1 else E.pack_conv_weight(w.to(dev), torch.float16, cin_pad)
+        # stride-1 grouped 3x3: compact diagonal blocks for the halo-tile kernel (N = K = channels per group, no zero multiplies)
+        self.w_halo = E.pack_grouped_weight_compact(w.to(dev), groups) if groups > 1 else None
         self.b = None if b is None else b.float().contiguous().to(dev)
 
     def __call__(self, x, **kw):
+        if self.w_halo is not None and kw.get('stride', 1) == 1:
+            N, H, W, Cx = x.shape
+            Cout, R, S, _ = self.w_halo.shape
+            if E.halo_supported(N, H, W, Cout, Cx, kw.get('in_coff', 0), Cout, R, S, 1, kw.get('pad', 0), kw.get('dil', 1), self.groups):
+                kw = {k: v for k, v in kw.items() if k != 'stride'}
+                return E.conv2d_halo_nhwc(x, self.w_halo, self.b, groups=self.groups, **kw)
         return E.conv2d_nhwc(x, self.w, self.b, groups=self.groups, **kw)
 
 

@@ -35,6 +35,10 @@ DENSE = [
     (1, 20, 20, 64, 48, 5, 2, 1, 'silu'),         # 5x5
     (2, 18, 26, 64, 16, 7, 3, 1, None),           # 7x7: the widest shift (6 pixels)
     (1, 30, 30, 256, 128, 3, 1, 1, 'relu'),       # four chunks, N = 128
+    (6, 120, 120, 128, 64, 3, 1, 1, 'relu'),      # ~9 tiles per CTA, two chunks, resident weights squeezed to 2 halo stages (one issuer)
+    (6, 120, 120, 64, 64, 3, 1, 1, 'relu'),       # ~9 tiles per CTA, three issuing warps
+    (4, 100, 100, 256, 64, 3, 1, 1, 'relu'),      # ~5 tiles per CTA, streamed weights through the ring (36 tiles of 8 KiB per m-tile)
+    (4, 90, 90, 64, 32, 3, 2, 2, 'relu'),         # dilation 2: 40 KiB halos, two issuers
 ]
 
 
