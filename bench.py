@@ -24,6 +24,7 @@ import argparse
 import ctypes
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -243,6 +244,35 @@ def timed_call(fn):
     return e0.elapsed_time(e1), r
 
 
+CONV_LABEL = re.compile(r"(k_conv_tc|k_conv_halo)\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+) k(\d+)x(\d+) s(\d+) d(\d+) g(\d+) act(\d+) res(\d+)\]")
+
+
+def profile_detail(lib, fn):
+    """profile_call in the library's detailed mode (conv launches keyed by layer shape) -> per kernel name {ms, count, gflop}: the algorithmic
+    FLOPs of the tensor-core kernels are computed from the launches themselves, 2 * pixels_out * Cout * R * S * Cin / groups per launch."""
+    old = os.environ.get("CSB_PROFILE_DETAIL")
+    os.environ["CSB_PROFILE_DETAIL"] = "1"
+    try:
+        prof = profile_call(lib, fn)
+    finally:
+        if old is None:
+            os.environ.pop("CSB_PROFILE_DETAIL", None)
+        else:
+            os.environ["CSB_PROFILE_DETAIL"] = old
+    agg = {}
+    for label, v in prof.items():
+        m = CONV_LABEL.match(label)
+        name = m.group(1) if m else label
+        a = agg.setdefault(name, {"ms": 0.0, "count": 0, "gflop": 0.0})
+        a["ms"] += v["ms"]
+        a["count"] += v["count"]
+        if m:
+            N, Hi, Wi, Cin, Cout, R, S_, st, dil, g = map(int, m.groups()[1:11])
+            Ho, Wo = (Hi + st - 1) // st, (Wi + st - 1) // st        # the engine's layers are 'same'-padded (stride 1) or strided: ceil(n / stride)
+            a["gflop"] += v["count"] * 2.0 * N * Ho * Wo * Cout * R * S_ * (Cin // max(1, g)) / 1e9
+    return agg
+
+
 def profile_call(lib, fn):
     """per-kernel device time of fn(): a CUDA event after every library launch (csb_profile_begin/end)"""
     import torch
@@ -307,12 +337,12 @@ def run_other(pipe, imgs_np, args, lib):
         zp.render_frame_batch(zb, warp=False)
         ms, _ = timed_call(lambda: zp.render_frame_batch(zb, warp=False))
         prof = profile_call(lib, lambda: zp.render_frame_batch(zb, warp=False))
-        zoe_lin = 2 * (24 * 1765 * 12 * 1024 * 1024 * 2 / 1e9 + 291.0) * 32 + 1011.9 * 32          # GFLOP on k_conv_tc: BEiT linears + DPT convs (2 net inputs) + detector
+        zoe_lin = 2 * (24 * 1765 * 12 * 1024 * 1024 * 2 / 1e9 + 291.0) * 32 + 1011.9 * 32          # GFLOP on the conv engine (k_conv_tc + k_conv_halo): BEiT linears + DPT convs (2 net inputs) + detector
         att = 2 * 24 * 16 * 4 * 1765 * 1765 * 64 / 1e9 * 32                                          # GFLOP on k_attention_tc
         res["seg_zoedepth_batch32"] = {"api": "KenBurnsPipeline(depth_est='zoe').render_frame_batch(32 frames 1024x1024x3 resident in HBM, warp=False): detector + "
                                               "ZoeDepth.infer(pad_input, with_flip_aug) + depth->disparity + instance flattening (BASELINE configs[2])",
                                        "frames_per_s": 32e3 / ms, "ms": ms,
-                                       "k_conv_tc_tflops": zoe_lin / prof["k_conv_tc"]["ms"] if "k_conv_tc" in prof else None,
+                                       "conv_engine_tflops": zoe_lin / sum(prof[k]["ms"] for k in ("k_conv_tc", "k_conv_halo") if k in prof) if "k_conv_tc" in prof else None,
                                        "k_attention_tc_tflops": att / prof["k_attention_tc"]["ms"] if "k_attention_tc" in prof else None,
                                        "per_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:10]}}
         del zp, zb
@@ -464,6 +494,7 @@ def main():
 
     # ---- per-kernel device time of the same step (second pass, a CUDA event after every launch) -> roofline
     prof = profile_call(lib, lambda: step(0, False))
+    prof_d = profile_detail(lib, lambda: step(0, False))       # the same step with conv launches keyed by layer shape: FLOPs per tensor-core kernel
 
     other = run_other(pipe, imgs_np, args, lib) if (world == 1 and not args.no_other) else None
 
@@ -488,20 +519,24 @@ def main():
         roof = None
         tr = traffic.get("kernels", {}).get(dom) if dom else None
         tr_same = bool(tr) and traffic.get("batch") == B and traffic.get("stages") == ",".join(stages) and traffic.get("depth") == args.depth
-        if dom == "k_conv_tc":
-            # algorithmic FLOPs of the tensor-core launches of one step: detector 1011.9 GFLOP / image @1024^2 (ConvNeXt-B 641.7 + neck 132.2
-            # + head 237.9), LeReS 591.9 GFLOP / image @640^2 input
-            # ZoeDepth on k_conv_tc: per 672^2 net input, T = 1765 tokens, D = 1024: 24 blocks x 12 T D^2 MAC of Linear layers + ~291 GFLOP of DPT
-            # reassemble / fusion / head convs (the 4 T^2 D attention MACs run on k_attention and are NOT counted here); 2 net inputs per frame
-            zoe_gflop = 2 * (24 * 1765 * 12 * 1024 * 1024 * 2 / 1e9 + 291.0)
-            depth_gflop = 0.0 if 'depth' not in stages else (591.9 if args.depth == 'leres' else zoe_gflop)
-            gflop = (1011.9 if 'seg' in stages else 0.0) * B + depth_gflop * B
-            ach = gflop / prof[dom]["ms"]                             # GFLOP / ms = TFLOP/s
+        if dom in ("k_conv_tc", "k_conv_halo"):
+            # Algorithmic FLOPs of the tensor-core launches of this step, computed from the launches themselves (profile_detail: 2 * output pixels *
+            # Cout * R * S * Cin / groups per launch).  Cross-check: detector 1011.9 GFLOP / image @1024^2 (ConvNeXt-B 641.7 + neck 132.2
+            # + head 237.9), LeReS 591.9 GFLOP / image @640^2; ZoeDepth per 672^2 net input 24 x 12 T D^2 MAC of Linear layers + ~291 GFLOP of DPT convs.
+            d = prof_d.get(dom, {"ms": prof[dom]["ms"], "count": prof[dom]["count"], "gflop": 0.0})
+            gflop, ach = d["gflop"], d["gflop"] / prof[dom]["ms"]      # GFLOP / ms = TFLOP/s, on the time of the undetailed pass
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak,
                     "traffic": (tr["dram_bytes_per_launch"] if tr_same else None),
                     "peak_source": "measured sustained bf16 cuBLAS (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback",
                     "launches_per_step": prof[dom]["count"], "algorithmic_gflop_per_step": gflop, "avg_launch_us": 1e3 * prof[dom]["ms"] / prof[dom]["count"],
-                    "flop_note": "the numerator also holds the depthwise 7x7/5x5 and mask-head FLOPs (~1-2 %), which run on other kernels: frac is that much generous"}
+                    "flop_note": "FLOPs summed over this kernel's launches of the step from their layer shapes (grouped convs: the group-sparse count)"}
+            # the conv engine as a whole: both tcgen05 kernels (k_conv_tc: per-tap pipeline, k_conv_halo: halo tiles for thin / grouped layers)
+            eng_ms = sum(prof[k]["ms"] for k in ("k_conv_tc", "k_conv_halo") if k in prof)
+            eng_gf = sum(prof_d[k]["gflop"] for k in ("k_conv_tc", "k_conv_halo") if k in prof_d)
+            roof["conv_engine"] = {"kernels": [k for k in ("k_conv_tc", "k_conv_halo") if k in prof], "ms_per_step": round(eng_ms, 3), "algorithmic_gflop_per_step": round(eng_gf, 1),
+                                   "achieved": eng_gf / eng_ms if eng_ms else None, "frac": (eng_gf / eng_ms / tc_peak) if eng_ms else None,
+                                   "per_kernel": {k: {"ms": round(prof[k]["ms"], 3), "gflop": round(prof_d[k]["gflop"], 1), "tflops": round(prof_d[k]["gflop"] / prof[k]["ms"], 1)}
+                                                  for k in ("k_conv_tc", "k_conv_halo") if k in prof and k in prof_d}}
             if tr:
                 roof["traffic_source"] = {"file": "profiles/r2_traffic.json", "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the "
                                           "kernel's launches of one step)", "same_config_as_this_run": tr_same, **{k: tr[k] for k in ("launches", "dram_read_bytes", "dram_write_bytes")}}

@@ -522,7 +522,7 @@ int conv_halo_launch(const csb_conv_desc* d, const void* x, const void* w, const
     k_conv_halo<<<grid, 128 * (kEpiGroups + 1), smem, (cudaStream_t) stream>>>(tmA, tmB, p);
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {
         char label[160];
-        snprintf(label, sizeof label, "k_conv_tc[%dx%dx%dx%d->%d k%dx%d s%d d%d g%d act%d res%d]", d->N, d->Hin, d->Win, d->Cin, d->Cout, d->R, d->S, d->stride, d->dil,
+        snprintf(label, sizeof label, "k_conv_halo[%dx%dx%dx%d->%d k%dx%d s%d d%d g%d act%d res%d]", d->N, d->Hin, d->Win, d->Cin, d->Cout, d->R, d->S, d->stride, d->dil,
                  d->groups, d->act, d->res_mode);
         return csb::launched(csb::profile_intern(label), (cudaStream_t) stream);
     }

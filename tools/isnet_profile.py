@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cartoonsegmentation_b200 import _lib                                   # noqa: E402
 from cartoonsegmentation_b200.animeinsseg import isnet as I                 # noqa: E402
 
-PAT = re.compile(r"k_conv_tc\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+) k(\d+)x(\d+) s(\d+) d(\d+) g(\d+) act(\d+) res(\d+)\]")
+PAT = re.compile(r"(k_conv_tc|k_conv_halo)\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+) k(\d+)x(\d+) s(\d+) d(\d+) g(\d+) act(\d+) res(\d+)\]")
 
 
 def main():
@@ -41,12 +41,12 @@ def main():
         if not m:
             other[k] = v
             continue
-        N, H, W, Cin, Cout, R, S_, st, dil, g, act, res = map(int, m.groups())
+        N, H, W, Cin, Cout, R, S_, st, dil, g, act, res = map(int, m.groups()[1:])
         Ho, Wo = (H + st - 1) // st, (W + st - 1) // st
         gflop = 2.0 * N * Ho * Wo * Cout * (Cin // g) * R * S_ / 1e9
         byts = 2.0 * N * (H * W * Cin + Ho * Wo * Cout)
         conv += v['ms']
-        rows.append(dict(shape=k[9:], ms=v['ms'], count=v['count'], gflop=gflop * v['count'], tflops=gflop * v['count'] / v['ms'], gbs=byts * v['count'] / v['ms'] / 1e6))
+        rows.append(dict(shape=('halo ' if k.startswith('k_conv_halo') else '') + k[k.index('['):], ms=v['ms'], count=v['count'], gflop=gflop * v['count'], tflops=gflop * v['count'] / v['ms'], gbs=byts * v['count'] / v['ms'] / 1e6))
     rows.sort(key=lambda r: -r['ms'])
     tot = sum(v['ms'] for v in prof.values())
     print(f"== ISNet B={B} @{S}^2: forward {wall:.2f} ms unprofiled ({wall / B:.3f} ms/instance), profiled sum {tot:.2f} ms, conv {conv:.2f} ms, "

@@ -16,7 +16,7 @@ from cartoonsegmentation_b200.animeinsseg import AnimeInsSeg               # noq
 from cartoonsegmentation_b200.depth_modules.leres import LeReS             # noqa: E402
 from cartoonsegmentation_b200.utils.synthetic import smooth_image          # noqa: E402
 
-PAT = re.compile(r"k_conv_tc\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+) k(\d+)x(\d+) s(\d+) d(\d+) g(\d+) act(\d+) res(\d+)\]")
+PAT = re.compile(r"(k_conv_tc|k_conv_halo)\[(\d+)x(\d+)x(\d+)x(\d+)->(\d+) k(\d+)x(\d+) s(\d+) d(\d+) g(\d+) act(\d+) res(\d+)\]")
 
 
 def profile(fn):
@@ -37,12 +37,12 @@ def table(name, prof):
         m = PAT.match(k)
         if not m:
             continue
-        N, H, W, Cin, Cout, R, S, st, dil, g, act, res = map(int, m.groups())
+        N, H, W, Cin, Cout, R, S, st, dil, g, act, res = map(int, m.groups()[1:])
         Ho, Wo = (H + st - 1) // st, (W + st - 1) // st
         gflop = 2.0 * N * Ho * Wo * Cout * (Cin // g) * R * S / 1e9
         byts = 2.0 * N * (H * W * Cin + Ho * Wo * Cout)
         conv += v['ms']
-        rows.append(dict(shape=k[9:], ms=v['ms'], count=v['count'], tflops=gflop * v['count'] / v['ms'], gbs=byts * v['count'] / v['ms'] / 1e6))
+        rows.append(dict(shape=('halo ' if k.startswith('k_conv_halo') else '') + k[k.index('['):], ms=v['ms'], count=v['count'], tflops=gflop * v['count'] / v['ms'], gbs=byts * v['count'] / v['ms'] / 1e6))
     rows.sort(key=lambda r: -r['ms'])
     print(f"== {name}: all kernels {tot:.2f} ms, conv {conv:.2f} ms")
     for r in rows[:28]:
