@@ -59,6 +59,7 @@ struct ConvKernelParams {
     const void* residual;
     int res_ld, res_coff, res_mode;   // 0 none, 1 add before activation, 2 add after activation
     int act;
+    int gelu_form;               // 0: mixed polynomial / sigmoid-form exact GELU, 1: tanh form (one MUFU per element)
     const float* act_param;      // per-channel PReLU slope
     void* out;
     float* out_f32;
@@ -147,6 +148,25 @@ __device__ __forceinline__ void gelu2_mufu(float& a, float& b) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
     upk2(fmul2(x, pk2(r0, r1)), a, b);
 }
+// Exact-erf GELU on two values in tanh form: gelu(x) = 0.5 x (1 + tanh(g(x))) with the same fitted g(x) = atanh(erf(x / sqrt2)) as gelu2_mufu, through ONE
+// MUFU op per element (tanh.approx.f32) instead of ex2 + rcp: 6 packed + 2 FMNMX + 2 MUFU per PAIR.  Selected per launch (CSB_GELU_FORM=tanh / GM < 0);
+// the accuracy of MUFU.TANH decides whether it may be the default (tools/gelu_check.py measures it against the correctly rounded result).
+__device__ __forceinline__ void gelu2_tanh(float& a, float& b) {
+    const uint64_t x = pk2(a, b);
+    float s0, s1;
+    upk2(fmul2(x, x), s0, s1);
+    const uint64_t x2 = pk2(fminf(s0, 64.0f), fminf(s1, 64.0f));
+#define CSB_C2(v) pk2(v, v)
+    uint64_t q = ffma2(x2, CSB_C2(-0.00035151723f), CSB_C2(0.037005644f));
+    q = ffma2(q, x2, CSB_C2(0.79750788f));
+    float u0, u1, t0, t1;
+    upk2(fmul2(q, x), u0, u1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+    const uint64_t h = fmul2(x, CSB_C2(0.5f));
+#undef CSB_C2
+    upk2(ffma2(h, pk2(t0, t1), h), a, b);
+}
 #ifndef CSB_GELU_MUFU_PAIRS
 #define CSB_GELU_MUFU_PAIRS 8
 #endif
@@ -203,7 +223,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
         } else if constexpr (ACT == CSB_ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {                // interleaved, so that neighbouring pairs run on different pipes
-                if ((j >> 1) * GM / 16 != ((j >> 1) + 1) * GM / 16) gelu2_mufu(y[j], y[j + 1]);
+                if constexpr (GM < 0) gelu2_tanh(y[j], y[j + 1]);
+                else if ((j >> 1) * GM / 16 != ((j >> 1) + 1) * GM / 16) gelu2_mufu(y[j], y[j + 1]);
                 else gelu2(y[j], y[j + 1]);
             }
         } else {
@@ -334,6 +355,11 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
 template <class T, int CG>
 __device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
                                                   const CUtensorMap* tmC) {
+    if (p.act == CSB_ACT_GELU && p.gelu_form == 1) {    // tanh-form GELU (experimental, CSB_GELU_FORM=tanh)
+        if (p.ln_stats) epilogue_role<T, CSB_ACT_GELU, CG, true, -1>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
+        else epilogue_role<T, CSB_ACT_GELU, CG, false, -1>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
+        return;
+    }
     if (p.ln_stats) {     // LayerNorm-folded 1x1 conv: only the activations that follow a LayerNorm on this path
         if (p.act == CSB_ACT_GELU) epilogue_role<T, CSB_ACT_GELU, CG, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
         else epilogue_role<T, CSB_ACT_NONE, CG, true>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
@@ -497,7 +523,12 @@ CUtensorMapSwizzle swizzle_of(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_
 
 std::atomic<int> g_pair_mode{[] { const char* e = getenv("CSB_CTA_PAIR"); return e ? atoi(e) : 1; }()};
 
+std::atomic<int> g_gelu_form{[] { const char* e = getenv("CSB_GELU_FORM"); return e && (e[0] == 't' || e[0] == '1') ? 1 : 0; }()};
+
 }  // namespace
+
+// A/B switch of the GELU epilogue form (0 mixed polynomial / sigmoid, 1 tanh); returns the previous form.
+extern "C" int csb_conv_set_gelu_form(int form) { return g_gelu_form.exchange(form); }
 
 // A/B switch of the CTA-pair path for tests and benchmarks (same values as the CSB_CTA_PAIR environment variable); returns the previous mode.
 extern "C" int csb_conv_set_pair_mode(int mode) { return g_pair_mode.exchange(mode); }
@@ -592,6 +623,7 @@ static int conv_impl(const csb_conv_desc* d, const void* x, const void* w, const
     p.stage_off = (uint32_t) (((size_t) p.stages * stage_bytes + 8 * (2 * kMaxStages + 2 * kAccStages) + 16 + 1023) & ~(size_t) 1023);
     const size_t smem = (size_t) p.stage_off + 4 * kMaxEpiGroups * 2048 + 1024 /*align*/;
     p.bias = bias; p.act = d->act; p.act_param = act_param;
+    p.gelu_form = g_gelu_form.load(std::memory_order_relaxed);
     p.residual = residual; p.res_ld = d->res_ld; p.res_coff = d->res_coff; p.res_mode = d->res_mode;
     p.out = y; p.out_f32 = y_f32; p.out_ld = d->out_ld; p.out_coff = d->out_coff; p.is_bf16 = d->dtype == 1;
     // Output tensor map for the epilogue's TMA tile stores: the channel slice [out_coff, out_coff + Cout) of the NHWC output, box = 32 channels x

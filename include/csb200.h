@@ -272,6 +272,11 @@ CSB_API int csb_conv2d_nhwc(const csb_conv_desc* desc, const void* x, const void
  * depend on the mode beyond fp32 accumulation order (identical: the k-order is unchanged). */
 CSB_API int csb_conv_set_pair_mode(int mode);
 
+/* A-B switch of the conv engine's GELU epilogue: 0 (default) exact-erf GELU evaluated as a mixed degree-19 polynomial / sigmoid form (|error| <= 2.6e-5),
+ * 1 the same fitted atanh(erf) argument through one tanh.approx MUFU op per element (fewer FMA-pipe instructions; accuracy bounded by MUFU.TANH).
+ * Same as the CSB_GELU_FORM=tanh environment variable; returns the previous form. */
+CSB_API int csb_conv_set_gelu_form(int form);
+
 /* Halo-tile path of the conv engine (csrc/tc_halo.cu) for stride-1 RxS convolutions: ONE activation halo box per 64-channel chunk feeds all R*S
  * taps through shifted tcgen05 shared-memory descriptors (the per-tap path moves R*S x the activation bytes from L2 to shared memory).
  *   desc->groups <= 1: w = [Cout][R][S][Cin] as for csb_conv2d_nhwc (which routes its eligible shapes with Cout <= 128 here by itself);

@@ -7,6 +7,7 @@ per kernel name the launch count, total DRAM bytes and bytes per launch -- the `
 """
 import argparse
 import csv
+import gzip
 import json
 import re
 from collections import OrderedDict
@@ -24,8 +25,10 @@ def main():
     ap.add_argument("csv"); ap.add_argument("out")
     ap.add_argument("--batch", type=int, default=32); ap.add_argument("--stages", default="seg,depth,warp"); ap.add_argument("--depth", default="leres")
     ap.add_argument("--steps", type=int, default=1, help="bench steps covered by the capture (totals are divided by it)")
+    ap.add_argument("--command", default="", help="the ncu command line, recorded in the output")
     a = ap.parse_args()
-    rows = [r for r in csv.reader(open(a.csv, errors="replace")) if len(r) > 10]
+    fh = gzip.open(a.csv, "rt", errors="replace") if a.csv.endswith(".gz") else open(a.csv, errors="replace")
+    rows = [r for r in csv.reader(fh) if len(r) > 10]
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
     per = {}
@@ -47,8 +50,9 @@ def main():
         n = len(d["ids"])
         out[k] = {"launches": n / a.steps, "dram_read_bytes": d["dram_read_bytes"] / a.steps, "dram_write_bytes": d["dram_write_bytes"] / a.steps,
                   "dram_bytes_per_launch": (d["dram_read_bytes"] + d["dram_write_bytes"]) / max(1, n), "ncu_time_ms": d["time_us"] * 1e-3 / a.steps}
-    res = {"what": "ncu dram__bytes_read.sum + dram__bytes_write.sum per kernel over one bench step (cold-cache, serialised replays)", "batch": a.batch, "stages": a.stages,
-           "depth": a.depth, "kernels": out}
+    res = {"what": "ncu dram__bytes_read.sum + dram__bytes_write.sum per kernel, per bench step (cold-cache, serialised replays; capture = the first "
+                   f"{a.steps} step(s) of `bench.py --no-other --no-cpu-baseline`, ncu -c limits the launch count)", "command": a.command, "batch": a.batch,
+           "stages": a.stages, "depth": a.depth, "kernels": out}
     json.dump(res, open(a.out, "w"), indent=1)
     for k, v in list(out.items())[:12]:
         print(f"{k:26s} x{v['launches']:6.0f}  {v['dram_bytes_per_launch'] / 1e6:9.1f} MB/launch  {v['ncu_time_ms']:8.2f} ms")
