@@ -345,8 +345,8 @@ class KenBurnsPipeline:
             small = torch.from_numpy(np.stack([scaledown_maxsize(im, self.cfg.depth_est_size, 32) for im in imgs])).to(self.device)
         logits = self.leres.forward(small)                                     # [N,h,w] fp32
         n, h, w = logits.shape
-        if ori_h >= h and ori_w >= w and not getattr(self, 'leres_host_tail', False):
-            # the reference's numpy/OpenCV tail (16 -> 8 bit quantisation, INTER_AREA resize back) on the device, bit-exact (csrc/leres_tail.cu):
+        if (h > ori_h or (ori_h >= h and ori_w >= w)) and not getattr(self, 'leres_host_tail', False):
+            # the reference's numpy/OpenCV tail (16 -> 8 bit quantisation, INTER_AREA / INTER_LANCZOS4 resize back) on the device, bit-exact (csrc/leres_tail.cu):
             # no D2H, no host work, the stream never waits for the CPU
             mm = torch.empty(2 * n, device=self.device, dtype=torch.int32)
             q8 = torch.empty((n, h, w), device=self.device, dtype=torch.uint8)

@@ -85,7 +85,7 @@ class AnimeInsSeg:
 
     def set_refine_method(self, refine_method: str = 'none', refine_size: int = 720, refine_ckpt=None):
         """reference :623-633.  'refinenet_isnet' = ISNetDIS(in_ch=4) on the tcgen05 engine (isnet.py); 'animeseg' (the alternative
-        anime-seg matting net, AnimeSegmentation.try_load) is outside the default path and not built."""
+        anime-seg matting net, AnimeSegmentation.try_load) cannot run in the reference either (see the branch below), so it raises here too."""
         if refine_method == 'none':
             self.postprocess_refine = None
         elif refine_method == 'refinenet_isnet':
@@ -99,7 +99,11 @@ class AnimeInsSeg:
             self.refine_size = refine_size
             self.postprocess_refine = self._postprocess_refine
         elif refine_method == 'animeseg':
-            raise NotImplementedError("refine method 'animeseg' (anime-seg isnet_is matting net) is not on the default path and not built")
+            # In the reference this branch is dead on the infer path: `animeseg_refine` (:78-82) reads `det_pred.pred_instances` of an mmdet
+            # DetDataSample, but `postprocess_results` (:700-702) hands it the AnimeInstances built by `_det_forward` (:447-462), which has no such
+            # attribute -> AttributeError on the first image with a detection.  Error behaviour is kept (an exception at selection time instead).
+            raise NotImplementedError("refine method 'animeseg': the reference's own call path for it raises AttributeError "
+                                      "(animeseg_refine expects a DetDataSample, infer passes AnimeInstances); use 'refinenet_isnet' or 'none'")
         else:
             raise NotImplementedError(f'Invalid refine method: {refine_method}')
 

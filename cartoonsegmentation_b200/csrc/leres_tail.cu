@@ -6,8 +6,16 @@
 // which stalls the GPU pipeline behind the host.  Here: per-image min/max (order-preserving keys), quantisation with the same float32 operation
 // order and OpenCV's rounding (cvRound = round-half-even of src * (float) alpha), and OpenCV's INTER_AREA-upscale = INTER_LINEAR fixed-point
 // kernel with area-mode source positions (imgproc/src/resize.cpp), all bit-exact against cv2 (oracle: orc_resize_area_up_u8c1, pinned to cv2
-// in the CPU suite).  Downscaling (INTER_LANCZOS4, inputs smaller than the estimator size) stays on the host path.
+// in the CPU suite).  Downscaling (kenburns_effect.py:574-575: INTER_LANCZOS4 when the estimator output has more rows than the frame, i.e. inputs smaller
+// than the estimator size rounded up to a multiple of 32) is OpenCV's 8-tap fixed-point resize (resize.cpp: HResizeLanczos4<uchar,int,short> +
+// VResizeLanczos4 + FixedPtCast<int,uchar,22>): the coefficient tables (interpolateLanczos4, double sin/cos of the host libm as OpenCV uses, rounded
+// to short x 2048) are built once per geometry on the host and cached on the device; k_lt_lanczos evaluates the 8 x 8 taps in OpenCV's int32 arithmetic.
 #include <math.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
 
 #include "common.cuh"
 
@@ -92,6 +100,104 @@ __global__ void __launch_bounds__(256) k_lt_resize(const uint8_t* __restrict__ q
     }
 }
 
+// cv2.resize(u8 C1, INTER_LANCZOS4): tab = [xofs (W ints) | yofs (H ints)] followed by shorts [alpha (W x 8) | beta (H x 8)]
+__global__ void __launch_bounds__(256) k_lt_lanczos(const uint8_t* __restrict__ q, int h, int w, int H, int W, const int* __restrict__ ofs,
+                                                    const short* __restrict__ coef, float* __restrict__ out) {
+    const int img = blockIdx.y;
+    const uint8_t* S = q + (long long) img * h * w;
+    float* O = out + (long long) img * H * W;
+    const int *xofs = ofs, *yofs = ofs + W;
+    const short *alpha = coef, *beta = coef + (long long) W * 8;
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < (long long) H * W; i += (long long) gridDim.x * blockDim.x) {
+        const int dx = (int) (i % W), dy = (int) (i / W);
+        const int sx = xofs[dx], sy = yofs[dy];
+        int xs[8], a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int x = sx - 3 + k;
+            xs[k] = x < 0 ? 0 : (x >= w ? w - 1 : x);               // HResizeLanczos4 border loop (cn = 1): clamp to the row
+            a[k] = alpha[dx * 8 + k];
+        }
+        int v = 0;                                                  // WT = int: OpenCV's own 32-bit arithmetic (wraps identically)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int y = sy - 3 + r;
+            y = y < 0 ? 0 : (y >= h ? h - 1 : y);                   // clip(sy - ksize2 + 1 + k, 0, ssize.height)
+            const uint8_t* row = S + (long long) y * w;
+            int hsum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) hsum += (int) row[xs[k]] * a[k];
+            v += hsum * (int) beta[dy * 8 + r];
+        }
+        v = (v + (1 << 21)) >> 22;                                  // FixedPtCast<int, uchar, INTER_RESIZE_COEF_BITS * 2>
+        O[i] = (float) (v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
+// imgproc/src/imgwarp.cpp interpolateLanczos4 (OpenCV 4.x), operation for operation (float / double mix as in the source)
+void lanczos4_coeffs(float x, float* coeffs) {
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    float sum = 0;
+    const double y0 = -(x + 3) * 3.1415926535897932384626433832795 * 0.25, s0 = sin(y0), c0 = cos(y0);
+    for (int i = 0; i < 8; i++) {
+        const float y0_ = (x + 3 - i);
+        if (fabs(y0_) >= 1e-6f) {
+            const double y = -y0_ * 3.1415926535897932384626433832795 * 0.25;
+            coeffs[i] = (float) ((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+        } else {
+            coeffs[i] = 1e30f;
+        }
+        sum += coeffs[i];
+    }
+    sum = 1.f / sum;
+    for (int i = 0; i < 8; i++) coeffs[i] *= sum;
+}
+
+short sat_short(float v) {                                           // saturate_cast<short>(float): cvRound (round half to even) + clamp
+    const long r = lrintf(v);
+    return (short) (r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+}
+
+struct LanczosTab { int* ofs = nullptr; short* coef = nullptr; };
+
+// resize.cpp cv::resize, INTER_LANCZOS4 branch: fx = (float) ((dx + 0.5) * scale - 0.5), sx = cvFloor(fx), fx -= sx (no index clamp for Lanczos)
+int lanczos_tables(int h, int w, int H, int W, LanczosTab& out) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int, int, int>, LanczosTab> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_tuple(dev, h, w, H, W);
+    auto it = cache.find(key);
+    if (it != cache.end()) { out = it->second; return CSB_OK; }
+    std::vector<int> ofs((size_t) W + H);
+    std::vector<short> coef(((size_t) W + H) * 8);
+    auto axis = [&](int dn, int sn, int* o, short* c) {
+        const double scale = 1.0 / ((double) dn / sn);               // scale_x = 1. / inv_scale_x, inv_scale_x = (double) dsize.width / ssize.width
+        for (int d = 0; d < dn; ++d) {
+            float f = (float) ((d + 0.5) * scale - 0.5);
+            const int s0 = (int) floorf(f);
+            f -= s0;
+            float cb[8];
+            lanczos4_coeffs(f, cb);
+            o[d] = s0;
+            for (int k = 0; k < 8; ++k) c[d * 8 + k] = sat_short(cb[k] * 2048.f);
+        }
+    };
+    axis(W, w, ofs.data(), coef.data());
+    axis(H, h, ofs.data() + W, coef.data() + (size_t) W * 8);
+    LanczosTab t;
+    if (cudaMalloc(&t.ofs, ofs.size() * sizeof(int)) != cudaSuccess || cudaMalloc(&t.coef, coef.size() * sizeof(short)) != cudaSuccess)
+        return csb::fail(CSB_ERR_CUDA, "%s: %s", "csb_leres_depth_tail", "cudaMalloc of the Lanczos tables failed");
+    if (cudaMemcpy(t.ofs, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(t.coef, coef.data(), coef.size() * sizeof(short), cudaMemcpyHostToDevice) != cudaSuccess)
+        return csb::fail(CSB_ERR_CUDA, "%s: %s", "csb_leres_depth_tail", "upload of the Lanczos tables failed");
+    cache[key] = t;
+    out = t;
+    return CSB_OK;
+}
+
 __global__ void __launch_bounds__(256) k_lt_tofloat(const uint8_t* __restrict__ q, long long n, float* __restrict__ out) {
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) out[i] = (float) q[i];
 }
@@ -133,8 +239,11 @@ extern "C" int csb_zero_to_min_positive(float* x, int N, long long per, unsigned
 
 extern "C" int csb_leres_depth_tail(const float* logits, int N, int h, int w, int H, int W, unsigned* minmax, uint8_t* q8, float* out, void* stream) {
     CSB_REQUIRE(logits && minmax && q8 && out && N > 0 && h > 0 && w > 0, "bad arguments");
-    CSB_REQUIRE(H >= h && W >= w, "only the INTER_AREA (upscaling / same size) branch of kenburns_effect.py:575-576 runs on the device");
+    const bool lanczos = h > H;                                     // kenburns_effect.py:573-574: k = depth.shape[0] / ori_h > 1 -> INTER_LANCZOS4 (both axes)
+    CSB_REQUIRE(lanczos || (H >= h && W >= w), "INTER_AREA with a shrinking width but growing height is not built (host path)");
     cudaStream_t st = (cudaStream_t) stream;
+    LanczosTab tab;
+    if (lanczos) CSB_TRY(lanczos_tables(h, w, H, W, tab));          // built once per geometry (synchronous upload on first use), then cached
     const long long per = (long long) h * w;
     CSB_TRY(csb::cuda_ok(cudaMemsetAsync(minmax, 0, sizeof(unsigned) * 2 * N, st), "memset"));
     csb::memset_done(st);
@@ -147,6 +256,11 @@ extern "C" int csb_leres_depth_tail(const float* logits, int N, int h, int w, in
     CSB_TRY(csb::launched("k_lt_minmax", st));
     k_lt_quant<<<dim3(gx, N), 256, 0, st>>>(logits, per, minmax, q8);
     CSB_TRY(csb::launched("k_lt_quant", st));
+    if (lanczos) {
+        int gl = (4 * csb::num_sms() + N - 1) / N;
+        k_lt_lanczos<<<dim3(gl < 1 ? 1 : gl, N), 256, 0, st>>>(q8, h, w, H, W, tab.ofs, tab.coef, out);
+        return csb::launched("k_lt_lanczos", st);
+    }
     if (H == h && W == w) {
         k_lt_tofloat<<<csb::wave_grid(per * N, 256, 4), 256, 0, st>>>(q8, per * N, out);
         return csb::launched("k_lt_tofloat", st);

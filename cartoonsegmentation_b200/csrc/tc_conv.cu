@@ -59,7 +59,7 @@ struct ConvKernelParams {
     const void* residual;
     int res_ld, res_coff, res_mode;   // 0 none, 1 add before activation, 2 add after activation
     int act;
-    int gelu_form;               // 0: mixed polynomial / sigmoid-form exact GELU, 1: tanh form (one MUFU per element)
+    int gelu_form;               // 1 (default): tanh form (one MUFU per element), 0: mixed polynomial / sigmoid-form exact GELU
     const float* act_param;      // per-channel PReLU slope
     void* out;
     float* out_f32;
@@ -149,8 +149,9 @@ __device__ __forceinline__ void gelu2_mufu(float& a, float& b) {
     upk2(fmul2(x, pk2(r0, r1)), a, b);
 }
 // Exact-erf GELU on two values in tanh form: gelu(x) = 0.5 x (1 + tanh(g(x))) with the same fitted g(x) = atanh(erf(x / sqrt2)) as gelu2_mufu, through ONE
-// MUFU op per element (tanh.approx.f32) instead of ex2 + rcp: 6 packed + 2 FMNMX + 2 MUFU per PAIR.  Selected per launch (CSB_GELU_FORM=tanh / GM < 0);
-// the accuracy of MUFU.TANH decides whether it may be the default (tools/gelu_check.py measures it against the correctly rounded result).
+// MUFU op per element (tanh.approx.f32) instead of ex2 + rcp: 6 packed + 2 FMNMX + 2 MUFU per PAIR.  The default form (GM < 0); measured against the
+// correctly rounded fp16 GELU over x in [-12, 12] (tools/gelu_check.py): rms abs error 6.4e-5 (polynomial / sigmoid mix: 5.5e-5), outputs that differ from
+// the correctly rounded value 15.5 % (mix: 28 %), same maximum.
 __device__ __forceinline__ void gelu2_tanh(float& a, float& b) {
     const uint64_t x = pk2(a, b);
     float s0, s1;
@@ -176,10 +177,10 @@ constexpr int kGeluMufuPairs = CSB_GELU_MUFU_PAIRS;      // of the 16 pairs of a
 // loads (warp-uniform -> broadcast), 4 x 16 B residual loads, activation on 32 independent values, 4 x 16 B stores.
 template <class T, int ACT, bool LN, int GM = kGeluMufuPairs>
 __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[32], size_t pix, int n0, bool row_ok, bool fast, uint32_t stage,
-                                               const CUtensorMap* tmC, int cw, int chh, int cimg, float neg_mean, float rstd) {
+                                               const CUtensorMap* tmC, int cw, int chh, int cimg, float neg_mean, float rstd, uint32_t stage_any) {
     // stage != 0: this full chunk leaves through shared memory and one TMA tile store per warp (rows outside the image are clipped by the TMA unit;
     // their arithmetic runs on in-bounds addresses because `pix` is clamped by the caller)
-    if (!row_ok && !(stage && fast && !p.out_f32)) return;
+    if (!row_ok && !(stage && fast && !p.out_f32) && !p.out_f32) return;      // (the fp32 path shuffles across the warp: every lane takes part)
     if (fast && !p.out_f32) {
         float y[32];
 #pragma unroll
@@ -262,7 +263,51 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
                               pack2<T>(y[8 * g + 6], y[8 * g + 7]));
         return;
     }
-    // generic path: channel tails, unaligned slices, fp32 outputs (head predictions)
+    // fp32 outputs (head predictions, e.g. the 169 dynamic-kernel channels of RTMDet-Ins): a lane owns one accumulator ROW, so a per-lane store
+    // touches 32 different lines per instruction (the 256 -> 169 head ran at 60 TFLOP/s on exactly that).  The chunk is transposed through the
+    // warp's 2 KiB staging tile, 16 columns at a time, and leaves as 64 B row segments (two rows per store instruction).
+    if (p.out_f32) {
+        const int lane = threadIdx.x & 31;
+        const T* res = p.res_mode ? reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0 : nullptr;
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int c = n0 + j;
+            float v = __uint_as_float(acc[j]);
+            if (c < p.Cout) {
+                if constexpr (LN) v = fmaf(rstd, v, neg_mean * __ldg(p.ln_colsum + c));
+                if (p.bias) v += __ldg(p.bias + c);
+                if (p.res_mode == 1) v += to_f<T>(res[j]);
+                v = apply_act<ACT>(v, p.act_param ? __ldg(p.act_param + c) : 0.25f);
+                if (p.res_mode == 2) v += to_f<T>(res[j]);
+            }
+            y[j] = v;
+        }
+        const unsigned long long obase = (unsigned long long) pix * (unsigned long long) p.out_ld + (unsigned long long) (p.out_coff + n0);
+        const uint32_t my_row = stage_any + (uint32_t) lane * 64u, sw = (uint32_t) ((lane >> 1) & 3);
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                st_shared_v4(my_row + (((uint32_t) g ^ sw) << 4), make_uint4(__float_as_uint(y[16 * hb + 4 * g]), __float_as_uint(y[16 * hb + 4 * g + 1]),
+                                                                         __float_as_uint(y[16 * hb + 4 * g + 2]), __float_as_uint(y[16 * hb + 4 * g + 3])));
+            __syncwarp();
+            const int c = lane & 15;
+            const bool col_ok = n0 + 16 * hb + c < p.Cout;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + (lane >> 4);
+                const unsigned long long ob = __shfl_sync(0xffffffffu, obase, r);
+                const bool ok = __shfl_sync(0xffffffffu, (int) row_ok, r) != 0;
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stage_any + (uint32_t) r * 64u + ((((uint32_t) c >> 2) ^ (uint32_t) ((r >> 1) & 3)) << 4) + (((uint32_t) c & 3u) << 2)));
+                if (ok && col_ok) p.out_f32[ob + (unsigned long long) (16 * hb + c)] = v;
+            }
+        }
+        return;
+    }
+    // generic path: channel tails and unaligned slices
     if (!row_ok) return;
     const T* res = p.res_mode ? reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff + n0 : nullptr;
 #pragma unroll
@@ -275,8 +320,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
         if (p.res_mode == 1) v += to_f<T>(res[j]);
         v = apply_act<ACT>(v, p.act_param ? __ldg(p.act_param + c) : 0.25f);
         if (p.res_mode == 2) v += to_f<T>(res[j]);
-        if (p.out_f32) p.out_f32[pix * p.out_ld + p.out_coff + c] = v;
-        else reinterpret_cast<T*>(p.out)[pix * p.out_ld + p.out_coff + c] = from_f<T>(v);
+        reinterpret_cast<T*>(p.out)[pix * p.out_ld + p.out_coff + c] = from_f<T>(v);
     }
 }
 
@@ -345,7 +389,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
                 __syncwarp();
                 if (lane == 0) release(as);
             }
-            epilogue_chunk<T, ACT, LN, GM>(p, acc, pix, n0, row_ok, fast, stage, tmC, cw, chh, img, neg_mean, rstd);
+            epilogue_chunk<T, ACT, LN, GM>(p, acc, pix, n0, row_ok, fast, stage, tmC, cw, chh, img, neg_mean, rstd, stage_base + (uint32_t) (warp - 4) * 2048u);
         }
         if (++as == kAccStages) { as = 0; aphase ^= 1u; }
     }
@@ -355,7 +399,7 @@ __device__ __forceinline__ void epilogue_role(const ConvKernelParams& p, uint32_
 template <class T, int CG>
 __device__ __forceinline__ void epilogue_dispatch(const ConvKernelParams& p, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, int total_tiles, uint32_t stage_base,
                                                   const CUtensorMap* tmC) {
-    if (p.act == CSB_ACT_GELU && p.gelu_form == 1) {    // tanh-form GELU (experimental, CSB_GELU_FORM=tanh)
+    if (p.act == CSB_ACT_GELU && p.gelu_form == 1) {    // tanh-form GELU (default)
         if (p.ln_stats) epilogue_role<T, CSB_ACT_GELU, CG, true, -1>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
         else epilogue_role<T, CSB_ACT_GELU, CG, false, -1>(p, tmem_base, tfull0, tempty0, total_tiles, stage_base, tmC);
         return;
@@ -523,11 +567,14 @@ CUtensorMapSwizzle swizzle_of(int bk) { return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_
 
 std::atomic<int> g_pair_mode{[] { const char* e = getenv("CSB_CTA_PAIR"); return e ? atoi(e) : 1; }()};
 
-std::atomic<int> g_gelu_form{[] { const char* e = getenv("CSB_GELU_FORM"); return e && (e[0] == 't' || e[0] == '1') ? 1 : 0; }()};
+// tanh form by default: measured on B200 (profiles/r2_gelu_form_ab.md) it is at least as accurate after the fp16 rounding of the output and 2-12 % faster
+// per C -> 4C layer, +3 % on the whole step (fewer FMA-pipe instructions -> less power -> higher clocks under the power cap); CSB_GELU_FORM=poly restores
+// the polynomial / sigmoid mix
+std::atomic<int> g_gelu_form{[] { const char* e = getenv("CSB_GELU_FORM"); return e && (e[0] == 'p' || e[0] == '0') ? 0 : 1; }()};
 
 }  // namespace
 
-// A/B switch of the GELU epilogue form (0 mixed polynomial / sigmoid, 1 tanh); returns the previous form.
+// A/B switch of the GELU epilogue form (0 mixed polynomial / sigmoid, 1 tanh = default); returns the previous form.
 extern "C" int csb_conv_set_gelu_form(int form) { return g_gelu_form.exchange(form); }
 
 // A/B switch of the CTA-pair path for tests and benchmarks (same values as the CSB_CTA_PAIR environment variable); returns the previous mode.

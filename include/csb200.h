@@ -139,8 +139,9 @@ CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, in
 CSB_API int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream);
 
 /* LeReS post-processing -- depth_modules/leres/__init__.py:117-140 (min/max normalise to 16 bit, cv2.convertScaleAbs to 8 bit,
- * bitwise_not) + kenburns_effect.py:572-577 (cv2.resize INTER_AREA back to the frame size, astype(float32)), bit-exact against numpy + OpenCV, for
- * the upscaling / same-size branch.  logits [N,h,w] fp32 -> out [N,H,W] fp32 (8-bit values); minmax: 2*N uint32, q8: N*h*w bytes of scratch. */
+ * bitwise_not) + kenburns_effect.py:572-577 (cv2.resize back to the frame size, astype(float32)), bit-exact against numpy + OpenCV: INTER_AREA for
+ * the upscaling / same-size branch (H >= h and W >= w), INTER_LANCZOS4 (8-tap fixed point, both axes) when h > H as the reference selects it.
+ * logits [N,h,w] fp32 -> out [N,H,W] fp32 (8-bit values); minmax: 2*N uint32, q8: N*h*w bytes of scratch. */
 CSB_API int csb_leres_depth_tail(const float* logits, int N, int h, int w, int H, int W, unsigned* minmax, uint8_t* q8, float* out, void* stream);
 
 /* `depth[depth == 0] = depth[depth > 0].min()` (anime_3dkenburns/kenburns_effect.py:577, :815), per image, in place: x [N, per] fp32,
@@ -272,9 +273,10 @@ CSB_API int csb_conv2d_nhwc(const csb_conv_desc* desc, const void* x, const void
  * depend on the mode beyond fp32 accumulation order (identical: the k-order is unchanged). */
 CSB_API int csb_conv_set_pair_mode(int mode);
 
-/* A-B switch of the conv engine's GELU epilogue: 0 (default) exact-erf GELU evaluated as a mixed degree-19 polynomial / sigmoid form (|error| <= 2.6e-5),
- * 1 the same fitted atanh(erf) argument through one tanh.approx MUFU op per element (fewer FMA-pipe instructions; accuracy bounded by MUFU.TANH).
- * Same as the CSB_GELU_FORM=tanh environment variable; returns the previous form. */
+/* A-B switch of the conv engine's GELU epilogue (exact-erf GELU, mmpretrain ConvNeXtBlock act_cfg=dict(type='GELU')): 1 (default) the fitted
+ * atanh(erf(x / sqrt2)) argument through one tanh.approx MUFU op per element, 0 the round-1 mix of a degree-19 polynomial and the sigmoid form
+ * (|error| <= 2.6e-5).  Both are below the fp16 rounding of the output; the tanh form issues fewer FMA-pipe instructions (profiles/r2_gelu_form_ab.md).
+ * CSB_GELU_FORM=poly / tanh in the environment selects the initial form; returns the previous form. */
 CSB_API int csb_conv_set_gelu_form(int form);
 
 /* Halo-tile path of the conv engine (csrc/tc_halo.cu) for stride-1 RxS convolutions: ONE activation halo box per 64-channel chunk feeds all R*S

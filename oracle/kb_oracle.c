@@ -428,3 +428,69 @@ ORC_API void orc_resize_area_up_u8c1(const uint8_t* src, int sh, int sw, int dh,
     }
     free(xo); free(xa);
 }
+
+/* cv2.resize(src 8UC1, (dw, dh), interpolation=INTER_LANCZOS4) -- the LeReS tail when the estimator output has more rows than the frame,
+ * kenburns_effect.py:573-575.  OpenCV imgproc/src/resize.cpp, in its own two-pass structure: per destination column / row the source offset
+ * sx = cvFloor(fx), fx = (float) ((dx + 0.5) * scale - 0.5) and eight coefficients interpolateLanczos4(fx - sx) (imgwarp.cpp) rounded to
+ * short x 2048 (saturate_cast<short>: cvRound); HResizeLanczos4<uchar,int,short> writes int rows (border taps clamped to the row),
+ * VResizeLanczos4 combines eight rows (row index clipped to the image) in int32 and FixedPtCast<int,uchar,22> rounds: (v + 2^21) >> 22, saturated. */
+static void orc_lanczos4(float x, float* coeffs) {
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    float sum = 0;
+    double y0 = -(x + 3) * 3.1415926535897932384626433832795 * 0.25, s0 = sin(y0), c0 = cos(y0);
+    for (int i = 0; i < 8; i++) {
+        float y0_ = (x + 3 - i);
+        if (fabs(y0_) >= 1e-6f) {
+            double y = -y0_ * 3.1415926535897932384626433832795 * 0.25;
+            coeffs[i] = (float) ((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+        } else {
+            coeffs[i] = 1e30f;
+        }
+        sum += coeffs[i];
+    }
+    sum = 1.f / sum;
+    for (int i = 0; i < 8; i++) coeffs[i] *= sum;
+}
+
+static short orc_sat_short(float v) {
+    long r = lrintf(v);
+    return (short) (r < -32768 ? -32768 : (r > 32767 ? 32767 : r));
+}
+
+ORC_API void orc_resize_lanczos4_u8c1(const uint8_t* src, int sh, int sw, int dh, int dw, uint8_t* dst) {
+    const double scale_x = 1.0 / ((double) dw / sw), scale_y = 1.0 / ((double) dh / sh);
+    int* xofs = (int*) malloc(sizeof(int) * dw);
+    short* alpha = (short*) malloc(sizeof(short) * dw * 8);
+    int* rows = (int*) malloc(sizeof(int) * (size_t) sh * dw);          /* the horizontal pass of every source row */
+    float cb[8];
+    for (int dx = 0; dx < dw; ++dx) {
+        float fx = (float) ((dx + 0.5) * scale_x - 0.5);
+        int sx = (int) floorf(fx);
+        fx -= sx;
+        xofs[dx] = sx;
+        orc_lanczos4(fx, cb);
+        for (int k = 0; k < 8; ++k) alpha[dx * 8 + k] = orc_sat_short(cb[k] * 2048.f);
+    }
+    for (int y = 0; y < sh; ++y)
+        for (int dx = 0; dx < dw; ++dx) {
+            int v = 0;
+            for (int k = 0; k < 8; ++k) v += src[(long) y * sw + clampi(xofs[dx] - 3 + k, 0, sw - 1)] * alpha[dx * 8 + k];
+            rows[(long) y * dw + dx] = v;
+        }
+    for (int dy = 0; dy < dh; ++dy) {
+        float fy = (float) ((dy + 0.5) * scale_y - 0.5);
+        int sy = (int) floorf(fy);
+        fy -= sy;
+        short beta[8];
+        orc_lanczos4(fy, cb);
+        for (int k = 0; k < 8; ++k) beta[k] = orc_sat_short(cb[k] * 2048.f);
+        for (int dx = 0; dx < dw; ++dx) {
+            unsigned v = 0;                                              /* int32 arithmetic as OpenCV's (unsigned here: defined wrap-around) */
+            for (int k = 0; k < 8; ++k) v += (unsigned) (rows[(long) clampi(sy - 3 + k, 0, sh - 1) * dw + dx] * (int) beta[k]);
+            int r = ((int) (v + (1u << 21))) >> 22;
+            dst[(long) dy * dw + dx] = (uint8_t) (r < 0 ? 0 : (r > 255 ? 255 : r));
+        }
+    }
+    free(xofs); free(alpha); free(rows);
+}

@@ -125,8 +125,11 @@ def leres_parity(size=640, seed=77):
 
 
 def main():
-    out = {'device': torch.cuda.get_device_name(0), 'det_1024': det_parity(1024), 'leres_640': leres_parity(640)}
-    if os.environ.get('CSB_PARITY_CSP', '1') != '0':
+    only = sys.argv[2] if len(sys.argv) > 2 else ''
+    out = {'device': torch.cuda.get_device_name(0), 'det_1024': det_parity(1024)}
+    if only != 'det':
+        out['leres_640'] = leres_parity(640)
+    if only != 'det' and os.environ.get('CSB_PARITY_CSP', '1') != '0':
         out['det_1024_cspnext_l'] = det_parity(1024, backbone='cspnext_l')
     s = json.dumps(out, indent=1)
     print(s)

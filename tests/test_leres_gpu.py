@@ -92,6 +92,57 @@ def test_device_tail_equals_host_numpy_opencv(built_lib, hw, HW):
         assert np.array_equal(out[i].cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("hw,HW", [((640, 448), (630, 441)), ((512, 512), (500, 500)), ((96, 128), (90, 131)), ((64, 96), (33, 47)), ((32, 32), (31, 64))])
+def test_device_tail_lanczos_branch_equals_opencv(built_lib, hw, HW):
+    """kenburns_effect.py:573-575: more estimator rows than frame rows -> cv2.resize(..., INTER_LANCZOS4).  The device branch (k_lt_lanczos, OpenCV's
+    8-tap fixed-point arithmetic) == cv2 and == the C restatement, bit for bit, incl. a ringing (0 / 255 stripes) image that saturates."""
+    import ctypes as C
+    import cv2
+    from cartoonsegmentation_b200._lib import check, lib, ptr, stream
+    from cartoonsegmentation_b200.depth_modules.leres import quantise_depth
+    from oracle import kb_oracle
+    (h, w), (H, W) = hw, HW
+    n = 3
+    rng = np.random.default_rng(h + W)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    logits = np.stack([(3 + np.sin(xx / (7.0 + i)) * np.cos(yy / 11.0) * 2 + rng.standard_normal((h, w)) * 0.05).astype(np.float32) for i in range(n)])
+    logits[1] = np.where((yy.astype(int) % 2) == 0, 0.0, 1.0)                    # stripes: every tap overshoots
+    logits[2] = rng.random((h, w), dtype=np.float32)
+    dev = torch.from_numpy(logits).cuda()
+    mm = torch.empty(2 * n, device='cuda', dtype=torch.int32)
+    q8 = torch.empty((n, h, w), device='cuda', dtype=torch.uint8)
+    out = torch.empty((n, H, W), device='cuda', dtype=torch.float32)
+    for _ in range(2):                                                          # second call: cached coefficient tables
+        check(lib().csb_leres_depth_tail(ptr(dev), n, h, w, H, W, ptr(mm), ptr(q8), ptr(out), stream()), "csb_leres_depth_tail")
+    for i in range(n):
+        d8 = quantise_depth(logits[i])
+        assert np.array_equal(q8[i].cpu().numpy(), d8)
+        ref = cv2.resize(d8, (W, H), interpolation=cv2.INTER_LANCZOS4)
+        orc = np.empty((H, W), np.uint8)
+        kb_oracle.lib().orc_resize_lanczos4_u8c1(d8.ctypes.data_as(C.c_void_p), h, w, H, W, orc.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(orc, ref)
+        assert np.array_equal(out[i].cpu().numpy(), ref.astype(np.float32))
+
+
+def test_pipeline_leres_small_frame_takes_device_lanczos(built_lib):
+    """310 x 215 and 310 x 200 frames with depth_est_size 320: scaledown_maxsize rounds the estimator input to 320 x 224 / 320 x 192 -> k > 1 -> LANCZOS4
+    on both axes (the width shrinks or grows), on the device"""
+    from cartoonsegmentation_b200.anime_3dkenburns.kenburns_effect import KenBurnsConfig, KenBurnsPipeline
+    from cartoonsegmentation_b200.utils.synthetic import smooth_image
+    from cartoonsegmentation_b200 import _lib
+    pipe = KenBurnsPipeline(KenBurnsConfig(det_size=320, max_size=1024, num_frame=3, depth_est='leres', depth_est_size=320))
+    for (fh, fw) in ((310, 215), (310, 200)):
+        imgs = [smooth_image(fh, fw, seed=5 + i) for i in range(2)]
+        pipe.leres_host_tail = False
+        l0 = _lib.launch_count()
+        a = pipe._depth_est_leres_batch(imgs)
+        assert _lib.launch_count() > l0
+        pipe.leres_host_tail = True
+        b = pipe._depth_est_leres_batch(imgs)
+        for x, y in zip(a, b):
+            assert x.shape == (1, 1, fh, fw) and torch.equal(x, y)
+
+
 def test_pipeline_leres_device_tail_matches_host_tail(built_lib):
     from cartoonsegmentation_b200.anime_3dkenburns.kenburns_effect import KenBurnsConfig, KenBurnsPipeline
     from cartoonsegmentation_b200.utils.synthetic import smooth_image

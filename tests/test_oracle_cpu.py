@@ -195,3 +195,21 @@ def test_area_upscale_restatement_matches_opencv():
         dst = np.empty((dh, dw), np.uint8)
         L.orc_resize_area_up_u8c1(src.ctypes.data_as(C.c_void_p), sh, sw, dh, dw, dst.ctypes.data_as(C.c_void_p))
         assert np.array_equal(dst, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_AREA))
+
+
+def test_lanczos4_restatement_matches_opencv():
+    """orc_resize_lanczos4_u8c1 (cv2.resize INTER_LANCZOS4 on 8UC1: 8-tap fixed point, the LeReS tail for frames smaller than the estimator input,
+    reference kenburns_effect.py:573-575) == cv2, bit for bit, for shrinking, growing and mixed geometries."""
+    import ctypes as C
+    import cv2
+    from oracle import kb_oracle
+    L = kb_oracle.lib()
+    rng = np.random.default_rng(1)
+    for (sh, sw, dh, dw) in [(640, 448, 630, 441), (512, 512, 500, 500), (96, 128, 90, 131), (64, 96, 33, 47), (40, 40, 39, 40), (32, 32, 31, 64), (17, 9, 16, 5)]:
+        src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        if sh == 512:
+            src[::2] = 255; src[1::2] = 0                         # ringing: exercises the saturation of FixedPtCast
+        dst = np.empty((dh, dw), np.uint8)
+        L.orc_resize_lanczos4_u8c1(src.ctypes.data_as(C.c_void_p), sh, sw, dh, dw, dst.ctypes.data_as(C.c_void_p))
+        ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LANCZOS4)
+        assert np.array_equal(dst, ref), (sh, sw, dh, dw, int(np.abs(dst.astype(int) - ref).max()), float((dst != ref).mean()))

@@ -14,6 +14,9 @@ y = E.conv2d_nhwc(x, w, torch.zeros(64, device='cuda'), act='gelu').float()
 ref = torch.nn.functional.gelu(x.float())
 err = (y - ref.half().float()).abs()        # vs the correctly rounded fp16 result
 print("gelu max abs err %.3e  (rel to |x| max %.3e)" % (err.max().item(), (err / x.float().abs().clamp_min(1)).max().item()))
+ulp = torch.maximum(ref.half().float().abs(), torch.tensor(6.1e-5, device='cuda')).log2().floor().exp2() * 2.0 ** -10        # fp16 ulp at the reference value
+print("gelu error in fp16 ulps of the result: max %.2f  rms %.3f  fraction != correctly rounded %.4f; rms abs err %.3e" %
+      ((err / ulp).max().item(), (err / ulp).pow(2).mean().sqrt().item(), (err > 0).float().mean().item(), err.pow(2).mean().sqrt().item()))
 for (N, H, W, Cin, Cout) in ((32, 64, 64, 512, 2048), (16, 256, 256, 128, 512), (32, 128, 128, 256, 1024)):
     xs = [torch.randn(N, H, W, Cin, device='cuda').half() for _ in range(3)]
     ww = E.pack_conv_weight(torch.randn(Cout, Cin, 1, 1, device='cuda') * Cin ** -0.5)
