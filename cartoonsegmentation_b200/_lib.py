@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libcsb200.so")
+_SO = os.environ.get("CSB200_LIB") or os.path.join(_HERE, "libcsb200.so")        # CSB200_LIB: an A/B build of the same library (build.py)
 _lib = None
 
 

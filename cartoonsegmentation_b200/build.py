@@ -11,10 +11,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-SO = os.path.join(HERE, "libcsb200.so")
+# A/B builds for experiments: CSB_BUILD_SUFFIX=_x CSB_EXTRA_NVCC="-DCSB_MBAR_HINT_NS=0" python -m cartoonsegmentation_b200.build -> libcsb200_x.so,
+# loaded instead of the default library when CSB200_LIB points at it (_lib.py)
+_SUFFIX = os.environ.get("CSB_BUILD_SUFFIX", "")
+OBJ = os.path.join(HERE, "_build" + _SUFFIX)
+SO = os.path.join(HERE, "libcsb200%s.so" % _SUFFIX)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-extended-lambda",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"] + os.environ.get("CSB_EXTRA_NVCC", "").split()
 EXPORT = ["-Xcompiler", "-fvisibility=hidden"]
 
 

@@ -53,28 +53,37 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* keys, int 
 // candidate record written by k_select_level: box[4], score, prior x, prior y, stride, location, level
 constexpr int kRec = 10;
 
-__global__ void __launch_bounds__(1024) k_select_level(Levels lv, int N, float score_thr, int nms_pre, int img_h, int img_w, float* __restrict__ cand,
+__global__ void __launch_bounds__(1024) k_select_level(Levels lv, int N, float score_thr, int nms_pre, int img_h, int img_w, int cap, float* __restrict__ cand,
                                                        int* __restrict__ cand_count) {
-    extern __shared__ unsigned long long keys[];
+    extern __shared__ unsigned long long keys[];          // `cap` keys
     __shared__ int s_count;
     const int lvl = blockIdx.x % lv.L, img = blockIdx.x / lv.L;
     const int h = lv.h[lvl], w = lv.w[lvl], nloc = h * w, stride = lv.stride[lvl];
     const float* cls = lv.cls[lvl] + (size_t) img * nloc;
     const float* reg = lv.reg[lvl] + (size_t) img * nloc * 4;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
-        const float s = 1.0f / (1.0f + expf(-cls[i]));                      // scores = cls.sigmoid()
-        if (s > score_thr) keys[atomicAdd(&s_count, 1)] = ((unsigned long long) __float_as_uint(s) << 32) | (unsigned) (0xffffffffu - (unsigned) i);
+    // Levels with more locations than the shared-memory array holds (det_size > 1024: 160 x 160 at stride 8) go through in chunks: the best nms_pre
+    // keys so far stay at the front, the next chunk's candidates are appended and the array is sorted again.  The key is a total order (score bits,
+    // inverted location), so the result does not depend on the chunking; a level that fits is one chunk, as before.
+    const int chunk = nloc <= cap ? nloc : cap - nms_pre;
+    int take = 0;
+    for (int c0 = 0; c0 < nloc; c0 += chunk) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = take;
+        __syncthreads();
+        const int c1 = c0 + chunk < nloc ? c0 + chunk : nloc;
+        for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            const float s = 1.0f / (1.0f + expf(-cls[i]));                  // scores = cls.sigmoid()
+            if (s > score_thr) keys[atomicAdd(&s_count, 1)] = ((unsigned long long) __float_as_uint(s) << 32) | (unsigned) (0xffffffffu - (unsigned) i);
+        }
+        __syncthreads();
+        const int count = s_count;
+        int p2 = 1;
+        while (p2 < count) p2 <<= 1;
+        for (int i = count + threadIdx.x; i < p2; i += blockDim.x) keys[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc(keys, p2);
+        take = count < nms_pre ? count : nms_pre;
     }
-    __syncthreads();
-    const int count = s_count;
-    int p2 = 1;
-    while (p2 < count) p2 <<= 1;
-    for (int i = count + threadIdx.x; i < p2; i += blockDim.x) keys[i] = 0ull;
-    __syncthreads();
-    bitonic_sort_desc(keys, p2);
-    const int take = count < nms_pre ? count : nms_pre;
     float* out = cand + ((size_t) img * lv.L + lvl) * nms_pre * kRec;
     for (int i = threadIdx.x; i < take; i += blockDim.x) {
         const unsigned long long k = keys[i];
@@ -436,14 +445,15 @@ extern "C" int csb_rtmdet_select(const float* const* cls, const float* const* re
     }
     int p2 = 1;
     while (p2 < maxloc) p2 <<= 1;
-    CSB_REQUIRE((size_t) p2 * 8 <= 200 * 1024, "level too large for the shared-memory sort: the location count is padded to a power of two and must be <= 16384 per level (det_size <= 1024)");
+    if (p2 > 16384) p2 = 16384;                            // larger levels are sorted in chunks of (16384 - nms_pre) locations (k_select_level)
+    CSB_REQUIRE(nms_pre > 0 && nms_pre <= 4096, "nms_pre must be in [1, 4096]");
     cudaStream_t st = (cudaStream_t) stream;
     static unsigned char attr_done[64] = {};
     if (csb::first_use_on_device(attr_done)) {          // per device, not per process
         cudaFuncSetAttribute(k_select_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
-    k_select_level<<<N * L, 1024, (size_t) p2 * 8, st>>>(lv, N, score_thr, nms_pre, img_h, img_w, cand, cand_count);
+    k_select_level<<<N * L, 1024, (size_t) p2 * 8, st>>>(lv, N, score_thr, nms_pre, img_h, img_w, p2, cand, cand_count);
     CSB_TRY(csb::launched("k_select_level", st));
     const int cap = L * nms_pre;
     int q2 = 1;

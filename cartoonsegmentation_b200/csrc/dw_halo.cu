@@ -39,16 +39,37 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// bounded wait: a broken pipeline traps (the launch reports an error) instead of hanging the GPU
+// Bounded wait: a broken pipeline traps (the launch reports an error) instead of hanging the GPU.  The try_wait carries a suspend-time hint: the
+// hardware parks the warp until the phase completes or the hint elapses, instead of returning after a few tens of nanoseconds -- ncu of the round-1
+// loop (profiles/r2_ncu_fc1.md) showed about half of all issued warp instructions of a GEMM launch in these polling loops (ISETP / IMAD / BRA of the
+// producer, MMA and epilogue warps), i.e. issue slots and power taken from the epilogue.  CSB_MBAR_HINT_NS=0 compiles the old loop.
+#ifndef CSB_MBAR_HINT_NS
+#define CSB_MBAR_HINT_NS 4000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if CSB_MBAR_HINT_NS > 0
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 1;; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t) CSB_MBAR_HINT_NS) : "memory");
+        if (ok) return;
+        if ((spin & 255u) == 0) {                                       // every 256 returns without completion (about 1 ms when the hint is honoured)
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+    }
+#else
     uint32_t ok = 0;
     long long t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
         if (spin == 64) t0 = clock64();
         if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
+#endif
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"

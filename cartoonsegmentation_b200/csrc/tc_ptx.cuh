@@ -24,8 +24,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a broken pipeline traps (the launch reports an error) instead of hanging the GPU.
+// Bounded wait: a broken pipeline traps (the launch reports an error) instead of hanging the GPU.  The try_wait carries a suspend-time hint: the
+// hardware parks the warp until the phase completes or the hint elapses, instead of returning after a few tens of nanoseconds -- ncu of the round-1
+// loop (profiles/r2_ncu_fc1.md) showed about half of all issued warp instructions of a GEMM launch in these polling loops (ISETP / IMAD / BRA of the
+// producer, MMA and epilogue warps), i.e. issue slots and power taken from the epilogue.  CSB_MBAR_HINT_NS=0 compiles the old loop.
+#ifndef CSB_MBAR_HINT_NS
+#define CSB_MBAR_HINT_NS 4000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if CSB_MBAR_HINT_NS > 0
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 1;; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t) CSB_MBAR_HINT_NS) : "memory");
+        if (ok) return;
+        if ((spin & 255u) == 0) {                                       // every 256 returns without completion (about 1 ms when the hint is honoured)
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+    }
+#else
     uint32_t ok = 0;
     long long t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
@@ -35,6 +54,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (spin == 64) t0 = clock64();
         if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
+#endif
 }
 // CG = 2 (CTA pair, tcgen05 cta_group::2): the load lands in THIS CTA's shared memory but signals the mbarrier of the pair's leader CTA
 // (`bar` is then a shared::cluster address obtained with mapa), which the .cta_group::2 form of the instruction permits.

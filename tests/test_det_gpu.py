@@ -111,6 +111,29 @@ def test_postprocess_on_oracle_heads_is_exact(env, size, cfg):
     assert (m != masks).float().mean().item() < 1e-4
 
 
+@pytest.mark.parametrize("size,nms_pre", [(1280, 1000), (1536, 300)])
+def test_selection_above_1024_chunked_topk_is_exact(env, size, nms_pre):
+    """det_size > 1024: the stride-8 level has more locations (25600 / 36864) than the shared-memory sort holds (16384 keys) and is selected in
+    chunks; top-k, decode and NMS must still equal the oracle's torch.topk / batched_nms on identical random head tensors, in the same order."""
+    A = env['A']
+    g = torch.Generator().manual_seed(size)
+    shapes = [(size // 8, size // 8), (size // 16, size // 16), (size // 32, size // 32)]
+    o_cls = [torch.randn((1, 1, h, w), generator=g) * 1.5 - 1.0 for h, w in shapes]          # ~45 % of the locations pass score_thr = 0.05... all chunks matter
+    o_reg = [torch.rand((1, 4, h, w), generator=g) * 60 + 4 for h, w in shapes]
+    o_ker = [torch.randn((1, 169, h, w), generator=g) for h, w in shapes]
+    ocfg = dict(D.DEFAULT_TEST_CFG, nms_pre=nms_pre)
+    boxes, scores, labels, kern, pri = D.decode_and_select(o_cls, o_reg, o_ker, D.RTMDetIns().bbox_head.strides, (size, size), ocfg)
+    tcfg = dict(nms_pre=nms_pre, score_thr=ocfg['score_thr'], nms=dict(iou_threshold=ocfg['iou_threshold']), max_per_img=ocfg['max_per_img'],
+                min_bbox_size=ocfg['min_bbox_size'], mask_thr_binary=ocfg['mask_thr_binary'])
+    mf = torch.zeros((1, shapes[0][0], shapes[0][1], 8), device='cuda')
+    out = A.rtmdet_postprocess(_to_nhwc(o_cls), _to_nhwc(o_reg), _to_nhwc(o_ker), mf, (size, size), tcfg)
+    k = int(out['num'][0])
+    assert k == len(boxes) and k > 10
+    assert torch.equal(out['boxes'][0, :k].cpu(), boxes)
+    assert (out['scores'][0, :k].cpu() - scores).abs().max().item() < 1e-6
+    assert torch.equal(out['kernels'][0, :k].cpu(), kern) and torch.equal(out['priors'][0, :k].cpu(), pri)
+
+
 def test_postprocess_edge_cases(env):
     A = env['A']
     N, cfgd = 2, dict(nms_pre=1000, score_thr=0.05, nms=dict(iou_threshold=0.6), max_per_img=100, min_bbox_size=0, mask_thr_binary=0.5)
