@@ -4,6 +4,7 @@ Functional layer (this part of the file): the tensor math of `generate_kenburns_
 of the `process_kenburns` frame loop (reference :1028-1040, 1069-1070) on the GPU through the C ABI.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -538,7 +539,7 @@ class KenBurnsPipeline:
 
     # ---- batched per-frame path (extension; the reference is a batch-1 loop over exactly these calls)
     def render_frame_batch(self, imgs, shift_u: float = 40.0, shift_v: float = -25.0, depth_ratio: float = 0.8, crop_frac: float = 0.97,
-                           raw_disparity=None, segment: bool = True, warp: bool = True, out_host=None, det_sub: int = 32, zoe_sub: int = 16):
+                           raw_disparity=None, segment: bool = True, warp: bool = True, out_host=None, det_sub: int = None, zoe_sub: int = 16):
         """One Ken-Burns frame per input frame, for a batch of equally sized frames -- per frame exactly the reference's sequence
         `AnimeInsSeg.infer` body (:862-872, refine off) -> `_depth_est` (:563-581 / :812-818) -> `depth_adjustment_animesseg` (:604) ->
         disparity -> cloud (:928-937) -> `process_shift` at camera offset (shift_u, shift_v) with the closest depth scaled by `depth_ratio`
@@ -563,19 +564,43 @@ class KenBurnsPipeline:
                 'data': [torch.empty((1, 4, H * W), device=dev) for _ in range(2)], 'scalars': torch.empty(8, device=dev),
                 'd2c': torch.empty(64, device=dev, dtype=torch.int64), 'shift': torch.empty(3, device=dev),
                 'out': torch.empty((B, H, W, 3), device=dev, dtype=torch.uint8)}
+        if det_sub is None:                                          # measured (gpurun r2c23): e2e 85.2 / 85.7 / 90.0 ms per 32 frames with sub-batches of 32 / 16 / 8
+            det_sub = int(os.environ.get('CSB_E2E_DET_SUB', '32'))
+        h2d_done = {}
         if imgs.is_cuda:
             batch = imgs
-        else:                                                        # H2D of this call's inputs (asynchronous from pinned memory)
-            batch = st['stage']
-            batch.copy_(imgs, non_blocking=True)
+        else:                                                        # H2D of this call's inputs from pinned memory, on the copy stream, one event per
+            batch = st['stage']                                      # detector sub-batch: only the first chunk's copy is exposed
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream.wait_stream(torch.cuda.current_stream())           # the staging buffer's previous consumers have finished
+            with torch.cuda.stream(self._copy_stream):
+                for s0 in range(0, B, det_sub if segment else B):
+                    s1 = min(B, s0 + (det_sub if segment else B))
+                    batch[s0:s1].copy_(imgs[s0:s1], non_blocking=True)
+                    h2d_done[s0] = torch.cuda.Event()
+                    h2d_done[s0].record(self._copy_stream)
+            if not segment:
+                torch.cuda.current_stream().wait_event(h2d_done.pop(0))
         cd = C.c_double
         focal, baseline = float(cfg.focal), float(cfg.baseline)
-        # ---- depth: LeReS is enqueued first, so that its (device-side) tail overlaps nothing on the host; ZoeDepth in sub-batches
+        # ---- segmentation (A1-A9): detector forward + post-process per sub-batch (each waits only for its own frames' H2D)
+        masks, nums_dev = [], []
+        if segment:
+            from ..animeinsseg import rtmdet_postprocess
+            seg = self.animeinsseg
+            test_cfg = seg.model.bbox_head.test_cfg
+            for s0 in range(0, B, det_sub):
+                if s0 in h2d_done:
+                    torch.cuda.current_stream().wait_event(h2d_done[s0])
+                cls, reg, ker, mf = seg.model.net.forward(batch[s0:s0 + det_sub])
+                o = rtmdet_postprocess(cls, reg, ker, mf, (H, W), test_cfg)
+                masks.append(o['masks']); nums_dev.append(o['num'])
+        # ---- depth over the whole batch: LeReS (tail on the device) or ZoeDepth in sub-batches
         disp = raw_disparity
-        handle = None
         if disp is None:
             if cfg.depth_est == 'leres':
-                handle = self.leres_enqueue(None, imgs_dev=batch)
+                disp = self.leres_finish_batch(self.leres_enqueue(None, imgs_dev=batch))
             elif cfg.depth_est == 'zoe':
                 disp = torch.empty((B, H, W), device=dev, dtype=torch.float32)
                 for s0 in range(0, B, zoe_sub):
@@ -584,18 +609,6 @@ class KenBurnsPipeline:
                         self.depth_zoe.disparity(d[i], focal, baseline, out=disp[s0 + i])
             else:
                 raise NotImplementedError(f"render_frame_batch: depth_est '{cfg.depth_est}' (pass raw_disparity=)")
-        # ---- segmentation (A1-A9): detector forward + post-process per sub-batch
-        masks, nums_dev = [], []
-        if segment:
-            from ..animeinsseg import rtmdet_postprocess
-            seg = self.animeinsseg
-            test_cfg = seg.model.bbox_head.test_cfg
-            for s0 in range(0, B, det_sub):
-                cls, reg, ker, mf = seg.model.net.forward(batch[s0:s0 + det_sub])
-                o = rtmdet_postprocess(cls, reg, ker, mf, (H, W), test_cfg)
-                masks.append(o['masks']); nums_dev.append(o['num'])
-        if handle is not None:
-            disp = self.leres_finish_batch(handle)
         disp = disp.reshape(B, H, W)
         nums = None
         if segment:
