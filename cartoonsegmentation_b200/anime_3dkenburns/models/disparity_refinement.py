@@ -122,14 +122,12 @@ class Refine:
         dev = self.dev
         img, disp = tenImage.float().to(dev), tenDisparity.float().to(dev)
         assert img.shape[0] == 1 and disp.shape[0] == 1, "the reference normalises over the whole batch tensor; batch 1 only"
-        m_i, s_i = img.mean(), img.std(unbiased=False)                                                 # :99-100 (tiny reductions: torch)
-        m_d, s_d = disp.mean(), disp.std(unbiased=False)
+        from .utils import net_output, pack_norm16, tensor_stats
+        st_i, st_d = tensor_stats(img), tensor_stats(disp)                                             # :99-100: {mean, std} on the device
         _, _, H, W = img.shape
         h, w = disp.shape[2:]
-        xi = torch.zeros((1, H, W, 16), device=dev, dtype=torch.float16)
-        xi[0, ..., :3] = ((img - m_i) / (s_i + 0.0000001))[0].permute(1, 2, 0)
-        xd = torch.zeros((1, h, w, 16), device=dev, dtype=torch.float16)
-        xd[0, ..., 0] = ((disp - m_d) / (s_d + 0.0000001))[0, 0]
+        xi = pack_norm16(img, st_i)                                                                    # [(img - m) / (s + 1e-7) (3) | zeros]
+        xd = pack_norm16(disp, st_d)
         cat1 = self._buf(1, H, W, 72)                                                                  # [imageOne(24) | upsample(48)]
         self._basic("netImageOne", xi, out=cat1, out_coff=0)
         one = cat1                                                                                     # channels 0..23 (+ the rest read as zero taps... see _down)
@@ -152,5 +150,4 @@ class Refine:
         self._up("netDisparityThr", cat2, cat1, 24)
         fou = self._basic("netDisparityFou", cat1)
         ref = self._basic("netRefine", fou, out_f32=True)                                              # [1,H,W,1] fp32
-        out = ref[..., 0][:, None] * (s_d + 0.0000001) + m_d                                           # :128-129
-        return torch.nn.functional.threshold(out, 0.0, 0.0)
+        return net_output(ref, None, st_d, 2)                                                          # :128-135: * (s + 1e-7) + m, threshold at 0 -> [1,1,H,W]

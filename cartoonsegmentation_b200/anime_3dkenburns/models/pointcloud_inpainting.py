@@ -140,24 +140,17 @@ class Inpaint:
         _, _, H, W = img.shape
         assert H % 8 == 0 and W % 8 == 0
         focal, baseline = objCommon['fltFocal'], objCommon['fltBaseline']
-        # :117-120 -- geometry of the raw frame (valid-masked points), same fused kernel as generate_kenburns_config but with eps 1e-7 here
-        tenDepth = (focal * baseline) / (disp + 0.0000001)
-        from .utils import depth_to_points, spatial_filter
-        tenValid = (spatial_filter(disp / disp.max(), 'laplacian').abs() < 0.03).float()
-        tenPoints = depth_to_points(tenDepth * tenValid, focal).view(1, 3, -1)
-        # :122-131 -- per-tensor normalisation (tiny reductions: torch)
-        m_i, s_i = img.mean(), img.std(unbiased=False)
-        m_d, s_d = disp.mean(), disp.std(unbiased=False)
-        img_n = (img - m_i) / (s_i + 0.0000001)
-        disp_n = (disp - m_d) / (s_d + 0.0000001)
-        x16 = torch.zeros((1, H, W, 16), device=dev, dtype=torch.float16)
-        x16[0, ..., :3] = img_n[0].permute(1, 2, 0)
-        x16[0, ..., 3] = disp_n[0, 0]
+        # :117-120 -- geometry of the raw frame: depth = fb / (disp + 1e-7), valid = |laplacian(disp / max)| < 0.03, points of depth * valid (one kernel)
+        from .utils import net_output, pack_norm16, tensor_stats
+        st_i, st_d = tensor_stats(img), tensor_stats(disp)                                               # {mean, std, max} on the device
+        tenPoints = torch.empty((1, 3, H * W), device=dev, dtype=torch.float32)
+        check(lib().csb_inpaint_points(ptr(disp), H, W, C.c_double(focal), C.c_double(baseline), ptr(st_d), ptr(tenPoints), stream()), "csb_inpaint_points")
+        # :122-131 -- per-tensor normalisation, packed as the NHWC fp16 input [img_n(3) | disp_n(1) | zeros]
+        x16 = pack_norm16(img, st_i, disp, st_d)
         c0, sl0, c1, sl1 = self.ctx
         ctx = c1(c0(x16, pad=1, act='prelu', act_param=sl0), pad=1, act='prelu', act_param=sl1)          # [1,H,W,64]
         payload = torch.empty((H * W, 72), device=dev, dtype=torch.float16)                               # [img(3) | disp(1) | context(64) | pad]
-        payload[:, :4] = x16[0, ..., :4].reshape(-1, 4)
-        payload[:, 4:68] = ctx.view(-1, 64)
+        check(lib().csb_inpaint_payload(ptr(x16), ptr(ctx), C.c_longlong(H * W), ptr(payload), stream()), "csb_inpaint_payload")
         # :135-142 -- context render + coverage median + masking, written as netInput's NHWC input
         sh = [float(v) for v in torch.as_tensor(tenShift).flatten().tolist()]
         CP = lib().csb_render_acc_channels(68)
@@ -184,10 +177,9 @@ class Inpaint:
                 if r != 3:
                     self._up_into((r, c), col[r + 1], col[r])
         out = {}
-        for k in ("netImage", "netDisparity"):
+        for k, st_k, post in (("netImage", st_i, 1), ("netDisparity", st_d, 2)):
             h0, slh, h1, hsc = self.head[k]
-            y = h1(h0(col[0], pad=1, act='prelu', act_param=slh), pad=1, out_f32=True) + hsc(col[0], out_f32=True)      # [1,H,W,c] fp32
-            out[k] = y.permute(0, 3, 1, 2).contiguous()
-        tenImage = (out["netImage"] * (s_i + 0.0000001) + m_i).clip(0.0, 1.0)                              # :190-192, :199 (eval mode)
-        tenDisp = torch.nn.functional.threshold(out["netDisparity"] * (s_d + 0.0000001) + m_d, 0.0, 0.0)   # :194-196, :200
+            # :190-200 (eval mode): (head + shortcut) * (std + 1e-7) + mean, image clipped to [0, 1], disparity thresholded at 0 -> [1,c,H,W] fp32
+            out[k] = net_output(h1(h0(col[0], pad=1, act='prelu', act_param=slh), pad=1, out_f32=True), hsc(col[0], out_f32=True), st_k, post)
+        tenImage, tenDisp = out["netImage"], out["netDisparity"]
         return {'tenExisting': existing, 'tenImage': tenImage, 'tenDisparity': tenDisp, 'segmasks': None}

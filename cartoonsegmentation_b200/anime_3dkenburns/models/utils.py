@@ -94,3 +94,33 @@ def render_degrid(zkey):
     zee = torch.empty((B, 1, H, W), device=zkey.device, dtype=torch.float32)
     check(lib().csb_pointcloud_degrid(ptr(zkey), B, H, W, ptr(zee), stream()), "csb_pointcloud_degrid")
     return zee
+
+
+def tensor_stats(x):
+    """{mean, population std, max} of a contiguous fp32 CUDA tensor on the device -> float32 [3] (csb_tensor_stats; no host read)."""
+    x = _f32(x)
+    scratch = torch.empty(3, device=x.device, dtype=torch.float64)
+    out = torch.empty(3, device=x.device, dtype=torch.float32)
+    check(lib().csb_tensor_stats(ptr(x), C.c_longlong(x.numel()), ptr(scratch), ptr(out), stream()), "csb_tensor_stats")
+    return out
+
+
+def pack_norm16(a, stats_a, b=None, stats_b=None, eps=0.0000001):
+    """[1,ca,H,W] (+ [1,cb,H,W]) fp32 -> [1,H,W,16] fp16 = [(a - mean) / (std + eps) | (b - mean) / (std + eps) | zeros] (csb_pack_norm16)."""
+    a = _f32(a)
+    _, ca, H, W = a.shape
+    cb = 0
+    if b is not None:
+        b = _f32(b)
+        cb = b.shape[1]
+    out = torch.empty((1, H, W, 16), device=a.device, dtype=torch.float16)
+    check(lib().csb_pack_norm16(ptr(a), ca, ptr(stats_a), ptr(b), cb, ptr(stats_b), C.c_longlong(H * W), C.c_float(eps), ptr(out), stream()), "csb_pack_norm16")
+    return out
+
+
+def net_output(a_nhwc, b_nhwc, stats, post, eps=0.0000001):
+    """(a [+ b]) [1,H,W,C] fp32 -> [1,C,H,W] fp32 = post(x * (std + eps) + mean); post: 0 none, 1 clip to [0,1], 2 threshold at 0 (csb_net_output)."""
+    _, H, W, Cc = a_nhwc.shape
+    out = torch.empty((1, Cc, H, W), device=a_nhwc.device, dtype=torch.float32)
+    check(lib().csb_net_output(ptr(a_nhwc), ptr(b_nhwc), Cc, C.c_longlong(H * W), ptr(stats), C.c_float(eps), post, ptr(out), stream()), "csb_net_output")
+    return out

@@ -138,6 +138,21 @@ CSB_API int csb_frame_crop_resize(const uint8_t* frame, int H, int W, int pw, in
 /* cv2.resize(src, (Wo,Ho), interpolation=INTER_LINEAR) on uint8 HWC images, bit-exact (used for scaledown_maxsize, utils/io_utils.py:254-274). */
 CSB_API int csb_resize_u8c3(const uint8_t* src, int H, int W, uint8_t* dst, int Ho, int Wo, void* stream);
 
+/* Input / output glue of the per-image Ken-Burns networks (csrc/kb_netio.cu), replacing the eager per-tensor ops around the reference's Inpaint and
+ * Refine nets (anime_3dkenburns/models/pointcloud_inpainting.py:117-131, 190-200; disparity_refinement.py:99-100, 128-135):
+ *   csb_tensor_stats     out[3] = {mean, population std (torch.std(unbiased=False)), max} of x[n] (double accumulation); scratch: 3 doubles
+ *   csb_pack_norm16      out [HW][16] fp16 = [(a - mean_a) / (std_a + eps) (ca planes of [ca][HW] fp32) | the same for b (cb planes) | zeros];
+ *                        stats_a / stats_b = csb_tensor_stats outputs (null: copy without normalisation)
+ *   csb_inpaint_payload  payload [HW][72] fp16 = [x16[:, 0:4] | ctx [HW][64] | zeros(4)]: the interleaved payload of csb_inpaint_context_render
+ *   csb_net_output       out [C][HW] fp32 = post((a [+ b]) [HW][C] * (std + eps) + mean), post: 0 none, 1 clip to [0, 1], 2 threshold at 0
+ *   csb_inpaint_points   valid-masked cloud of the raw frame (:117-120): points [3][HW] from disp [H][W]; stats = csb_tensor_stats(disp) (uses the max) */
+CSB_API int csb_tensor_stats(const float* x, long long n, double* scratch, float* out, void* stream);
+CSB_API int csb_pack_norm16(const float* a, int ca, const float* stats_a, const float* b, int cb, const float* stats_b, long long HW, float eps, void* out16,
+                            void* stream);
+CSB_API int csb_inpaint_payload(const void* x16, const void* ctx64, long long HW, void* payload72, void* stream);
+CSB_API int csb_net_output(const float* a, const float* b, int C, long long HW, const float* stats, float eps, int post, float* out_nchw, void* stream);
+CSB_API int csb_inpaint_points(const float* disp, int H, int W, double focal, double baseline, const float* stats, float* points, void* stream);
+
 /* LeReS post-processing -- depth_modules/leres/__init__.py:117-140 (min/max normalise to 16 bit, cv2.convertScaleAbs to 8 bit,
  * bitwise_not) + kenburns_effect.py:572-577 (cv2.resize back to the frame size, astype(float32)), bit-exact against numpy + OpenCV: INTER_AREA for
  * the upscaling / same-size branch (H >= h and W >= w), INTER_LANCZOS4 (8-tap fixed point, both axes) when h > H as the reference selects it.

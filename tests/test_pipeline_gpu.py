@@ -177,3 +177,50 @@ def test_depth_adjustment_median_and_resized_variants(built_lib):
         b = AO.depth_adjustment_animesseg(masks, small.clone(), img, use_medium=um)
         assert a.shape == b.shape == small.shape
         assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item()      # two bilinear resamplings: fp32 rounding order only
+
+
+@pytest.mark.gpu
+def test_net_io_kernels_equal_the_torch_ops_of_the_reference(built_lib):
+    """csrc/kb_netio.cu against the eager torch expressions of pointcloud_inpainting.py:117-131, 190-200 and disparity_refinement.py:99-100, 128-135:
+    statistics to fp32 rounding; every elementwise kernel BIT-EXACT when fed the same statistics."""
+    import ctypes as C
+    from cartoonsegmentation_b200._lib import check, lib, ptr, stream
+    from cartoonsegmentation_b200.anime_3dkenburns.models import utils as U
+    H, W, focal, baseline = 104, 136, 512.0, 40.0
+    g = torch.Generator(device='cuda').manual_seed(5)
+    img = torch.rand((1, 3, H, W), device='cuda', generator=g)
+    disp = (torch.from_numpy(smooth_disparity(H, W, seed=3)).cuda().reshape(1, 1, H, W) * 0.7 + 0.05).contiguous()
+    # ---- statistics
+    for t in (img, disp):
+        st = U.tensor_stats(t).cpu()
+        ref = torch.stack([t.mean(), t.std(unbiased=False), t.max()]).cpu()
+        assert (st - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() and st[2] == ref[2]
+    st_i = torch.stack([img.mean(), img.std(unbiased=False), img.max()]).contiguous()            # torch's own statistics -> exact comparisons below
+    st_d = torch.stack([disp.mean(), disp.std(unbiased=False), disp.max()]).contiguous()
+    # ---- normalise + pack
+    x16 = U.pack_norm16(img, st_i, disp, st_d)
+    ref16 = torch.zeros((1, H, W, 16), device='cuda', dtype=torch.float16)
+    ref16[0, ..., :3] = ((img - st_i[0]) / (st_i[1] + 0.0000001))[0].permute(1, 2, 0)
+    ref16[0, ..., 3] = ((disp - st_d[0]) / (st_d[1] + 0.0000001))[0, 0]
+    assert torch.equal(x16, ref16)
+    xd = U.pack_norm16(disp, st_d)
+    assert torch.equal(xd[..., 0], ref16[..., 3]) and not xd[..., 1:].any()
+    # ---- payload
+    ctx = torch.randn((1, H, W, 64), device='cuda', generator=g).half()
+    payload = torch.empty((H * W, 72), device='cuda', dtype=torch.float16)
+    check(lib().csb_inpaint_payload(ptr(x16), ptr(ctx), C.c_longlong(H * W), ptr(payload), stream()), "csb_inpaint_payload")
+    assert torch.equal(payload[:, :4], x16[0, ..., :4].reshape(-1, 4)) and torch.equal(payload[:, 4:68], ctx.view(-1, 64)) and not payload[:, 68:].any()
+    # ---- valid-masked cloud of the raw frame
+    pts = torch.empty((1, 3, H * W), device='cuda')
+    check(lib().csb_inpaint_points(ptr(disp), H, W, C.c_double(focal), C.c_double(baseline), ptr(st_d), ptr(pts), stream()), "csb_inpaint_points")
+    tenDepth = (focal * baseline) / (disp + 0.0000001)
+    tenValid = (U.spatial_filter(disp / disp.max(), 'laplacian').abs() < 0.03).float()
+    ref_pts = U.depth_to_points(tenDepth * tenValid, focal).view(1, 3, -1)
+    assert 0.05 < tenValid.mean().item() < 1.0 and torch.equal(pts, ref_pts)
+    # ---- output: de-normalise, clip / threshold, NHWC -> NCHW
+    a, b = torch.randn((1, H, W, 3), device='cuda', generator=g), torch.randn((1, H, W, 3), device='cuda', generator=g)
+    out = U.net_output(a, b, st_i, 1)
+    assert torch.equal(out, ((a + b).permute(0, 3, 1, 2) * (st_i[1] + 0.0000001) + st_i[0]).clip(0.0, 1.0))
+    d1 = torch.randn((1, H, W, 1), device='cuda', generator=g)
+    out = U.net_output(d1, None, st_d, 2)
+    assert torch.equal(out, torch.nn.functional.threshold(d1[..., 0][:, None] * (st_d[1] + 0.0000001) + st_d[0], 0.0, 0.0))
