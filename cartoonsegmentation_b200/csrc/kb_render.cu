@@ -59,17 +59,17 @@ __device__ __forceinline__ void apply_shift(float& x, float& y, float& z, float 
 __device__ __forceinline__ Proj project(float x, float y, float z, int H, int W, double focal, double focal_baseline) {
     Proj p;
     p.ok = false;
-    if ((double) z < 0.001) return p;                                          // :82
+    if (z < 0.001f) return p;                                                  // :82  (double) z < 0.001: float(0.001) is the smallest float >= 0.001, so the float compare decides identically
     float nx = 0.0f - x, ny = 0.0f - y, nz = 0.0f - z;                         // fltLineVector :80
     float s = __fmaf_rn(0.0f, nx, __fmul_rn(0.0f, ny));                        // x/y terms of both dot products
     float num = __fadd_rn(__fsub_rn((float) focal, z), s);                     // :86
     float den = __fadd_rn(nz, s);                                              // :87
     float dist = __fdiv_rn(num, den);                                          // :88
-    if (fabs((double) den) < 0.001) return p;                                  // :90
+    if (fabsf(den) < 0.001f) return p;                                         // :90  (same argument)
     float ix = __fmaf_rn(nx, dist, x);                                         // :94
     float iy = __fmaf_rn(ny, dist, y);
-    p.ox = (float) (((double) ix + (0.5 * W)) - 0.5);                          // :96
-    p.oy = (float) (((double) iy + (0.5 * H)) - 0.5);                          // :97
+    p.ox = __fadd_rn(ix, (float) (0.5 * W - 0.5));                             // :96  the double sum is exact and rounded once: one float add of the exact constant
+    p.oy = __fadd_rn(iy, (float) (0.5 * H - 0.5));                             // :97
     p.err = (float) (1000000.0 - (focal_baseline / ((double) z + 0.0000001))); // :99
     p.x0 = (int) floorf(p.ox);
     p.y0 = (int) floorf(p.oy);
@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(256) k_degrid(const int* __restrict__ zkey, in
             int x1 = x + ox[k], y1 = y + oy[k], x2 = x - ox[k], y2 = y - oy[k];
             if (x1 < 0 || x1 >= W || y1 < 0 || y1 >= H || x2 < 0 || x2 >= W || y2 < 0 || y2 >= H) continue;
             float a = zv(y1, x1), d = zv(y2, x2);
-            if ((double) c >= (double) a + 1.0 && (double) c >= (double) d + 1.0) {   // :187-188
+            // :187-188 compares in double: c >= a + 1.0 with the sum exact.  For floats c, a that is c >= (smallest float >= a + 1) = add.ru
+            if (c >= __fadd_ru(a, 1.0f) && c >= __fadd_ru(d, 1.0f)) {
                 cnt += 2;
                 sum = __fadd_rn(sum, a);
                 sum = __fadd_rn(sum, d);
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256) k_splat(const float* __restrict__ pts, co
             off[k] = 0;
             if (cx >= 0 && cx < W && cy >= 0 && cy < H) {
                 size_t o = (size_t) cy * W + cx;
-                if ((double) p.err <= (double) __ldg(Z + o) + 1.0) {                      // :269
+                if (p.err <= __fadd_rd(__ldg(Z + o), 1.0f)) {                             // :269 in double; err <= z + 1 <=> err <= (largest float <= z + 1) = add.rd
                     pass |= 1u << k;
                     off[k] = o * CP;
                 }
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) k_splat_h16(const float* __restrict__ pts
             off[k] = 0;
             if (cx >= 0 && cx < W && cy >= 0 && cy < H) {
                 size_t o = (size_t) cy * W + cx;
-                if ((double) p.err <= (double) __ldg(zee + o) + 1.0) { pass |= 1u << k; off[k] = o * CP; }
+                if (p.err <= __fadd_rd(__ldg(zee + o), 1.0f)) { pass |= 1u << k; off[k] = o * CP; }
             }
         }
         if (!pass) continue;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) k_cover_batched(const float* __restrict__
             if (cx < 0 || cx >= W || cy < 0 || cy >= H) continue;
             if (!(p.w[k] >= 1.17549435e-38f)) continue;
             size_t o = (size_t) cy * W + cx;
-            if ((double) p.err <= (double) __ldg(Z + o) + 1.0) Cv[o] = 1;
+            if (p.err <= __fadd_rd(__ldg(Z + o), 1.0f)) Cv[o] = 1;
         }
     }
 }
