@@ -348,6 +348,10 @@ class RTMDetIns:
                         u, stats = E.conv2d_halo_nhwc(t, blk['dw_tc'], blk['dwb'], pad=3, groups=t.shape[3], stats=True)
                     else:
                         u, stats = E.dwconv_stats_nhwc(t, blk['dw'], blk['dwb'])
+                    if E.convnext_mlp_supported(t.shape[3], blk['fc2'].w.shape[3]):
+                        # stages 1-2: LN -> fc1 -> GELU -> fc2 -> + residual in one launch, the 4C intermediate never reaches HBM (k_mlp_tc)
+                        E.convnext_mlp_nhwc(u, stats, *blk['fc1_ln'], blk['fc2'].w, blk['fc2'].b, t, eps=1e-6, out=t)
+                        continue
                     h = E.conv2d_ln_nhwc(u, stats, *blk['fc1_ln'], eps=1e-6, act='gelu')
                 else:
                     u = E.dwconv_nhwc(t, blk['dw'], blk['dwb'], ln=blk['ln'], eps=1e-6)

@@ -733,3 +733,384 @@ extern "C" int csb_conv2d_ln_nhwc(const csb_conv_desc* d, const void* x, const v
     CSB_REQUIRE(stats && colsum, "null pointer");
     return conv_impl(d, x, w, bias, nullptr, residual, y, nullptr, stats, colsum, eps, stream);
 }
+
+// ================================================================================================ fused ConvNeXt MLP
+// LayerNorm -> Linear C -> 4C -> GELU -> Linear 4C -> C (layer scale folded) -> + residual in ONE kernel (mmpretrain ConvNeXtBlock,
+// SURVEY.md Appendix A.4), for the wide-image stages (C = 128 / 256) where the 4C intermediate dominates the HBM traffic of the block (2.1 GB per
+// launch at 32 x 256^2 x 512, written by fc1 and read back by fc2): here it never leaves the SM.
+//
+// Per 128-pixel tile: the activation tile X [128 x C] is loaded once (C / 64 swizzled k-blocks).  The hidden dimension is walked in chunks of HC
+// units (128 for C = 128, 64 for C = 256):
+//     GEMM1  Hacc[b] (TMEM, HC columns, two buffers) = X . W1[chunk]^T                         M128 x N=HC x K=C
+//     EPI1   12 epilogue warps: tcgen05.ld -> folded LayerNorm + bias + GELU -> fp16 -> shared memory, written directly in the canonical K-major
+//            128B-swizzled operand layout (16 B chunk index ^ (row & 7)), two buffers
+//     GEMM2  Y (TMEM, C columns) += Hs[b] . W2[:, chunk]^T                                      M128 x N=C x K=HC
+// and after the last chunk EPI2 = the ordinary epilogue (bias, residual, TMA tile store).  The MMA warp issues GEMM1(j+1) before GEMM2(j), so the
+// tensor pipe works on the next chunk while the epilogue warps convert the current one.  Weight chunks stream through a 3-stage ring of 32 KiB
+// stages in exactly the order the MMA warp consumes them: W1(0), W1(1), W2(0), W1(2), W2(1), ..., W2(last).
+// The arithmetic (k-order of both accumulations, fp16 rounding of the hidden activations) is that of csb_conv2d_ln_nhwc followed by
+// csb_conv2d_nhwc, so the results are bit-identical to the two-launch path.
+namespace {
+
+struct MlpParams {
+    int C, Hd, HC, NJ, k1b, k2b, tiles_m;
+    const float* b1;
+    const float* colsum;
+    const float* stats;
+    int ln_nchunk;
+    float ln_inv_c, ln_eps;
+    uint32_t x_bytes, ring_off, h_off, h_bytes, bar_off;      // shared-memory layout (byte offsets from the 1 KiB-aligned base)
+    int sub16;                                                // EPI1 task width: 16 accumulator columns (1) or 32 (0)
+};
+
+constexpr int kMlpStages = 3;
+constexpr uint32_t kMlpStageBytes = 32768;
+// barriers (8 B each): full[3] empty[3] xfull xempty haccf[2] hacce[2] hsf[2] hse[2] yfull yempty
+enum { MB_FULL = 0, MB_EMPTY = 3, MB_XFULL = 6, MB_XEMPTY = 7, MB_HACCF = 8, MB_HACCE = 10, MB_HSF = 12, MB_HSE = 14, MB_YFULL = 16, MB_YEMPTY = 17, MB_COUNT = 18 };
+
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NCOL]) {
+    if constexpr (NCOL == 32) tmem_ld32(taddr, v);
+    else tmem_ld16(taddr, v);
+}
+
+// EPI1 of one hidden chunk for one warp: its tasks are the NCOL-column slices first, first + EG, ... of the chunk's HC accumulator columns (TMEM lane
+// quarter of the warp).  Per task: tcgen05.ld -> folded LayerNorm + bias + GELU -> fp16 -> shared memory in the K-major 128B-swizzled operand layout
+// (k-block = column / 64, row m, 16 B chunk (column % 64) / 8 ^ (m & 7)).  NCOL = 16 balances 8 tasks per quarter over 3 warps as 3 / 3 / 2.
+template <class T, int NCOL, int EG>
+__device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpParams& q, int first, int j, int b, int m, int lane, uint32_t tm_lane, uint32_t hrow,
+                                         uint32_t hacce_bar, uint64_t nm, uint64_t rs) {
+    const int ntask = q.HC / NCOL;
+    int last = -1;
+    for (int t = first; t < ntask; t += EG) last = t;
+    if (last < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hacce_bar);
+    }
+    for (int t = first; t < ntask; t += EG) {
+        uint32_t acc[NCOL];
+        tmem_ld_cols<NCOL>(tm_lane + (uint32_t) (b * q.HC + t * NCOL), acc);
+        if (t == last) {                                             // this warp has read all it needs from the accumulator buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hacce_bar);
+        }
+        const int c0 = t * NCOL, n0 = j * q.HC + c0;                 // column inside the chunk, hidden unit
+        float y[NCOL];
+#pragma unroll
+        for (int g = 0; g < NCOL / 4; ++g) {                         // folded LayerNorm: rstd * acc + (-mean * rstd * colsum + bias')
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(q.colsum + n0) + g), b4 = __ldg(reinterpret_cast<const float4*>(q.b1 + n0) + g);
+            upk2(ffma2(rs, pk2(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1])), ffma2(nm, pk2(c4.x, c4.y), pk2(b4.x, b4.y))), y[4 * g], y[4 * g + 1]);
+            upk2(ffma2(rs, pk2(__uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3])), ffma2(nm, pk2(c4.z, c4.w), pk2(b4.z, b4.w))), y[4 * g + 2], y[4 * g + 3]);
+        }
+        if (p.gelu_form == 1) {
+#pragma unroll
+            for (int i = 0; i < NCOL; i += 2) gelu2_tanh(y[i], y[i + 1]);
+        } else {                                                     // the polynomial / sigmoid mix, pair for pair as epilogue_chunk selects it (position inside the 32-column chunk)
+#pragma unroll
+            for (int i = 0; i < NCOL; i += 2) {
+                const int pi = ((c0 & 31) + i) >> 1;                 // NCOL = 16: c0 & 31 is 0 or 16, warp-uniform
+                if (pi * kGeluMufuPairs / 16 != (pi + 1) * kGeluMufuPairs / 16) gelu2_mufu(y[i], y[i + 1]);
+                else gelu2(y[i], y[i + 1]);
+            }
+        }
+        const uint32_t rowaddr = hrow + (uint32_t) (c0 >> 6) * 16384u;
+        const uint32_t ck0 = (uint32_t) ((c0 & 63) >> 3);
+#pragma unroll
+        for (int g = 0; g < NCOL / 8; ++g)
+            st_shared_v4(rowaddr + (((ck0 + (uint32_t) g) ^ (uint32_t) (m & 7)) << 4),
+                         make_uint4(pack2<T>(y[8 * g], y[8 * g + 1]), pack2<T>(y[8 * g + 2], y[8 * g + 3]), pack2<T>(y[8 * g + 4], y[8 * g + 5]), pack2<T>(y[8 * g + 6], y[8 * g + 7])));
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(512, 1) k_mlp_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                                                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
+                                                   const ConvKernelParams p, const MlpParams q) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t ring_base = smem_base + q.ring_off, h_base = smem_base + q.h_off, bar_base = smem_base + q.bar_off;
+    auto bar = [&](int i) { return bar_base + 8u * (uint32_t) i; };
+    const uint32_t tmem_slot = bar(MB_COUNT);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int EG = 3, NEPI = 4 * EG;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kMlpStages; ++s) { mbar_init(bar(MB_FULL + s), 1); mbar_init(bar(MB_EMPTY + s), 1); }
+        mbar_init(bar(MB_XFULL), 1); mbar_init(bar(MB_XEMPTY), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar(MB_HACCF + b), 1); mbar_init(bar(MB_HACCE + b), NEPI);
+            mbar_init(bar(MB_HSF + b), NEPI); mbar_init(bar(MB_HSE + b), 1);
+        }
+        mbar_init(bar(MB_YFULL), 1); mbar_init(bar(MB_YEMPTY), NEPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tm_y = tmem_base, tm_h0 = tmem_base + (uint32_t) q.C;          // Y: columns [0, C), Hacc[b]: [C + b * HC, ...)
+    const int cta = blockIdx.x, ncta = gridDim.x;
+    const uint32_t w1_kb_bytes = (uint32_t) q.HC * 128u, w2_kb_bytes = (uint32_t) q.C * 128u;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0) {
+            // ===================================================== TMA producer
+            if (elect_one()) {
+                int stage = 0;
+                uint32_t phase = 0, xphase = 0;
+                auto load_w1 = [&](int j) {
+                    mbar_wait(bar(MB_EMPTY + stage), phase ^ 1u);
+                    mbar_expect_tx(bar(MB_FULL + stage), (uint32_t) q.k1b * w1_kb_bytes);
+                    for (int kb = 0; kb < q.k1b; ++kb)
+                        tma_load_2d<1>(ring_base + (uint32_t) stage * kMlpStageBytes + (uint32_t) kb * w1_kb_bytes, &tmW1, bar(MB_FULL + stage), kb * 64, j * q.HC);
+                    if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+                };
+                auto load_w2 = [&](int j) {
+                    mbar_wait(bar(MB_EMPTY + stage), phase ^ 1u);
+                    mbar_expect_tx(bar(MB_FULL + stage), (uint32_t) q.k2b * w2_kb_bytes);
+                    for (int kb = 0; kb < q.k2b; ++kb)
+                        tma_load_2d<1>(ring_base + (uint32_t) stage * kMlpStageBytes + (uint32_t) kb * w2_kb_bytes, &tmW2, bar(MB_FULL + stage), j * q.HC + kb * 64, 0);
+                    if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+                };
+                for (int tile = cta; tile < q.tiles_m; tile += ncta) {
+                    mbar_wait(bar(MB_XEMPTY), xphase ^ 1u);
+                    mbar_expect_tx(bar(MB_XFULL), q.x_bytes);
+                    for (int kb = 0; kb < q.k1b; ++kb)
+                        tma_load_4d<1>(smem_base + (uint32_t) kb * 16384u, &tmX, bar(MB_XFULL), p.in_coff + kb * 64, tile * kBlockM, 0, 0);
+                    xphase ^= 1u;
+                    load_w1(0);
+                    for (int j = 1; j < q.NJ; ++j) { load_w1(j); load_w2(j - 1); }
+                    load_w2(q.NJ - 1);
+                }
+            }
+        } else if (warp == 1) {
+            // ===================================================== MMA issuer
+            const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+            const uint32_t idesc1 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (q.HC >> 3) << 17) | ((uint32_t) (kBlockM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (q.C >> 3) << 17) | ((uint32_t) (kBlockM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0, xphase = 0, yphase = 0;
+            // buffer b = j & 1 is used NJ / 2 times per tile: its u-th use (u = it * NJ / 2 + (j >> 1)) completes phase u of its barriers
+            uint32_t ubase = 0;                                                  // it * NJ / 2
+            auto gemm1 = [&](int j, bool last) {
+                const int b = j & 1;
+                const uint32_t u = ubase + (uint32_t) (j >> 1);
+                mbar_wait(bar(MB_HACCE + b), (u & 1u) ^ 1u);                     // the epilogue has read this accumulator buffer's previous contents
+                mbar_wait(bar(MB_FULL + stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t wb = ring_base + (uint32_t) stage * kMlpStageBytes;
+                    for (int kb = 0; kb < q.k1b; ++kb) {
+                        const uint64_t adesc = make_desc(smem_base + (uint32_t) kb * 16384u, 128), bdesc = make_desc(wb + (uint32_t) kb * w1_kb_bytes, 128);
+                        for (int k = 0; k < 4; ++k) umma_f16<1>(tm_h0 + (uint32_t) (b * q.HC), adesc + 2u * k, bdesc + 2u * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit<1>(bar(MB_EMPTY + stage));
+                    umma_commit<1>(bar(MB_HACCF + b));
+                    if (last) umma_commit<1>(bar(MB_XEMPTY));                        // X tile free: the producer may load the next tile's activations
+                }
+                __syncwarp();
+                if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+            };
+            auto gemm2 = [&](int j, bool last) {
+                const int b = j & 1;
+                mbar_wait(bar(MB_HSF + b), (ubase + (uint32_t) (j >> 1)) & 1u);      // the epilogue warps have written this chunk's fp16 activations
+                mbar_wait(bar(MB_FULL + stage), phase);
+                if (j == 0) { mbar_wait(bar(MB_YEMPTY), yphase ^ 1u); yphase ^= 1u; } // the previous tile's output accumulator has been read
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t wb = ring_base + (uint32_t) stage * kMlpStageBytes, hb = h_base + (uint32_t) b * q.h_bytes;
+                    for (int kb = 0; kb < q.k2b; ++kb) {
+                        const uint64_t adesc = make_desc(hb + (uint32_t) kb * 16384u, 128), bdesc = make_desc(wb + (uint32_t) kb * w2_kb_bytes, 128);
+                        for (int k = 0; k < 4; ++k) umma_f16<1>(tm_y, adesc + 2u * k, bdesc + 2u * k, idesc2, (j | kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit<1>(bar(MB_EMPTY + stage));
+                    umma_commit<1>(bar(MB_HSE + b));
+                    if (last) umma_commit<1>(bar(MB_YFULL));
+                }
+                __syncwarp();
+                if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+            };
+            for (int tile = cta; tile < q.tiles_m; tile += ncta) {
+                mbar_wait(bar(MB_XFULL), xphase);
+                xphase ^= 1u;
+                tc_fence_after();
+                gemm1(0, q.NJ == 1);
+                for (int j = 1; j < q.NJ; ++j) { gemm1(j, j == q.NJ - 1); gemm2(j - 1, false); }
+                gemm2(q.NJ - 1, true);
+                ubase += (uint32_t) (q.NJ >> 1);
+            }
+        }
+    } else {
+        // ===================================================== epilogue warps: EPI1 per hidden chunk, EPI2 per tile
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        const int qd = warp & 3, grp = (warp - 4) >> 2;
+        const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && (!p.bias || ((uintptr_t) p.bias % 16 == 0));
+        const uint32_t stage_any = smem_base + p.stage_off + (uint32_t) (warp - 4) * 2048u;
+        const uint32_t lane_base = ((uint32_t) (qd * 32) << 16);
+        const int nc1 = q.HC / 32, nc2 = q.C / 32;
+        uint32_t ubase = 0, yphase = 0;
+        int rot = grp;
+        for (int tile = cta; tile < q.tiles_m; tile += ncta) {
+            const int m = qd * 32 + lane;
+            const long long row = (long long) tile * kBlockM + m;
+            const bool row_ok = row < p.W;
+            const size_t pix = (size_t) (row_ok ? row : (long long) p.W - 1);
+            float neg_mean, rstd;
+            {
+                const float2* sp = reinterpret_cast<const float2*>(q.stats) + pix * q.ln_nchunk;
+                float s1 = 0.f, s2 = 0.f;
+                for (int c = 0; c < q.ln_nchunk; ++c) { const float2 t = __ldg(sp + c); s1 += t.x; s2 += t.y; }
+                const float mean = s1 * q.ln_inv_c;
+                rstd = rsqrtf(fmaxf(fmaf(s2, q.ln_inv_c, -mean * mean), 0.f) + q.ln_eps);
+                neg_mean = -mean * rstd;
+            }
+            const uint64_t nm = pk2(neg_mean, neg_mean), rs = pk2(rstd, rstd);
+            for (int j = 0; j < q.NJ; ++j) {
+                const int b = j & 1;
+                const int first = rot;                                       // this warp group's chunks of the hidden chunk: first, first + EG, ...
+                if (++rot == EG) rot = 0;
+                const uint32_t u = ubase + (uint32_t) (j >> 1);
+                mbar_wait(bar(MB_HACCF + b), u & 1u);
+                tc_fence_after();
+                mbar_wait(bar(MB_HSE + b), (u & 1u) ^ 1u);                    // GEMM2 of the chunk that used this shared-memory buffer before has completed
+                if (q.sub16) mlp_epi1<T, 16, EG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
+                else mlp_epi1<T, 32, EG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(MB_HSF + b));
+            }
+            ubase += (uint32_t) (q.NJ >> 1);
+            // ---- EPI2: the block's output tile (bias, residual, TMA tile store), as k_conv_tc's epilogue
+            mbar_wait(bar(MB_YFULL), yphase);
+            yphase ^= 1u;
+            tc_fence_after();
+            const uint32_t stage = p.tma_store ? stage_any : 0u;
+            const int cw = tile * kBlockM + qd * 32;
+            int last2 = -1;
+            for (int ch = grp; ch < nc2; ch += EG) last2 = ch;
+            if (last2 < 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(MB_YEMPTY));
+            }
+            for (int ch = grp; ch < nc2; ch += EG) {
+                uint32_t acc[32];
+                tmem_ld32(tm_y + lane_base + (uint32_t) (ch * 32), acc);
+                if (ch == last2) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(MB_YEMPTY));
+                }
+                epilogue_chunk<T, CSB_ACT_NONE, false>(p, acc, pix, ch * 32, row_ok, aligned && ch * 32 + 32 <= p.Cout, stage, &tmC, cw, 0, 0, 0.f, 1.f, stage_any);
+            }
+        }
+        if (p.tma_store && lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
+    }
+}
+
+std::atomic<int> g_mlp_mode{[] { const char* e = getenv("CSB_FUSE_MLP"); return e ? atoi(e) : 1; }()};
+
+}  // namespace
+
+// 1 if csb_convnext_mlp_nhwc can run this block shape (C = 128 or 256, hidden = 4C) and the fused path is enabled (CSB_FUSE_MLP, default 1).
+extern "C" int csb_convnext_mlp_supported(int C, int hidden) { return g_mlp_mode.load(std::memory_order_relaxed) != 0 && (C == 128 || C == 256) && hidden == 4 * C; }
+extern "C" int csb_convnext_mlp_set_mode(int mode) { return g_mlp_mode.exchange(mode); }
+
+extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long long pixels, int C, int hidden, const void* w1, const float* b1, const float* colsum,
+                                     const float* stats, float eps, const void* w2, const float* b2, const void* residual, int res_ld, int res_coff, void* y,
+                                     int y_ld, int y_coff, int dtype, void* stream) {
+    CSB_REQUIRE(x && w1 && b1 && colsum && stats && w2 && y, "null pointer");
+    CSB_REQUIRE((C == 128 || C == 256) && hidden == 4 * C && pixels > 0 && pixels < (1ll << 31), "fused MLP: C must be 128 or 256 with hidden = 4 C");
+    CSB_REQUIRE(x_ld % 8 == 0 && x_coff % 8 == 0 && y_ld % 8 == 0 && y_coff % 8 == 0 && (!residual || (res_ld % 8 == 0 && res_coff % 8 == 0)), "channel strides / offsets must be multiples of 8");
+    CSB_REQUIRE((((uintptr_t) x | (uintptr_t) w1 | (uintptr_t) w2 | (uintptr_t) y | (uintptr_t) b1 | (uintptr_t) colsum | (uintptr_t) b2) & 15) == 0 && ((uintptr_t) stats & 7) == 0,
+                "pointers must be 16-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return csb::fail(CSB_ERR_CUDA, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled unavailable");
+    MlpParams q{};
+    q.C = C; q.Hd = hidden; q.HC = C == 128 ? 128 : 64; q.NJ = hidden / q.HC; q.k1b = C / 64; q.k2b = q.HC / 64;
+    q.tiles_m = (int) ((pixels + kBlockM - 1) / kBlockM);
+    q.b1 = b1; q.colsum = colsum; q.stats = stats; q.ln_nchunk = C / 64; q.ln_inv_c = 1.0f / (float) C; q.ln_eps = eps;
+    q.x_bytes = (uint32_t) q.k1b * 16384u;
+    q.ring_off = q.x_bytes;
+    q.h_off = q.ring_off + kMlpStages * kMlpStageBytes;
+    q.h_bytes = (uint32_t) q.k2b * 16384u;
+    q.bar_off = q.h_off + 2u * q.h_bytes;
+    { const char* e = getenv("CSB_MLP_SUB16"); q.sub16 = e ? atoi(e) : 0; }     // measured (gpurun r2c28): 32-column tasks 1237 / 781 us, 16-column 1261 / 878 us
+    ConvKernelParams p{};
+    p.N = 1; p.H = 1; p.W = (int) pixels; p.Cin = hidden; p.Cout = C; p.R = p.S = 1; p.stride = 1; p.bh = 1; p.bw = kBlockM;
+    p.tiles_h = 1; p.tiles_w = q.tiles_m; p.tiles_m = q.tiles_m; p.tiles_n = 1; p.block_n = C; p.in_coff = x_coff;
+    p.bias = b2; p.residual = residual; p.res_ld = res_ld; p.res_coff = res_coff; p.res_mode = residual ? 2 : 0; p.act = CSB_ACT_NONE;
+    p.out = y; p.out_ld = y_ld; p.out_coff = y_coff; p.is_bf16 = dtype == 1;
+    p.gelu_form = g_gelu_form.load(std::memory_order_relaxed);
+    p.stage_off = (q.bar_off + 8u * (MB_COUNT + 2) + 1023u) & ~1023u;
+    const size_t smem = (size_t) p.stage_off + 4 * kMaxEpiGroups * 2048 + 1024;
+    CSB_REQUIRE(smem <= 227 * 1024, "fused MLP: shared-memory budget exceeded");
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const cuuint64_t esz = 2;
+    CUtensorMap tmX, tmW1, tmW2, tmC;
+    {
+        cuuint64_t gdim[4] = {(cuuint64_t) x_ld, (cuuint64_t) pixels, 1, 1}, gstr[3] = {(cuuint64_t) x_ld * esz, (cuuint64_t) x_ld * esz * pixels, (cuuint64_t) x_ld * esz * pixels};
+        cuuint32_t box[4] = {64, (cuuint32_t) kBlockM, 1, 1}, estr[4] = {1, 1, 1, 1};
+        if (enc(&tmX, dt, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled(X) failed");
+    }
+    {
+        cuuint64_t wdim[2] = {(cuuint64_t) C, (cuuint64_t) hidden}, wstr[1] = {(cuuint64_t) C * esz};
+        cuuint32_t wbox[2] = {64, (cuuint32_t) q.HC}, westr[2] = {1, 1};
+        if (enc(&tmW1, dt, 2, const_cast<void*>(w1), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled(W1) failed");
+        cuuint64_t vdim[2] = {(cuuint64_t) hidden, (cuuint64_t) C}, vstr[1] = {(cuuint64_t) hidden * esz};
+        cuuint32_t vbox[2] = {64, (cuuint32_t) C};
+        if (enc(&tmW2, dt, 2, const_cast<void*>(w2), vdim, vstr, vbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled(W2) failed");
+    }
+    {
+        cuuint64_t cdim[4] = {(cuuint64_t) C, (cuuint64_t) pixels, 1, 1};
+        cuuint64_t cstr[3] = {(cuuint64_t) y_ld * esz, (cuuint64_t) y_ld * esz * pixels, (cuuint64_t) y_ld * esz * pixels};
+        cuuint32_t cbox[4] = {32, 32, 1, 1}, cestr[4] = {1, 1, 1, 1};
+        char* cbase = reinterpret_cast<char*>(y) + (size_t) y_coff * esz;
+        if (enc(&tmC, dt, 4, cbase, cdim, cstr, cbox, cestr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled(C) failed");
+        p.tma_store = 1;
+    }
+    static unsigned char attr_done[64] = {};
+    if (csb::first_use_on_device(attr_done)) {
+        cudaFuncSetAttribute(k_mlp_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }
+    const int sms = csb::num_sms();
+    const int grid = q.tiles_m < sms ? q.tiles_m : sms;
+    if (dtype == 1) k_mlp_tc<__nv_bfloat16><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+    else k_mlp_tc<__half><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+    if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {
+        char label[160];
+        snprintf(label, sizeof label, "k_mlp_tc[%lldx%d->%d->%d]", pixels, C, hidden, C);
+        return csb::launched(csb::profile_intern(label), (cudaStream_t) stream);
+    }
+    return csb::launched("k_mlp_tc", (cudaStream_t) stream);
+}

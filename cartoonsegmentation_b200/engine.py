@@ -137,6 +137,24 @@ def dwconv_stats_nhwc(x, w, bias=None, out=None, xoff=0, yoff=0, channels=None):
     return out, stats
 
 
+def convnext_mlp_supported(C_, hidden):
+    return bool(lib().csb_convnext_mlp_supported(int(C_), int(hidden)))
+
+
+def convnext_mlp_nhwc(x, stats, w1, b1, colsum, w2, b2, residual, eps=1e-6, out=None):
+    """residual + W2 GELU(LayerNorm(x) W1^T + b1) + b2 in one launch (csb_convnext_mlp_nhwc); LayerNorm folded as for conv2d_ln_nhwc,
+    layer scale folded into w2 / b2.  x, residual: [N,H,W,C]; w1 [4C,1,1,C], w2 [C,1,1,4C] packed; out may be `residual` (in place)."""
+    N, H, W, Cx = x.shape
+    hidden = w1.shape[0]
+    assert w1.shape[3] == Cx and w2.shape[0] == Cx and w2.shape[3] == hidden and x.dtype == w1.dtype == w2.dtype
+    if out is None:
+        out = torch.empty((N, H, W, Cx), device=x.device, dtype=x.dtype)
+    check(lib().csb_convnext_mlp_nhwc(ptr(x), Cx, 0, C.c_longlong(N * H * W), Cx, hidden, ptr(w1), ptr(b1), ptr(colsum), ptr(stats), _cf(eps), ptr(w2), ptr(b2),
+                                      ptr(residual), residual.shape[3] if residual is not None else 0, 0, ptr(out), out.shape[3], 0,
+                                      1 if x.dtype == torch.bfloat16 else 0, stream()), "csb_convnext_mlp_nhwc")
+    return out
+
+
 def conv2d_ln_nhwc(x, stats, w, bias, colsum, eps=1e-6, act=None, residual=None, res_mode=0, out=None, out_coff=0):
     """1x1 conv of LayerNorm(x) with the LayerNorm folded into the epilogue (see fold_layernorm); x is the un-normalised NHWC tensor."""
     N, H, W, Cx = x.shape

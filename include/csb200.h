@@ -322,6 +322,19 @@ CSB_API int csb_dwconv_stats_nhwc(const void* x, int ldx, int xoff, const float*
 CSB_API int csb_conv2d_ln_nhwc(const csb_conv_desc* desc, const void* x, const void* w, const float* bias, const float* colsum, const float* stats,
                        float eps, const void* residual, void* y, void* stream);
 
+/* The ConvNeXt block's MLP in ONE launch (csrc/tc_conv.cu: k_mlp_tc): y = residual + W2 GELU(LayerNorm(x) W1^T + b1) + b2 with the LayerNorm
+ * folded as in csb_conv2d_ln_nhwc (w1 = W1 diag(gamma) packed [hidden][C], b1 = bias + W1 beta, colsum, stats from csb_dwconv_stats_nhwc) and the
+ * layer scale folded into w2 [C][hidden] / b2.  The 4C-wide hidden activations stay in tensor memory / shared memory.  C = 128 or 256 with
+ * hidden = 4 C (the two wide-image stages of ConvNeXt-B, mmpretrain ConvNeXtBlock); x, residual, y: NHWC fp16 (dtype 0) / bf16 (1) with `pixels`
+ * rows, channel strides *_ld and offsets *_coff (multiples of 8); y may alias residual.  Bit-identical to csb_conv2d_ln_nhwc + csb_conv2d_nhwc.
+ * csb_convnext_mlp_supported: 1 if the shape qualifies and the path is enabled (CSB_FUSE_MLP, default 1; csb_convnext_mlp_set_mode returns the
+ * previous mode). */
+CSB_API int csb_convnext_mlp_supported(int C, int hidden);
+CSB_API int csb_convnext_mlp_set_mode(int mode);
+CSB_API int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long long pixels, int C, int hidden, const void* w1, const float* b1, const float* colsum,
+                          const float* stats, float eps, const void* w2, const float* b2, const void* residual, int res_ld, int res_coff, void* y, int y_ld,
+                          int y_coff, int dtype, void* stream);
+
 /* HBM-bound NHWC fp16 layers between the tensor-core convs (csrc/nn_elem.cu).  Channel-slice addressing: ld = channels of the
  * buffer, off = first channel, so concats (CSPNeXtPAFPN, MaskFeatModule, CSPLayer -- SURVEY.md Appendix A.3-A.6) need no copy.
  *   csb_dwconv_nhwc     depthwise KxK (K = 3/5/7, stride 1, zero pad K/2) + bias, then LayerNorm over C (ln_gamma/ln_beta != NULL:
