@@ -209,8 +209,67 @@ __global__ void __launch_bounds__(256) k_layernorm(const __half* __restrict__ x,
     }
 }
 
+// C <= 128 (the ConvNeXt stem / first downsample norms, the two largest LayerNorm launches of the detector): 16 lanes cover a pixel, so a warp
+// normalises two pixels side by side instead of idling half of its lanes; PIX pixel pairs per iteration, reductions over 16 lanes (4 shuffles).
+template <int PIX>
+__global__ void __launch_bounds__(256) k_layernorm_h16(const __half* __restrict__ x, int ldx, int xoff, const float* __restrict__ g, const float* __restrict__ b, float eps,
+                                                       long long npix, int C, __half* __restrict__ y, int ldy, int yoff) {
+    const int lane = threadIdx.x & 31, sub = lane >> 4, c0 = 8 * (lane & 15);
+    const bool on = c0 < C;
+    const long long ngroups = (npix + 2 * PIX - 1) / (2 * PIX);
+    float gg[8], bb[8];
+    if (on) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + c0)), g1 = __ldg(reinterpret_cast<const float4*>(g + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c0)), b1 = __ldg(reinterpret_cast<const float4*>(b + c0 + 4));
+        gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+    }
+    auto sum16 = [](float v) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    for (long long grp = (long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < ngroups; grp += (long long) gridDim.x * (blockDim.x >> 5)) {
+        H8 raw[PIX];
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) {
+            const long long pix = (grp * PIX + p) * 2 + sub;
+            if (pix < npix && on) raw[p] = *reinterpret_cast<const H8*>(x + pix * ldx + xoff + c0);
+        }
+#pragma unroll
+        for (int p = 0; p < PIX; ++p) {
+            const long long pix = (grp * PIX + p) * 2 + sub;
+            const bool live = pix < npix && on;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float s1 = 0.0f;
+            if (live) {
+                unpack8(raw[p], v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s1 += v[e];                      // same per-lane order as k_layernorm
+            }
+            const float mean = sum16(s1) / (float) C;
+            float s2 = 0.0f;
+            if (live)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { float d = v[e] - mean; s2 += d * d; }
+            const float rstd = rsqrtf(sum16(s2) / (float) C + eps);
+            if (live) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
+                *reinterpret_cast<H8*>(y + pix * ldy + yoff + c0) = pack8(o);
+            }
+        }
+    }
+}
+
 static int launch_layernorm(const __half* x, int ldx, int xoff, const float* g, const float* b, float eps, long long npix, int C, __half* y, int ldy, int yoff,
                             cudaStream_t st) {
+    static const int h16 = [] { const char* e = getenv("CSB_LN_H16"); return e ? atoi(e) : 1; }();
+    if (h16 && C <= 128 && C % 8 == 0) {
+        k_layernorm_h16<8><<<csb::wave_grid((npix + 15) / 16 * 32, 256, 8), 256, 0, st>>>(x, ldx, xoff, g, b, eps, npix, C, y, ldy, yoff);
+        return csb::launched("k_layernorm", st);
+    }
     const int nv = (C + 255) / 256;
 #define CSB_LN(NV_, PIX_) k_layernorm<NV_, PIX_><<<csb::wave_grid((npix + PIX_ - 1) / PIX_ * 32, 256, 8), 256, 0, st>>>(x, ldx, xoff, g, b, eps, npix, C, y, ldy, yoff)
     if (nv == 1) CSB_LN(1, 8);

@@ -42,6 +42,11 @@ def test_elementwise_layers_vs_torch(env):
         assert (y.float() - r).abs().max().item() < 8e-3, C_
         y2 = E.layernorm_nhwc(x, lg, lb, 1e-6)
         assert (y2.float() - F.layer_norm(x.float(), (C_,), lg, lb, 1e-6)).abs().max().item() < 4e-3
+    for C_, shape in ((128, (1, 7, 9)), (64, (3, 5, 5)), (96, (1, 1, 1))):     # C <= 128: two pixels per warp (k_layernorm_h16), odd pixel counts
+        x = (torch.randn(*shape, C_, device='cuda', generator=g) * 2 + 0.5).half()
+        lg, lb = torch.rand(C_, device='cuda', generator=g) + 0.5, torch.randn(C_, device='cuda', generator=g) * 0.1
+        y2 = E.layernorm_nhwc(x, lg, lb, 1e-6)
+        assert (y2.float() - F.layer_norm(x.float(), (C_,), lg, lb, 1e-6)).abs().max().item() < 4e-3
     x = torch.randn(1, 9, 11, 64, device='cuda', generator=g).half()
     w5 = torch.randn(64, 1, 5, 5, device='cuda', generator=g) / 5
     y = E.dwconv_nhwc(x, w5[:, 0].permute(1, 2, 0).contiguous(), None, act='silu')
