@@ -357,8 +357,15 @@ __global__ void __launch_bounds__(256) k_image_prep_s2d(const uint8_t* __restric
             const int cs = swap_rb ? 2 - c : c;
             dst[e] = __float2half_rn(((float) src[e - c + cs] - mean[c]) / sd[c]);
         }
-        if (r == P - 1)
-            for (int e = P * P * 3; e < CP; ++e) y[cell * CP + e] = __float2half_rn(0.f);
+        if (r == P - 1) {                                          // zero padding: 8-byte stores when the tail starts 8-byte aligned (P = 2: halves 12 .. CP)
+            const int e0 = P * P * 3;
+            if ((e0 & 3) == 0 && (CP & 3) == 0) {
+                uint2* z = reinterpret_cast<uint2*>(y + cell * CP + e0);
+                for (int e = 0; e < (CP - e0) / 4; ++e) z[e] = make_uint2(0u, 0u);
+            } else {
+                for (int e = e0; e < CP; ++e) y[cell * CP + e] = __float2half_rn(0.f);
+            }
+        }
     }
 }
 
@@ -393,6 +400,41 @@ __global__ void __launch_bounds__(256) k_image_prep_s2d4(const uint8_t* __restri
             const float v[8] = {o[8 * g], o[8 * g + 1], o[8 * g + 2], o[8 * g + 3], o[8 * g + 4], o[8 * g + 5], o[8 * g + 6], o[8 * g + 7]};
             *reinterpret_cast<H8*>(dst + 8 * g) = pack8(v);
         }
+    }
+}
+
+// The LeReS case (P = 2, 2 x 2 space-to-depth of the 7x7 stride-2 stem): one thread per output cell; each patch row is 6 bytes at a 2-byte aligned
+// address (three 16-bit loads), the 12 + (CP - 12) halves of the cell leave as CP / 8 16-byte stores.  NV = CP / 8 (2 or 8).
+template <int NV>
+__global__ void __launch_bounds__(256) k_image_prep_s2d2(const uint8_t* __restrict__ img, unsigned ncell, int Ho, int Wo, int H, int W, float m0, float m1,
+                                                         float m2, float s0, float s1, float s2, int swap_rb, __half* __restrict__ y) {
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    for (unsigned cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncell; cell += gridDim.x * blockDim.x) {
+        const unsigned ox = cell % (unsigned) Wo, t = cell / (unsigned) Wo, oy = t % (unsigned) Ho, n = t / (unsigned) Ho;
+        const uint8_t* src = img + (((size_t) n * H + (size_t) oy * 2) * W + (size_t) ox * 2) * 3;
+        float o[16];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint16_t* row = reinterpret_cast<const uint16_t*>(src + (size_t) r * W * 3);
+            const uint32_t w0 = __ldg(row), w1 = __ldg(row + 1), w2 = __ldg(row + 2);
+            const uint8_t px[6] = {(uint8_t) w0, (uint8_t) (w0 >> 8), (uint8_t) w1, (uint8_t) (w1 >> 8), (uint8_t) w2, (uint8_t) (w2 >> 8)};
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+                const int c = e % 3, cs = swap_rb ? 2 - c : c;
+                o[r * 6 + e] = ((float) px[e - c + cs] - mean[c]) / sd[c];
+            }
+        }
+#pragma unroll
+        for (int e = 12; e < 16; ++e) o[e] = 0.f;
+        __half* dst = y + (size_t) cell * (NV * 8);
+        {
+            const float v0[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]}, v1[8] = {o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]};
+            *reinterpret_cast<H8*>(dst) = pack8(v0);
+            *reinterpret_cast<H8*>(dst + 8) = pack8(v1);
+        }
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int g = 2; g < NV; ++g) *reinterpret_cast<H8*>(dst + 8 * g) = pack8(z);
     }
 }
 
@@ -487,7 +529,13 @@ extern "C" int csb_image_prep_s2d_nhwc(const uint8_t* img, int N, int H, int W, 
     if (P == 4 && CP == 64 && ncell < (1ll << 31) && ((uintptr_t) img & 3) == 0 && ((uintptr_t) y & 15) == 0)
         k_image_prep_s2d4<<<csb::wave_grid(ncell, 256, 8), 256, 0, (cudaStream_t) stream>>>(img, (unsigned) ncell, H / P, W / P, H, W, mean3[0], mean3[1], mean3[2],
                                                                                               std3[0], std3[1], std3[2], swap_rb, (__half*) y);
-    else
+    else if (P == 2 && (CP == 16 || CP == 64) && W % 2 == 0 && ncell < (1ll << 31) && ((uintptr_t) img & 1) == 0 && ((uintptr_t) y & 15) == 0) {
+        // (every patch row starts at an even byte offset: (row * W + 2 ox) * 3 with W even)
+        if (CP == 16) k_image_prep_s2d2<2><<<csb::wave_grid(ncell, 256, 8), 256, 0, (cudaStream_t) stream>>>(img, (unsigned) ncell, H / P, W / P, H, W, mean3[0], mean3[1],
+                                                                                                      mean3[2], std3[0], std3[1], std3[2], swap_rb, (__half*) y);
+        else k_image_prep_s2d2<8><<<csb::wave_grid(ncell, 256, 8), 256, 0, (cudaStream_t) stream>>>(img, (unsigned) ncell, H / P, W / P, H, W, mean3[0], mean3[1],
+                                                                                                     mean3[2], std3[0], std3[1], std3[2], swap_rb, (__half*) y);
+    } else
         k_image_prep_s2d<<<csb::wave_grid((long long) N * (H / P) * (W / P) * P, 256, 8), 256, 0, (cudaStream_t) stream>>>(
             img, N, H, W, P, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], swap_rb, CP, (__half*) y);
     return csb::launched("k_image_prep", (cudaStream_t) stream);

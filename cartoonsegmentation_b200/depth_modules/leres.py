@@ -120,6 +120,10 @@ class _FTB:
 
 
 STEM_S2D = __import__("os").environ.get("CSB_LERES_S2D", "1") != "0"       # space-to-depth form of the 7x7 stride-2 stem (see LeReS.__init__)
+# channels of the space-to-depth stem input: 12 real ones padded to 16 (per-tap kernel, 25 TMA boxes of 32 B rows per tile: 1.25 ms per 32 frames) or to
+# 64 (halo-tile kernel: one halo box per tile, the 25 taps are shifted descriptors on it: conv -0.45 ms, but the prep kernel writes 4x the bytes:
+# +0.6 ms).  Measured on B200 (gpurun r2c32 / r2c33): 16 wins by 0.2-0.6 ms per step.
+STEM_CP = int(__import__("os").environ.get("CSB_LERES_STEM_CP", "16"))
 
 
 class LeReS:
@@ -144,7 +148,7 @@ class LeReS:
                         s_ = 2 * bb + dx + 3
                         if 0 <= s_ <= 6:
                             w5[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3, a + 2, bb + 2] = w7[:, :, r, s_]
-        self.stem_s2d = _C(w5, b7, dev, cin_pad=16)
+        self.stem_s2d = _C(w5, b7, dev, cin_pad=STEM_CP)
         self.layers = []
         for li, nblk in enumerate(LAYERS, start=1):
             blocks = []
@@ -200,7 +204,7 @@ class LeReS:
         # estimateleres: BGR -> RGB (depthmap.py:35), ToTensor on float (no /255 again), Normalize(ImageNet) (:26) on img/255
         mean, std = [255.0 * m for m in IMAGENET_MEAN], [255.0 * s for s in IMAGENET_STD]
         if STEM_S2D:
-            f = self.encoder(E.image_prep_s2d_nhwc(img_u8, mean, std, 2, 16, swap_rb=not rgb_input), s2d=True)
+            f = self.encoder(E.image_prep_s2d_nhwc(img_u8, mean, std, 2, STEM_CP, swap_rb=not rgb_input), s2d=True)
         else:
             f = self.encoder(E.image_prep_nhwc(img_u8, mean, std, swap_rb=not rgb_input, CP=16))
         x32 = self.conv1(self.conv(f[3]), pad=1)

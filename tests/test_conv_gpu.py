@@ -168,22 +168,24 @@ def test_conv_cta_pair_matches_single_cta(eng, N, H, W, Cin, Cout, k, stride, pa
     assert torch.equal(outs[0], outs[2]), f"pair path differs: max {(outs[0].float() - outs[2].float()).abs().max().item()}"
 
 
-@pytest.mark.parametrize("N,H,W,C", [(2, 40, 48, 128), (1, 33, 47, 128), (3, 24, 40, 256), (1, 67, 129, 256), (8, 64, 64, 128)])
-def test_fused_convnext_mlp_is_bit_identical_to_the_two_launch_path(eng, N, H, W, C):
+@pytest.mark.parametrize("N,H,W,C,dt", [(2, 40, 48, 128, 'f16'), (1, 33, 47, 128, 'f16'), (3, 24, 40, 256, 'f16'), (1, 67, 129, 256, 'f16'), (8, 64, 64, 128, 'f16'),
+                                        (1, 33, 47, 128, 'bf16'), (2, 24, 40, 256, 'bf16')])
+def test_fused_convnext_mlp_is_bit_identical_to_the_two_launch_path(eng, N, H, W, C, dt):
     """k_mlp_tc (LN -> fc1 -> GELU -> fc2 -> + residual, hidden activations kept on the SM) against csb_conv2d_ln_nhwc + csb_conv2d_nhwc: same k-order
     of both accumulations and the same fp16 rounding of the hidden activations -> bit-identical, incl. ragged last tiles, multi-tile CTAs and the
     in-place (out == residual) form the backbone uses; the two-launch result is also checked against PyTorch fp32."""
     g = torch.Generator(device='cuda').manual_seed(C + H)
     Hd = 4 * C
-    x = (torch.randn(N, H, W, C, device='cuda', generator=g) * 1.5 + 0.3).half()
-    t = torch.randn(N, H, W, C, device='cuda', generator=g).half()
+    tdt = torch.float16 if dt == 'f16' else torch.bfloat16
+    x = (torch.randn(N, H, W, C, device='cuda', generator=g) * 1.5 + 0.3).to(tdt)
+    t = torch.randn(N, H, W, C, device='cuda', generator=g).to(tdt)
     w1 = torch.randn(Hd, C, device='cuda', generator=g) / C ** 0.5
     b1 = torch.randn(Hd, device='cuda', generator=g) * 0.1
     gamma, beta = torch.rand(C, device='cuda', generator=g) + 0.5, torch.randn(C, device='cuda', generator=g) * 0.1
     w2 = torch.randn(C, Hd, device='cuda', generator=g) / Hd ** 0.5
     b2 = torch.randn(C, device='cuda', generator=g) * 0.1
-    wf, bf, colsum = eng.fold_layernorm(w1, b1, gamma, beta)
-    w2p = eng.pack_conv_weight(w2.reshape(C, Hd, 1, 1))
+    wf, bf, colsum = eng.fold_layernorm(w1, b1, gamma, beta, tdt)
+    w2p = eng.pack_conv_weight(w2.reshape(C, Hd, 1, 1), tdt)
     stats = torch.stack([torch.stack([x[..., c:c + 64].float().sum(-1), x[..., c:c + 64].float().pow(2).sum(-1)], -1) for c in range(0, C, 64)], -2)
     stats = stats.reshape(-1, C // 64, 2).contiguous()
     h = eng.conv2d_ln_nhwc(x, stats, wf, bf, colsum, act='gelu')
@@ -196,4 +198,5 @@ def test_fused_convnext_mlp_is_bit_identical_to_the_two_launch_path(eng, N, H, W
     assert torch.equal(t2, two)
     xn = torch.nn.functional.layer_norm(x.float(), (C,), gamma, beta, 1e-6)
     ref = t.float() + torch.nn.functional.gelu(xn @ w1.t() + b1) @ w2.t() + b2
-    assert (two.float() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 4e-3
+    tol = 4e-3 if dt == 'f16' else 3e-2
+    assert (two.float() - ref).abs().max().item() <= tol * ref.abs().max().item() + tol

@@ -153,3 +153,20 @@ def test_pipeline_leres_device_tail_matches_host_tail(built_lib):
     b = pipe._depth_est_leres_batch(imgs)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("CP", [16, 64])
+def test_space_to_depth_prep_p2(built_lib, CP):
+    """csb_image_prep_s2d_nhwc, P = 2 (the LeReS stem input): channel (dy*2+dx)*3 + c = normalised pixel (2Y+dy, 2X+dx), zero padded to CP; the
+    specialised one-thread-per-cell kernel against the torch formula, with and without the R/B swap, even and 4-unaligned widths."""
+    from cartoonsegmentation_b200 import engine as E
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    for (N, H, W), swap in (((2, 12, 20), False), ((1, 6, 10), True), ((3, 64, 62), True)):
+        img = torch.randint(0, 256, (N, H, W, 3), device='cuda', dtype=torch.uint8)
+        out = E.image_prep_s2d_nhwc(img, mean, std, 2, CP, swap_rb=swap)
+        src = img.flip(-1) if swap else img
+        ref = (src.float() - torch.tensor(mean, device='cuda')) / torch.tensor(std, device='cuda')
+        ref = ref.view(N, H // 2, 2, W // 2, 2, 3).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 12)
+        assert out.shape == (N, H // 2, W // 2, CP)
+        assert (out[..., :12].float() - ref).abs().max().item() < 2e-3 and not out[..., 12:].any()
