@@ -346,29 +346,45 @@ __global__ void __launch_bounds__(256) k_resample_rows(const __half* __restrict_
         lx = fx - x0;
     }
     const int oy0 = blockIdx.y * R;
+    if (MODE == 0) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int oy = oy0 + r;
-        if (oy >= Ho) break;
-        H8 out;
-        if (MODE == 0) {
+        for (int r = 0; r < R; ++r) {
+            const int oy = oy0 + r;
+            if (oy >= Ho) break;
             const int iy = min((int) floorf(oy * sh), Hi - 1);
-            out = *reinterpret_cast<const H8*>(xb + ((long long) iy * Wi + x0) * ldx);
-        } else {
+            *reinterpret_cast<H8*>(yb + (long long) oy * Wo * ldy) = *reinterpret_cast<const H8*>(xb + ((long long) iy * Wi + x0) * ldx);
+        }
+        return;
+    }
+    // bilinear: G rows at a time, all 4 G corner loads issued before the first interpolation (bytes in flight, not instructions, bound this kernel)
+    constexpr int G = 4;
+#pragma unroll
+    for (int r0 = 0; r0 < R; r0 += G) {
+        H8 raw[G][4];
+        float lyv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int oy = min(oy0 + r0 + g, Ho - 1);                  // rows past the end repeat the last row's loads (never stored)
             const float fy = MODE == 2 ? oy * sh : fmaxf((oy + 0.5f) * sh - 0.5f, 0.0f);
             const int y0 = min((int) fy, Hi - 1), y1 = min(y0 + 1, Hi - 1);
-            const float ly = fy - y0;
+            lyv[g] = fy - y0;
+            raw[g][0] = *reinterpret_cast<const H8*>(xb + ((long long) y0 * Wi + x0) * ldx);
+            raw[g][1] = *reinterpret_cast<const H8*>(xb + ((long long) y0 * Wi + x1) * ldx);
+            raw[g][2] = *reinterpret_cast<const H8*>(xb + ((long long) y1 * Wi + x0) * ldx);
+            raw[g][3] = *reinterpret_cast<const H8*>(xb + ((long long) y1 * Wi + x1) * ldx);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int oy = oy0 + r0 + g;
+            if (oy >= Ho) break;
+            const float ly = lyv[g];
             float a[8], b[8], c[8], d[8], o[8];
-            unpack8(*reinterpret_cast<const H8*>(xb + ((long long) y0 * Wi + x0) * ldx), a);
-            unpack8(*reinterpret_cast<const H8*>(xb + ((long long) y0 * Wi + x1) * ldx), b);
-            unpack8(*reinterpret_cast<const H8*>(xb + ((long long) y1 * Wi + x0) * ldx), c);
-            unpack8(*reinterpret_cast<const H8*>(xb + ((long long) y1 * Wi + x1) * ldx), d);
+            unpack8(raw[g][0], a); unpack8(raw[g][1], b); unpack8(raw[g][2], c); unpack8(raw[g][3], d);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
                 o[e] = (1.0f - ly) * ((1.0f - lx) * a[e] + lx * b[e]) + ly * ((1.0f - lx) * c[e] + lx * d[e]);
-            out = pack8(o);
+            *reinterpret_cast<H8*>(yb + (long long) oy * Wo * ldy) = pack8(o);
         }
-        *reinterpret_cast<H8*>(yb + (long long) oy * Wo * ldy) = out;
     }
 }
 
