@@ -824,8 +824,8 @@ __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpPar
     }
 }
 
-template <class T>
-__global__ void __launch_bounds__(512, 1) k_mlp_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+template <class T, int EG>
+__global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                                                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
                                                    const ConvKernelParams p, const MlpParams q) {
     extern __shared__ uint8_t smem_raw[];
@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(512, 1) k_mlp_tc(const __grid_constant__ CUten
     const uint32_t tmem_slot = bar(MB_COUNT);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int EG = 3, NEPI = 4 * EG;
+    constexpr int NEPI = 4 * EG;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -957,7 +957,8 @@ __global__ void __launch_bounds__(512, 1) k_mlp_tc(const __grid_constant__ CUten
         }
     } else {
         // ===================================================== epilogue warps: EPI1 per hidden chunk, EPI2 per tile
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        if constexpr (EG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");      // 16 epilogue warps: the pool is the CTA's launch allocation (640 x 96 = 61440): 4 x 32 x 40 + 16 x 32 x 104 = 58368
         const int qd = warp & 3, grp = (warp - 4) >> 2;
         const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && (!p.bias || ((uintptr_t) p.bias % 16 == 0));
         const uint32_t stage_any = smem_base + p.stage_off + (uint32_t) (warp - 4) * 2048u;
@@ -1057,6 +1058,10 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     q.h_bytes = (uint32_t) q.k2b * 16384u;
     q.bar_off = q.h_off + 2u * q.h_bytes;
     { const char* e = getenv("CSB_MLP_SUB16"); q.sub16 = e ? atoi(e) : 0; }     // measured (gpurun r2c28): 32-column tasks 1237 / 781 us, 16-column 1261 / 878 us
+    // CSB_MLP_EG=4: 16 epilogue warps (640 threads, 104 registers each) on 16-column tasks: 8 / 4 tasks per TMEM lane quarter split evenly over 4 warps.
+    // Measured (gpurun r2c36): 1252 / 857 us against 1238 / 836 us with 12 warps -- neither more warps nor the even split moves the GELU epilogue.
+    static const int eg = [] { const char* e = getenv("CSB_MLP_EG"); return e && atoi(e) == 4 ? 4 : 3; }();
+    if (eg == 4) q.sub16 = 1;
     ConvKernelParams p{};
     p.N = 1; p.H = 1; p.W = (int) pixels; p.Cin = hidden; p.Cout = C; p.R = p.S = 1; p.stride = 1; p.bh = 1; p.bw = kBlockM;
     p.tiles_h = 1; p.tiles_w = q.tiles_m; p.tiles_m = q.tiles_m; p.tiles_n = 1; p.block_n = C; p.in_coff = x_coff;
@@ -1064,7 +1069,7 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     p.out = y; p.out_ld = y_ld; p.out_coff = y_coff; p.is_bf16 = dtype == 1;
     p.gelu_form = g_gelu_form.load(std::memory_order_relaxed);
     p.stage_off = (q.bar_off + 8u * (MB_COUNT + 2) + 1023u) & ~1023u;
-    const size_t smem = (size_t) p.stage_off + 4 * kMaxEpiGroups * 2048 + 1024;
+    const size_t smem = (size_t) p.stage_off + 4 * 4 * 2048 + 1024;              // staging for up to 16 epilogue warps
     CSB_REQUIRE(smem <= 227 * 1024, "fused MLP: shared-memory budget exceeded");
     const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const cuuint64_t esz = 2;
@@ -1100,13 +1105,20 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     }
     static unsigned char attr_done[64] = {};
     if (csb::first_use_on_device(attr_done)) {
-        cudaFuncSetAttribute(k_mlp_tc<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__half, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     const int sms = csb::num_sms();
     const int grid = q.tiles_m < sms ? q.tiles_m : sms;
-    if (dtype == 1) k_mlp_tc<__nv_bfloat16><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
-    else k_mlp_tc<__half><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+    if (eg == 4) {
+        if (dtype == 1) k_mlp_tc<__nv_bfloat16, 4><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+        else k_mlp_tc<__half, 4><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+    } else {
+        if (dtype == 1) k_mlp_tc<__nv_bfloat16, 3><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+        else k_mlp_tc<__half, 3><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+    }
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {
         char label[160];
         snprintf(label, sizeof label, "k_mlp_tc[%lldx%d->%d->%d]", pixels, C, hidden, C);
