@@ -761,12 +761,39 @@ struct MlpParams {
     float ln_inv_c, ln_eps;
     uint32_t x_bytes, ring_off, h_off, h_bytes, bar_off;      // shared-memory layout (byte offsets from the 1 KiB-aligned base)
     int sub16;                                                // EPI1 task width: 16 accumulator columns (1) or 32 (0)
+    int diag;                                                 // CSB_MLP_DIAG (profiling only, wrong results): 1 skip the GELU, 2 skip the LayerNorm fold, 4 skip the smem store
+    int stages;                                               // weight ring depth: 3 x CG stages of 32 KiB / CG per CTA
 };
 
-constexpr int kMlpStages = 3;
-constexpr uint32_t kMlpStageBytes = 32768;
-// barriers (8 B each): full[3] empty[3] xfull xempty haccf[2] hacce[2] hsf[2] hse[2] yfull yempty
-enum { MB_FULL = 0, MB_EMPTY = 3, MB_XFULL = 6, MB_XEMPTY = 7, MB_HACCF = 8, MB_HACCE = 10, MB_HSF = 12, MB_HSE = 14, MB_YFULL = 16, MB_YEMPTY = 17, MB_COUNT = 18 };
+constexpr int kMlpMaxStages = 6;
+constexpr uint32_t kMlpStageBytes = 32768;                    // per weight chunk over the CTA group: a pair's CTAs hold half of it each
+// barriers (8 B each): full[6] empty[6] xfull xempty haccf[2] hacce[2] hsf[2] hse[2] yfull yempty
+enum { MB_FULL = 0, MB_EMPTY = 6, MB_XFULL = 12, MB_XEMPTY = 13, MB_HACCF = 14, MB_HACCE = 16, MB_HSF = 18, MB_HSE = 20, MB_YFULL = 22, MB_YEMPTY = 23, MB_COUNT = 24 };
+
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire: the leader's MMA warp consumes shared memory written by the PEER CTA's epilogue warps (they arrive with
+// release.cluster after fence.proxy.async)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spin = 1;; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(4000u) : "memory");
+        if (ok) return;
+        if ((spin & 255u) == 0) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 8000000000ll) __trap();
+        }
+    }
+}
+// arrival of an epilogue warp on a barrier that lives in the pair's leader CTA (CG = 2) or in this CTA (CG = 1)
+template <int CG>
+__device__ __forceinline__ void arrive_lead(uint32_t local_bar) {
+    if constexpr (CG == 2) mbar_arrive_cluster_release(mapa_u32(local_bar, 0));
+    else mbar_arrive(local_bar);
+}
 
 template <int NCOL>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NCOL]) {
@@ -777,7 +804,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NCOL]
 // EPI1 of one hidden chunk for one warp: its tasks are the NCOL-column slices first, first + EG, ... of the chunk's HC accumulator columns (TMEM lane
 // quarter of the warp).  Per task: tcgen05.ld -> folded LayerNorm + bias + GELU -> fp16 -> shared memory in the K-major 128B-swizzled operand layout
 // (k-block = column / 64, row m, 16 B chunk (column % 64) / 8 ^ (m & 7)).  NCOL = 16 balances 8 tasks per quarter over 3 warps as 3 / 3 / 2.
-template <class T, int NCOL, int EG>
+template <class T, int NCOL, int EG, int CG>
 __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpParams& q, int first, int j, int b, int m, int lane, uint32_t tm_lane, uint32_t hrow,
                                          uint32_t hacce_bar, uint64_t nm, uint64_t rs) {
     const int ntask = q.HC / NCOL;
@@ -786,7 +813,7 @@ __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpPar
     if (last < 0) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(hacce_bar);
+        if (lane == 0) arrive_lead<CG>(hacce_bar);
     }
     for (int t = first; t < ntask; t += EG) {
         uint32_t acc[NCOL];
@@ -794,17 +821,22 @@ __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpPar
         if (t == last) {                                             // this warp has read all it needs from the accumulator buffer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(hacce_bar);
+            if (lane == 0) arrive_lead<CG>(hacce_bar);
         }
         const int c0 = t * NCOL, n0 = j * q.HC + c0;                 // column inside the chunk, hidden unit
         float y[NCOL];
+        if (q.diag & 2) {
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) y[i] = __uint_as_float(acc[i]);
+        } else
 #pragma unroll
         for (int g = 0; g < NCOL / 4; ++g) {                         // folded LayerNorm: rstd * acc + (-mean * rstd * colsum + bias')
             const float4 c4 = __ldg(reinterpret_cast<const float4*>(q.colsum + n0) + g), b4 = __ldg(reinterpret_cast<const float4*>(q.b1 + n0) + g);
             upk2(ffma2(rs, pk2(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1])), ffma2(nm, pk2(c4.x, c4.y), pk2(b4.x, b4.y))), y[4 * g], y[4 * g + 1]);
             upk2(ffma2(rs, pk2(__uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3])), ffma2(nm, pk2(c4.z, c4.w), pk2(b4.z, b4.w))), y[4 * g + 2], y[4 * g + 3]);
         }
-        if (p.gelu_form == 1) {
+        if (q.diag & 1) {
+        } else if (p.gelu_form == 1) {
 #pragma unroll
             for (int i = 0; i < NCOL; i += 2) gelu2_tanh(y[i], y[i + 1]);
         } else {                                                     // the polynomial / sigmoid mix, pair for pair as epilogue_chunk selects it (position inside the 32-column chunk)
@@ -817,6 +849,7 @@ __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpPar
         }
         const uint32_t rowaddr = hrow + (uint32_t) (c0 >> 6) * 16384u;
         const uint32_t ck0 = (uint32_t) ((c0 & 63) >> 3);
+        if (!(q.diag & 4))
 #pragma unroll
         for (int g = 0; g < NCOL / 8; ++g)
             st_shared_v4(rowaddr + (((ck0 + (uint32_t) g) ^ (uint32_t) (m & 7)) << 4),
@@ -824,7 +857,10 @@ __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpPar
     }
 }
 
-template <class T, int EG>
+// CG = 2: a CTA pair (one TPC) works on two m-tiles with tcgen05 cta_group::2 (M = 256 per MMA): each CTA loads its own activation tile and HALF of
+// every weight chunk, so the weight stream (4.3 GB per launch from L2) crosses the L2 -> SM fabric once per pair.  Kept as an option: correct, not faster.  Barriers as in k_conv_tc<., 2>: TMA "full" barriers live in the leader and receive both CTAs' bytes; MMA completions are multicast commits;
+// the epilogue warps of both CTAs arrive on the leader's hacce / hsf / yempty barriers (cluster-scope release).
+template <class T, int EG, int CG>
 __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                                                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmC,
                                                    const ConvKernelParams p, const MlpParams q) {
@@ -836,6 +872,9 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NEPI = 4 * EG;
+    const int rank = CG == 2 ? (int) cluster_ctarank() : 0;
+    const int nstage = q.stages;
+    const uint32_t stage_bytes = kMlpStageBytes / CG;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -844,65 +883,77 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kMlpStages; ++s) { mbar_init(bar(MB_FULL + s), 1); mbar_init(bar(MB_EMPTY + s), 1); }
+        for (int s = 0; s < kMlpMaxStages; ++s) { mbar_init(bar(MB_FULL + s), 1); mbar_init(bar(MB_EMPTY + s), 1); }
         mbar_init(bar(MB_XFULL), 1); mbar_init(bar(MB_XEMPTY), 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar(MB_HACCF + b), 1); mbar_init(bar(MB_HACCE + b), NEPI);
-            mbar_init(bar(MB_HSF + b), NEPI); mbar_init(bar(MB_HSE + b), 1);
+            mbar_init(bar(MB_HACCF + b), 1); mbar_init(bar(MB_HACCE + b), NEPI * CG);
+            mbar_init(bar(MB_HSF + b), NEPI * CG); mbar_init(bar(MB_HSE + b), 1);
         }
-        mbar_init(bar(MB_YFULL), 1); mbar_init(bar(MB_YEMPTY), NEPI);
+        mbar_init(bar(MB_YFULL), 1); mbar_init(bar(MB_YEMPTY), NEPI * CG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t) kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const uint32_t tm_y = tmem_base, tm_h0 = tmem_base + (uint32_t) q.C;          // Y: columns [0, C), Hacc[b]: [C + b * HC, ...)
-    const int cta = blockIdx.x, ncta = gridDim.x;
-    const uint32_t w1_kb_bytes = (uint32_t) q.HC * 128u, w2_kb_bytes = (uint32_t) q.C * 128u;
+    const int cta = CG == 2 ? (int) (blockIdx.x >> 1) : (int) blockIdx.x, ncta = CG == 2 ? (int) (gridDim.x >> 1) : (int) gridDim.x;
+    const int ngroups = (q.tiles_m + CG - 1) / CG;                                // tiles of 128 x CG rows
+    const uint32_t w1_kb_bytes = (uint32_t) (q.HC / CG) * 128u, w2_kb_bytes = (uint32_t) (q.C / CG) * 128u;      // per CTA
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0) {
-            // ===================================================== TMA producer
+            // ===================================================== TMA producer (one per CTA; in a pair both signal the leader's full barriers)
             if (elect_one()) {
                 int stage = 0;
                 uint32_t phase = 0, xphase = 0;
+                const uint32_t full_lead0 = CG == 2 ? mapa_u32(bar(MB_FULL), 0) : bar(MB_FULL);
+                const uint32_t xfull_lead = CG == 2 ? mapa_u32(bar(MB_XFULL), 0) : bar(MB_XFULL);
                 auto load_w1 = [&](int j) {
                     mbar_wait(bar(MB_EMPTY + stage), phase ^ 1u);
-                    mbar_expect_tx(bar(MB_FULL + stage), (uint32_t) q.k1b * w1_kb_bytes);
+                    if (rank == 0) mbar_expect_tx(bar(MB_FULL + stage), (uint32_t) (CG * q.k1b) * w1_kb_bytes);
                     for (int kb = 0; kb < q.k1b; ++kb)
-                        tma_load_2d<1>(ring_base + (uint32_t) stage * kMlpStageBytes + (uint32_t) kb * w1_kb_bytes, &tmW1, bar(MB_FULL + stage), kb * 64, j * q.HC);
-                    if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+                        tma_load_2d<CG>(ring_base + (uint32_t) stage * stage_bytes + (uint32_t) kb * w1_kb_bytes, &tmW1, full_lead0 + 8u * stage, kb * 64,
+                                        j * q.HC + rank * (q.HC / CG));
+                    if (++stage == nstage) { stage = 0; phase ^= 1u; }
                 };
                 auto load_w2 = [&](int j) {
                     mbar_wait(bar(MB_EMPTY + stage), phase ^ 1u);
-                    mbar_expect_tx(bar(MB_FULL + stage), (uint32_t) q.k2b * w2_kb_bytes);
+                    if (rank == 0) mbar_expect_tx(bar(MB_FULL + stage), (uint32_t) (CG * q.k2b) * w2_kb_bytes);
                     for (int kb = 0; kb < q.k2b; ++kb)
-                        tma_load_2d<1>(ring_base + (uint32_t) stage * kMlpStageBytes + (uint32_t) kb * w2_kb_bytes, &tmW2, bar(MB_FULL + stage), j * q.HC + kb * 64, 0);
-                    if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+                        tma_load_2d<CG>(ring_base + (uint32_t) stage * stage_bytes + (uint32_t) kb * w2_kb_bytes, &tmW2, full_lead0 + 8u * stage, j * q.HC + kb * 64,
+                                        rank * (q.C / CG));
+                    if (++stage == nstage) { stage = 0; phase ^= 1u; }
                 };
-                for (int tile = cta; tile < q.tiles_m; tile += ncta) {
+                for (int grp = cta; grp < ngroups; grp += ncta) {
+                    const int tile = grp * CG + rank;                         // a tile past the end (odd tile count) loads zero rows and stores nothing
                     mbar_wait(bar(MB_XEMPTY), xphase ^ 1u);
-                    mbar_expect_tx(bar(MB_XFULL), q.x_bytes);
+                    if (rank == 0) mbar_expect_tx(bar(MB_XFULL), CG * q.x_bytes);
                     for (int kb = 0; kb < q.k1b; ++kb)
-                        tma_load_4d<1>(smem_base + (uint32_t) kb * 16384u, &tmX, bar(MB_XFULL), p.in_coff + kb * 64, tile * kBlockM, 0, 0);
+                        tma_load_4d<CG>(smem_base + (uint32_t) kb * 16384u, &tmX, xfull_lead, p.in_coff + kb * 64, tile * kBlockM, 0, 0);
                     xphase ^= 1u;
                     load_w1(0);
                     for (int j = 1; j < q.NJ; ++j) { load_w1(j); load_w2(j - 1); }
                     load_w2(q.NJ - 1);
                 }
             }
-        } else if (warp == 1) {
-            // ===================================================== MMA issuer
+        } else if (warp == 1 && rank == 0) {
+            // ===================================================== MMA issuer (the leader CTA of a pair)
             const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-            const uint32_t idesc1 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (q.HC >> 3) << 17) | ((uint32_t) (kBlockM >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (q.C >> 3) << 17) | ((uint32_t) (kBlockM >> 4) << 24);
+            const uint32_t idesc1 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (q.HC >> 3) << 17) | ((uint32_t) ((kBlockM * CG) >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (q.C >> 3) << 17) | ((uint32_t) ((kBlockM * CG) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0, xphase = 0, yphase = 0;
             // buffer b = j & 1 is used NJ / 2 times per tile: its u-th use (u = it * NJ / 2 + (j >> 1)) completes phase u of its barriers
@@ -910,42 +961,44 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
             auto gemm1 = [&](int j, bool last) {
                 const int b = j & 1;
                 const uint32_t u = ubase + (uint32_t) (j >> 1);
-                mbar_wait(bar(MB_HACCE + b), (u & 1u) ^ 1u);                     // the epilogue has read this accumulator buffer's previous contents
+                mbar_wait(bar(MB_HACCE + b), (u & 1u) ^ 1u);                     // the epilogue warps (of both CTAs) have read this accumulator buffer
                 mbar_wait(bar(MB_FULL + stage), phase);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t wb = ring_base + (uint32_t) stage * kMlpStageBytes;
+                    const uint32_t wb = ring_base + (uint32_t) stage * stage_bytes;
                     for (int kb = 0; kb < q.k1b; ++kb) {
                         const uint64_t adesc = make_desc(smem_base + (uint32_t) kb * 16384u, 128), bdesc = make_desc(wb + (uint32_t) kb * w1_kb_bytes, 128);
-                        for (int k = 0; k < 4; ++k) umma_f16<1>(tm_h0 + (uint32_t) (b * q.HC), adesc + 2u * k, bdesc + 2u * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma_f16<CG>(tm_h0 + (uint32_t) (b * q.HC), adesc + 2u * k, bdesc + 2u * k, idesc1, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit<1>(bar(MB_EMPTY + stage));
-                    umma_commit<1>(bar(MB_HACCF + b));
-                    if (last) umma_commit<1>(bar(MB_XEMPTY));                        // X tile free: the producer may load the next tile's activations
+                    umma_commit<CG>(bar(MB_EMPTY + stage));
+                    umma_commit<CG>(bar(MB_HACCF + b));
+                    if (last) umma_commit<CG>(bar(MB_XEMPTY));                       // X tile free: the producers may load the next tile's activations
                 }
                 __syncwarp();
-                if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+                if (++stage == nstage) { stage = 0; phase ^= 1u; }
             };
             auto gemm2 = [&](int j, bool last) {
                 const int b = j & 1;
-                mbar_wait(bar(MB_HSF + b), (ubase + (uint32_t) (j >> 1)) & 1u);      // the epilogue warps have written this chunk's fp16 activations
+                // the epilogue warps (of both CTAs) have written this chunk's fp16 activations
+                if constexpr (CG == 2) mbar_wait_cluster(bar(MB_HSF + b), (ubase + (uint32_t) (j >> 1)) & 1u);
+                else mbar_wait(bar(MB_HSF + b), (ubase + (uint32_t) (j >> 1)) & 1u);
                 mbar_wait(bar(MB_FULL + stage), phase);
                 if (j == 0) { mbar_wait(bar(MB_YEMPTY), yphase ^ 1u); yphase ^= 1u; } // the previous tile's output accumulator has been read
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t wb = ring_base + (uint32_t) stage * kMlpStageBytes, hb = h_base + (uint32_t) b * q.h_bytes;
+                    const uint32_t wb = ring_base + (uint32_t) stage * stage_bytes, hb = h_base + (uint32_t) b * q.h_bytes;
                     for (int kb = 0; kb < q.k2b; ++kb) {
                         const uint64_t adesc = make_desc(hb + (uint32_t) kb * 16384u, 128), bdesc = make_desc(wb + (uint32_t) kb * w2_kb_bytes, 128);
-                        for (int k = 0; k < 4; ++k) umma_f16<1>(tm_y, adesc + 2u * k, bdesc + 2u * k, idesc2, (j | kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma_f16<CG>(tm_y, adesc + 2u * k, bdesc + 2u * k, idesc2, (j | kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit<1>(bar(MB_EMPTY + stage));
-                    umma_commit<1>(bar(MB_HSE + b));
-                    if (last) umma_commit<1>(bar(MB_YFULL));
+                    umma_commit<CG>(bar(MB_EMPTY + stage));
+                    umma_commit<CG>(bar(MB_HSE + b));
+                    if (last) umma_commit<CG>(bar(MB_YFULL));
                 }
                 __syncwarp();
-                if (++stage == kMlpStages) { stage = 0; phase ^= 1u; }
+                if (++stage == nstage) { stage = 0; phase ^= 1u; }
             };
-            for (int tile = cta; tile < q.tiles_m; tile += ncta) {
+            for (int grp = cta; grp < ngroups; grp += ncta) {
                 mbar_wait(bar(MB_XFULL), xphase);
                 xphase ^= 1u;
                 tc_fence_after();
@@ -959,14 +1012,15 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
         // ===================================================== epilogue warps: EPI1 per hidden chunk, EPI2 per tile
         if constexpr (EG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");      // 16 epilogue warps: the pool is the CTA's launch allocation (640 x 96 = 61440): 4 x 32 x 40 + 16 x 32 x 104 = 58368
-        const int qd = warp & 3, grp = (warp - 4) >> 2;
+        const int qd = warp & 3, grpw = (warp - 4) >> 2;
         const bool aligned = ((p.out_ld | p.out_coff) % 8 == 0) && (!p.res_mode || ((p.res_ld | p.res_coff) % 8 == 0)) && (!p.bias || ((uintptr_t) p.bias % 16 == 0));
         const uint32_t stage_any = smem_base + p.stage_off + (uint32_t) (warp - 4) * 2048u;
         const uint32_t lane_base = ((uint32_t) (qd * 32) << 16);
-        const int nc1 = q.HC / 32, nc2 = q.C / 32;
+        const int nc2 = q.C / 32;
         uint32_t ubase = 0, yphase = 0;
-        int rot = grp;
-        for (int tile = cta; tile < q.tiles_m; tile += ncta) {
+        int rot = grpw;
+        for (int grp = cta; grp < ngroups; grp += ncta) {
+            const int tile = grp * CG + rank;
             const int m = qd * 32 + lane;
             const long long row = (long long) tile * kBlockM + m;
             const bool row_ok = row < p.W;
@@ -989,11 +1043,11 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
                 mbar_wait(bar(MB_HACCF + b), u & 1u);
                 tc_fence_after();
                 mbar_wait(bar(MB_HSE + b), (u & 1u) ^ 1u);                    // GEMM2 of the chunk that used this shared-memory buffer before has completed
-                if (q.sub16) mlp_epi1<T, 16, EG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
-                else mlp_epi1<T, 32, EG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
+                if (q.sub16) mlp_epi1<T, 16, EG, CG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
+                else mlp_epi1<T, 32, EG, CG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(MB_HSF + b));
+                if (lane == 0) arrive_lead<CG>(bar(MB_HSF + b));
             }
             ubase += (uint32_t) (q.NJ >> 1);
             // ---- EPI2: the block's output tile (bias, residual, TMA tile store), as k_conv_tc's epilogue
@@ -1003,19 +1057,19 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
             const uint32_t stage = p.tma_store ? stage_any : 0u;
             const int cw = tile * kBlockM + qd * 32;
             int last2 = -1;
-            for (int ch = grp; ch < nc2; ch += EG) last2 = ch;
+            for (int ch = grpw; ch < nc2; ch += EG) last2 = ch;
             if (last2 < 0) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(MB_YEMPTY));
+                if (lane == 0) arrive_lead<CG>(bar(MB_YEMPTY));
             }
-            for (int ch = grp; ch < nc2; ch += EG) {
+            for (int ch = grpw; ch < nc2; ch += EG) {
                 uint32_t acc[32];
                 tmem_ld32(tm_y + lane_base + (uint32_t) (ch * 32), acc);
                 if (ch == last2) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(MB_YEMPTY));
+                    if (lane == 0) arrive_lead<CG>(bar(MB_YEMPTY));
                 }
                 epilogue_chunk<T, CSB_ACT_NONE, false>(p, acc, pix, ch * 32, row_ok, aligned && ch * 32 + 32 <= p.Cout, stage, &tmC, cw, 0, 0, 0.f, 1.f, stage_any);
             }
@@ -1024,9 +1078,11 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();          // neither CTA leaves (or frees TMEM) while its peer may still signal it / read its shared memory
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t) kTmemCols) : "memory");
     }
 }
 
@@ -1054,14 +1110,21 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     q.b1 = b1; q.colsum = colsum; q.stats = stats; q.ln_nchunk = C / 64; q.ln_inv_c = 1.0f / (float) C; q.ln_eps = eps;
     q.x_bytes = (uint32_t) q.k1b * 16384u;
     q.ring_off = q.x_bytes;
-    q.h_off = q.ring_off + kMlpStages * kMlpStageBytes;
+    // CTA pairs (CSB_MLP_PAIR=1; off by default): each CTA holds half of every weight chunk (16 KiB stages, 6 deep).  Bit-identical, but measured
+    // slower (gpurun r2c38: 1706 / 1119 us against 1284 / 801 us): the kernel is bound by the per-chunk GEMM1 -> epilogue -> GEMM2 hand-offs, which the
+    // cross-CTA arrivals lengthen, not by the weight stream it halves.
+    static const int pair_env = [] { const char* e = getenv("CSB_MLP_PAIR"); return e ? atoi(e) : 0; }();
+    static const int eg = [] { const char* e = getenv("CSB_MLP_EG"); return e && atoi(e) == 4 ? 4 : 3; }();      // 12 (default) or 16 epilogue warps
+    const int cg = (pair_env && eg == 3 && q.tiles_m >= 2) ? 2 : 1;
+    q.stages = 3 * cg;
+    q.h_off = q.ring_off + 3u * kMlpStageBytes;                       // 3 x 32 KiB or 6 x 16 KiB
     q.h_bytes = (uint32_t) q.k2b * 16384u;
     q.bar_off = q.h_off + 2u * q.h_bytes;
     { const char* e = getenv("CSB_MLP_SUB16"); q.sub16 = e ? atoi(e) : 0; }     // measured (gpurun r2c28): 32-column tasks 1237 / 781 us, 16-column 1261 / 878 us
     // CSB_MLP_EG=4: 16 epilogue warps (640 threads, 104 registers each) on 16-column tasks: 8 / 4 tasks per TMEM lane quarter split evenly over 4 warps.
     // Measured (gpurun r2c36): 1252 / 857 us against 1238 / 836 us with 12 warps -- neither more warps nor the even split moves the GELU epilogue.
-    static const int eg = [] { const char* e = getenv("CSB_MLP_EG"); return e && atoi(e) == 4 ? 4 : 3; }();
     if (eg == 4) q.sub16 = 1;
+    { const char* e = getenv("CSB_MLP_DIAG"); q.diag = e ? atoi(e) : 0; }
     ConvKernelParams p{};
     p.N = 1; p.H = 1; p.W = (int) pixels; p.Cin = hidden; p.Cout = C; p.R = p.S = 1; p.stride = 1; p.bh = 1; p.bw = kBlockM;
     p.tiles_h = 1; p.tiles_w = q.tiles_m; p.tiles_m = q.tiles_m; p.tiles_n = 1; p.block_n = C; p.in_coff = x_coff;
@@ -1083,12 +1146,12 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     }
     {
         cuuint64_t wdim[2] = {(cuuint64_t) C, (cuuint64_t) hidden}, wstr[1] = {(cuuint64_t) C * esz};
-        cuuint32_t wbox[2] = {64, (cuuint32_t) q.HC}, westr[2] = {1, 1};
+        cuuint32_t wbox[2] = {64, (cuuint32_t) (q.HC / cg)}, westr[2] = {1, 1};          // a pair's CTAs load half of the chunk's rows each
         if (enc(&tmW1, dt, 2, const_cast<void*>(w1), wdim, wstr, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled(W1) failed");
         cuuint64_t vdim[2] = {(cuuint64_t) hidden, (cuuint64_t) C}, vstr[1] = {(cuuint64_t) hidden * esz};
-        cuuint32_t vbox[2] = {64, (cuuint32_t) C};
+        cuuint32_t vbox[2] = {64, (cuuint32_t) (C / cg)};
         if (enc(&tmW2, dt, 2, const_cast<void*>(w2), vdim, vstr, vbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return csb::fail(CSB_ERR_INVALID, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled(W2) failed");
@@ -1105,19 +1168,33 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     }
     static unsigned char attr_done[64] = {};
     if (csb::first_use_on_device(attr_done)) {
-        cudaFuncSetAttribute(k_mlp_tc<__half, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_mlp_tc<__half, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__half, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__half, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__half, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     const int sms = csb::num_sms();
-    const int grid = q.tiles_m < sms ? q.tiles_m : sms;
-    if (eg == 4) {
-        if (dtype == 1) k_mlp_tc<__nv_bfloat16, 4><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
-        else k_mlp_tc<__half, 4><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+    if (cg == 2 && eg == 3) {
+        const int pairs = (q.tiles_m + 1) / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned) (2 * (pairs < sms / 2 ? pairs : sms / 2))); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t) stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (dtype == 1) cudaLaunchKernelEx(&cfg, k_mlp_tc<__nv_bfloat16, 3, 2>, tmX, tmW1, tmW2, tmC, p, q);
+        else cudaLaunchKernelEx(&cfg, k_mlp_tc<__half, 3, 2>, tmX, tmW1, tmW2, tmC, p, q);
     } else {
-        if (dtype == 1) k_mlp_tc<__nv_bfloat16, 3><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
-        else k_mlp_tc<__half, 3><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+        const int grid = q.tiles_m < sms ? q.tiles_m : sms;
+        if (eg == 4) {
+            if (dtype == 1) k_mlp_tc<__nv_bfloat16, 4, 1><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+            else k_mlp_tc<__half, 4, 1><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+        } else {
+            if (dtype == 1) k_mlp_tc<__nv_bfloat16, 3, 1><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+            else k_mlp_tc<__half, 3, 1><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+        }
     }
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {
         char label[160];
