@@ -762,13 +762,15 @@ struct MlpParams {
     uint32_t x_bytes, ring_off, h_off, h_bytes, bar_off;      // shared-memory layout (byte offsets from the 1 KiB-aligned base)
     int sub16;                                                // EPI1 task width: 16 accumulator columns (1) or 32 (0)
     int diag;                                                 // CSB_MLP_DIAG (profiling only, wrong results): 1 skip the GELU, 2 skip the LayerNorm fold, 4 skip the smem store
-    int stages;                                               // weight ring depth: 3 x CG stages of 32 KiB / CG per CTA
+    int stages;                                               // weight ring depth
+    uint32_t stage_bytes;                                     // bytes of one weight chunk over the CTA group (a pair's CTAs hold half each)
+    int NB;                                                   // hidden-chunk buffers in flight (Hacc in TMEM, Hs in shared memory): 2 or 3; GEMM1 runs NB - 1 chunks ahead of GEMM2
 };
 
 constexpr int kMlpMaxStages = 6;
-constexpr uint32_t kMlpStageBytes = 32768;                    // per weight chunk over the CTA group: a pair's CTAs hold half of it each
-// barriers (8 B each): full[6] empty[6] xfull xempty haccf[2] hacce[2] hsf[2] hse[2] yfull yempty
-enum { MB_FULL = 0, MB_EMPTY = 6, MB_XFULL = 12, MB_XEMPTY = 13, MB_HACCF = 14, MB_HACCE = 16, MB_HSF = 18, MB_HSE = 20, MB_YFULL = 22, MB_YEMPTY = 23, MB_COUNT = 24 };
+constexpr int kMlpMaxBuf = 3;
+// barriers (8 B each): full[6] empty[6] xfull xempty haccf[3] hacce[3] hsf[3] hse[3] yfull yempty
+enum { MB_FULL = 0, MB_EMPTY = 6, MB_XFULL = 12, MB_XEMPTY = 13, MB_HACCF = 14, MB_HACCE = 17, MB_HSF = 20, MB_HSE = 23, MB_YFULL = 26, MB_YEMPTY = 27, MB_COUNT = 28 };
 
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -874,7 +876,8 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
     constexpr int NEPI = 4 * EG;
     const int rank = CG == 2 ? (int) cluster_ctarank() : 0;
     const int nstage = q.stages;
-    const uint32_t stage_bytes = kMlpStageBytes / CG;
+    const uint32_t stage_bytes = q.stage_bytes / CG;
+    const int NB = q.NB, LEAD = q.NB - 1;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
@@ -885,7 +888,7 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kMlpMaxStages; ++s) { mbar_init(bar(MB_FULL + s), 1); mbar_init(bar(MB_EMPTY + s), 1); }
         mbar_init(bar(MB_XFULL), 1); mbar_init(bar(MB_XEMPTY), 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kMlpMaxBuf; ++b) {
             mbar_init(bar(MB_HACCF + b), 1); mbar_init(bar(MB_HACCE + b), NEPI * CG);
             mbar_init(bar(MB_HSF + b), NEPI * CG); mbar_init(bar(MB_HSE + b), 1);
         }
@@ -944,9 +947,10 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
                     for (int kb = 0; kb < q.k1b; ++kb)
                         tma_load_4d<CG>(smem_base + (uint32_t) kb * 16384u, &tmX, xfull_lead, p.in_coff + kb * 64, tile * kBlockM, 0, 0);
                     xphase ^= 1u;
-                    load_w1(0);
-                    for (int j = 1; j < q.NJ; ++j) { load_w1(j); load_w2(j - 1); }
-                    load_w2(q.NJ - 1);
+                    for (int j = 0; j < q.NJ + LEAD; ++j) {               // the MMA warp's consumption order
+                        if (j < q.NJ) load_w1(j);
+                        if (j >= LEAD) load_w2(j - LEAD);
+                    }
                 }
             }
         } else if (warp == 1 && rank == 0) {
@@ -956,11 +960,13 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
             const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t) (q.C >> 3) << 17) | ((uint32_t) ((kBlockM * CG) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0, xphase = 0, yphase = 0;
-            // buffer b = j & 1 is used NJ / 2 times per tile: its u-th use (u = it * NJ / 2 + (j >> 1)) completes phase u of its barriers
-            uint32_t ubase = 0;                                                  // it * NJ / 2
+            // chunks use the buffers round-robin over the whole run of the CTA: the g-th chunk uses buffer g % NB for the (g / NB)-th time
+            int b1 = 0, b2 = 0;
+            uint32_t u1 = 0, u2 = 0;
             auto gemm1 = [&](int j, bool last) {
-                const int b = j & 1;
-                const uint32_t u = ubase + (uint32_t) (j >> 1);
+                const int b = b1;
+                const uint32_t u = u1;
+                if (++b1 == NB) { b1 = 0; ++u1; }
                 mbar_wait(bar(MB_HACCE + b), (u & 1u) ^ 1u);                     // the epilogue warps (of both CTAs) have read this accumulator buffer
                 mbar_wait(bar(MB_FULL + stage), phase);
                 tc_fence_after();
@@ -978,10 +984,12 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
                 if (++stage == nstage) { stage = 0; phase ^= 1u; }
             };
             auto gemm2 = [&](int j, bool last) {
-                const int b = j & 1;
+                const int b = b2;
+                const uint32_t u = u2;
+                if (++b2 == NB) { b2 = 0; ++u2; }
                 // the epilogue warps (of both CTAs) have written this chunk's fp16 activations
-                if constexpr (CG == 2) mbar_wait_cluster(bar(MB_HSF + b), (ubase + (uint32_t) (j >> 1)) & 1u);
-                else mbar_wait(bar(MB_HSF + b), (ubase + (uint32_t) (j >> 1)) & 1u);
+                if constexpr (CG == 2) mbar_wait_cluster(bar(MB_HSF + b), u & 1u);
+                else mbar_wait(bar(MB_HSF + b), u & 1u);
                 mbar_wait(bar(MB_FULL + stage), phase);
                 if (j == 0) { mbar_wait(bar(MB_YEMPTY), yphase ^ 1u); yphase ^= 1u; } // the previous tile's output accumulator has been read
                 tc_fence_after();
@@ -1002,10 +1010,10 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
                 mbar_wait(bar(MB_XFULL), xphase);
                 xphase ^= 1u;
                 tc_fence_after();
-                gemm1(0, q.NJ == 1);
-                for (int j = 1; j < q.NJ; ++j) { gemm1(j, j == q.NJ - 1); gemm2(j - 1, false); }
-                gemm2(q.NJ - 1, true);
-                ubase += (uint32_t) (q.NJ >> 1);
+                for (int j = 0; j < q.NJ + LEAD; ++j) {                       // GEMM1 runs LEAD chunks ahead of GEMM2
+                    if (j < q.NJ) gemm1(j, j == q.NJ - 1);
+                    if (j >= LEAD) gemm2(j - LEAD, j - LEAD == q.NJ - 1);
+                }
             }
         }
     } else {
@@ -1017,8 +1025,8 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
         const uint32_t stage_any = smem_base + p.stage_off + (uint32_t) (warp - 4) * 2048u;
         const uint32_t lane_base = ((uint32_t) (qd * 32) << 16);
         const int nc2 = q.C / 32;
-        uint32_t ubase = 0, yphase = 0;
-        int rot = grpw;
+        uint32_t ue = 0, yphase = 0;
+        int be = 0, rot = grpw;
         for (int grp = cta; grp < ngroups; grp += ncta) {
             const int tile = grp * CG + rank;
             const int m = qd * 32 + lane;
@@ -1036,10 +1044,11 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
             }
             const uint64_t nm = pk2(neg_mean, neg_mean), rs = pk2(rstd, rstd);
             for (int j = 0; j < q.NJ; ++j) {
-                const int b = j & 1;
+                const int b = be;
+                const uint32_t u = ue;
+                if (++be == NB) { be = 0; ++ue; }
                 const int first = rot;                                       // this warp group's chunks of the hidden chunk: first, first + EG, ...
                 if (++rot == EG) rot = 0;
-                const uint32_t u = ubase + (uint32_t) (j >> 1);
                 mbar_wait(bar(MB_HACCF + b), u & 1u);
                 tc_fence_after();
                 mbar_wait(bar(MB_HSE + b), (u & 1u) ^ 1u);                    // GEMM2 of the chunk that used this shared-memory buffer before has completed
@@ -1049,7 +1058,6 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
                 __syncwarp();
                 if (lane == 0) arrive_lead<CG>(bar(MB_HSF + b));
             }
-            ubase += (uint32_t) (q.NJ >> 1);
             // ---- EPI2: the block's output tile (bias, residual, TMA tile store), as k_conv_tc's epilogue
             mbar_wait(bar(MB_YFULL), yphase);
             yphase ^= 1u;
@@ -1105,7 +1113,11 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     EncodeTiledFn enc = encode_fn();
     if (!enc) return csb::fail(CSB_ERR_CUDA, "%s: %s", "csb_convnext_mlp_nhwc", "cuTensorMapEncodeTiled unavailable");
     MlpParams q{};
-    q.C = C; q.Hd = hidden; q.HC = C == 128 ? 128 : 64; q.NJ = hidden / q.HC; q.k1b = C / 64; q.k2b = q.HC / 64;
+    // C = 128: two chunk buffers of 128 hidden units; CSB_MLP_NB=3 = three buffers of 64 units with GEMM1 two chunks ahead of GEMM2 (measured slower,
+    // gpurun r2c39: 1366 against 1282 us -- twice the hand-offs per tile).  C = 256: two buffers of 64 units (shared memory: the X tile is 64 KiB).
+    static const int nb_env = [] { const char* e = getenv("CSB_MLP_NB"); return e ? atoi(e) : 2; }();
+    q.NB = (C == 128 && nb_env == 3) ? 3 : 2;
+    q.C = C; q.Hd = hidden; q.HC = (C == 128 && q.NB == 2) ? 128 : 64; q.NJ = hidden / q.HC; q.k1b = C / 64; q.k2b = q.HC / 64;
     q.tiles_m = (int) ((pixels + kBlockM - 1) / kBlockM);
     q.b1 = b1; q.colsum = colsum; q.stats = stats; q.ln_nchunk = C / 64; q.ln_inv_c = 1.0f / (float) C; q.ln_eps = eps;
     q.x_bytes = (uint32_t) q.k1b * 16384u;
@@ -1116,10 +1128,12 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     static const int pair_env = [] { const char* e = getenv("CSB_MLP_PAIR"); return e ? atoi(e) : 0; }();
     static const int eg = [] { const char* e = getenv("CSB_MLP_EG"); return e && atoi(e) == 4 ? 4 : 3; }();      // 12 (default) or 16 epilogue warps
     const int cg = (pair_env && eg == 3 && q.tiles_m >= 2) ? 2 : 1;
-    q.stages = 3 * cg;
-    q.h_off = q.ring_off + 3u * kMlpStageBytes;                       // 3 x 32 KiB or 6 x 16 KiB
+    q.stage_bytes = (uint32_t) q.HC * (uint32_t) C * 2u;             // W1 chunk [HC x C] = W2 chunk [C x HC]: 16 or 32 KiB
+    q.stages = (int) (98304u / q.stage_bytes) * cg;                    // 96 KiB of ring per CTA
+    if (q.stages > kMlpMaxStages) q.stages = kMlpMaxStages;
+    q.h_off = q.ring_off + (uint32_t) q.stages * (q.stage_bytes / cg);
     q.h_bytes = (uint32_t) q.k2b * 16384u;
-    q.bar_off = q.h_off + 2u * q.h_bytes;
+    q.bar_off = q.h_off + (uint32_t) q.NB * q.h_bytes;
     { const char* e = getenv("CSB_MLP_SUB16"); q.sub16 = e ? atoi(e) : 0; }     // measured (gpurun r2c28): 32-column tasks 1237 / 781 us, 16-column 1261 / 878 us
     // CSB_MLP_EG=4: 16 epilogue warps (640 threads, 104 registers each) on 16-column tasks: 8 / 4 tasks per TMEM lane quarter split evenly over 4 warps.
     // Measured (gpurun r2c36): 1252 / 857 us against 1238 / 836 us with 12 warps -- neither more warps nor the even split moves the GELU epilogue.
