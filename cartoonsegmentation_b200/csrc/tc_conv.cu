@@ -764,6 +764,8 @@ struct MlpParams {
     int diag;                                                 // CSB_MLP_DIAG (profiling only, wrong results): 1 skip the GELU, 2 skip the LayerNorm fold, 4 skip the smem store
     int stages;                                               // weight ring depth
     uint32_t stage_bytes;                                     // bytes of one weight chunk over the CTA group (a pair's CTAs hold half each)
+    int res_pf;                                               // prefetch the residual rows into L2 at tile start
+    uint32_t vec_off;                                         // shared-memory copy of colsum[Hd] | b1[Hd] (fp32), 0 = read them from global memory
     int NB;                                                   // hidden-chunk buffers in flight (Hacc in TMEM, Hs in shared memory): 2 or 3; GEMM1 runs NB - 1 chunks ahead of GEMM2
 };
 
@@ -790,6 +792,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         }
     }
 }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 // arrival of an epilogue warp on a barrier that lives in the pair's leader CTA (CG = 2) or in this CTA (CG = 1)
 template <int CG>
 __device__ __forceinline__ void arrive_lead(uint32_t local_bar) {
@@ -808,7 +815,7 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[NCOL]
 // (k-block = column / 64, row m, 16 B chunk (column % 64) / 8 ^ (m & 7)).  NCOL = 16 balances 8 tasks per quarter over 3 warps as 3 / 3 / 2.
 template <class T, int NCOL, int EG, int CG>
 __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpParams& q, int first, int j, int b, int m, int lane, uint32_t tm_lane, uint32_t hrow,
-                                         uint32_t hacce_bar, uint64_t nm, uint64_t rs) {
+                                         uint32_t hacce_bar, uint64_t nm, uint64_t rs, uint32_t vec) {
     const int ntask = q.HC / NCOL;
     int last = -1;
     for (int t = first; t < ntask; t += EG) last = t;
@@ -833,7 +840,14 @@ __device__ __forceinline__ void mlp_epi1(const ConvKernelParams& p, const MlpPar
         } else
 #pragma unroll
         for (int g = 0; g < NCOL / 4; ++g) {                         // folded LayerNorm: rstd * acc + (-mean * rstd * colsum + bias')
-            const float4 c4 = __ldg(reinterpret_cast<const float4*>(q.colsum + n0) + g), b4 = __ldg(reinterpret_cast<const float4*>(q.b1 + n0) + g);
+            float4 c4, b4;
+            if (vec) {                                               // staged once per CTA: with ~218 KiB of shared memory in use the L1 keeps ~10 KiB, and the
+                c4 = ld_shared_f4(vec + (uint32_t) (n0 + 4 * g) * 4u);    // per-task __ldg of these vectors was the top stall of the kernel (ncu: long_scoreboard)
+                b4 = ld_shared_f4(vec + (uint32_t) (q.Hd + n0 + 4 * g) * 4u);
+            } else {
+                c4 = __ldg(reinterpret_cast<const float4*>(q.colsum + n0) + g);
+                b4 = __ldg(reinterpret_cast<const float4*>(q.b1 + n0) + g);
+            }
             upk2(ffma2(rs, pk2(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1])), ffma2(nm, pk2(c4.x, c4.y), pk2(b4.x, b4.y))), y[4 * g], y[4 * g + 1]);
             upk2(ffma2(rs, pk2(__uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3])), ffma2(nm, pk2(c4.z, c4.w), pk2(b4.z, b4.w))), y[4 * g + 2], y[4 * g + 3]);
         }
@@ -1027,6 +1041,14 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
         const int nc2 = q.C / 32;
         uint32_t ue = 0, yphase = 0;
         int be = 0, rot = grpw;
+        const uint32_t vec = q.vec_off ? smem_base + q.vec_off : 0u;
+        if (vec) {                                                   // colsum | b1 -> shared memory, once per CTA (epilogue warps only: named barrier 1)
+            for (int i = (int) threadIdx.x - 128; i < q.Hd; i += NEPI * 32) {
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(vec + (uint32_t) i * 4u), "f"(__ldg(q.colsum + i)) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(vec + (uint32_t) (q.Hd + i) * 4u), "f"(__ldg(q.b1 + i)) : "memory");
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(NEPI * 32) : "memory");
+        }
         for (int grp = cta; grp < ngroups; grp += ncta) {
             const int tile = grp * CG + rank;
             const int m = qd * 32 + lane;
@@ -1043,6 +1065,10 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
                 neg_mean = -mean * rstd;
             }
             const uint64_t nm = pk2(neg_mean, neg_mean), rs = pk2(rstd, rstd);
+            if (q.res_pf && grpw == 0 && p.res_mode && row_ok) {     // the residual row EPI2 will add: pull it into L2 now (EPI2's loads were exposed HBM latency)
+                const char* rrow = reinterpret_cast<const char*>(reinterpret_cast<const T*>(p.residual) + pix * p.res_ld + p.res_coff);
+                for (int o = 0; o < q.C * 2; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + o));
+            }
             for (int j = 0; j < q.NJ; ++j) {
                 const int b = be;
                 const uint32_t u = ue;
@@ -1052,8 +1078,8 @@ __global__ void __launch_bounds__(128 * (EG + 1), 1) k_mlp_tc(const __grid_const
                 mbar_wait(bar(MB_HACCF + b), u & 1u);
                 tc_fence_after();
                 mbar_wait(bar(MB_HSE + b), (u & 1u) ^ 1u);                    // GEMM2 of the chunk that used this shared-memory buffer before has completed
-                if (q.sub16) mlp_epi1<T, 16, EG, CG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
-                else mlp_epi1<T, 32, EG, CG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs);
+                if (q.sub16) mlp_epi1<T, 16, EG, CG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs, vec);
+                else mlp_epi1<T, 32, EG, CG>(p, q, first, j, b, m, lane, tm_h0 + lane_base, h_base + (uint32_t) b * q.h_bytes + (uint32_t) m * 128u, bar(MB_HACCE + b), nm, rs, vec);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) arrive_lead<CG>(bar(MB_HSF + b));
@@ -1146,7 +1172,12 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     p.out = y; p.out_ld = y_ld; p.out_coff = y_coff; p.is_bf16 = dtype == 1;
     p.gelu_form = g_gelu_form.load(std::memory_order_relaxed);
     p.stage_off = (q.bar_off + 8u * (MB_COUNT + 2) + 1023u) & ~1023u;
-    const size_t smem = (size_t) p.stage_off + 4 * 4 * 2048 + 1024;              // staging for up to 16 epilogue warps
+    // [X | ring | Hs | barriers | pad | epilogue staging (2 KiB per epilogue warp) | colsum, b1 copies]
+    static const int vec_env = [] { const char* e = getenv("CSB_MLP_VEC_SMEM"); return e ? atoi(e) : 1; }();
+    { const char* e = getenv("CSB_MLP_RES_PF"); q.res_pf = e ? atoi(e) : 1; }
+    const uint32_t staging = (uint32_t) (4 * eg) * 2048u, vec_bytes = 2u * (uint32_t) hidden * 4u;
+    q.vec_off = (vec_env && (size_t) p.stage_off + staging + vec_bytes + 1024 <= 227 * 1024) ? p.stage_off + staging : 0u;
+    const size_t smem = (size_t) p.stage_off + staging + (q.vec_off ? vec_bytes : 0u) + 1024;
     CSB_REQUIRE(smem <= 227 * 1024, "fused MLP: shared-memory budget exceeded");
     const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const cuuint64_t esz = 2;
