@@ -260,6 +260,11 @@ def profile_detail(lib, fn):
             os.environ.pop("CSB_PROFILE_DETAIL", None)
         else:
             os.environ["CSB_PROFILE_DETAIL"] = old
+    return aggregate_detail(prof)
+
+
+def aggregate_detail(prof):
+    """{detailed launch label: {ms, count}} -> {kernel: {ms, count, gflop, gbytes}} (pure: unit-tested in tests/test_host_logic_cpu.py)"""
     agg = {}
     for label, v in prof.items():
         m = CONV_LABEL.match(label)

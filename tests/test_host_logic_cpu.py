@@ -161,3 +161,32 @@ def test_lazy_rescaling_online_softmax_matches_attention():
     out = o / l[:, None]
     rr = np.sqrt(((out - ref) ** 2).mean() / (ref ** 2).mean())
     assert rr < 1e-3 and rescales < (Tp // 64) * ((T + 31) // 32)              # exact enough, and genuinely lazy
+
+
+def test_bench_roofline_accounting_from_launch_labels():
+    """bench.aggregate_detail: FLOPs / compulsory bytes of the tensor-core launches from their detailed profile labels (what roofline.achieved,
+    algorithmic_bytes_per_launch and conv_engine are built from)."""
+    import bench
+    prof = {
+        "k_conv_tc[32x64x64x512->2048 k1x1 s1 d1 g1 act3 res0]": {"ms": 10.0, "count": 27},
+        "k_conv_tc[32x128x128x256->256 k3x3 s2 d1 g1 act2 res2]": {"ms": 1.0, "count": 1},
+        "k_conv_halo[32x40x40x1024->1024 k3x3 s1 d1 g32 act1 res0]": {"ms": 2.0, "count": 22},
+        "k_mlp_tc[2097152x128->512->128]": {"ms": 3.6, "count": 3},
+        "k_layernorm": {"ms": 1.2, "count": 7},
+    }
+    agg = bench.aggregate_detail(prof)
+    px = 32 * 64 * 64
+    assert agg["k_conv_tc"]["count"] == 28 and abs(agg["k_conv_tc"]["ms"] - 11.0) < 1e-9
+    g1 = 27 * 2.0 * px * 2048 * 512 / 1e9
+    g2 = 2.0 * 32 * 64 * 64 * 256 * 9 * 256 / 1e9                               # stride 2: 64 x 64 output pixels
+    assert abs(agg["k_conv_tc"]["gflop"] - (g1 + g2)) < 1e-6 * (g1 + g2)
+    b1 = 27 * (2.0 * px * (512 + 2048) + 2.0 * 2048 * 512) / 1e9
+    b2 = (2.0 * 32 * (128 * 128 * 256 + 64 * 64 * 256 * 2) + 2.0 * 256 * 9 * 256) / 1e9      # residual read counted
+    assert abs(agg["k_conv_tc"]["gbytes"] - (b1 + b2)) < 1e-6 * (b1 + b2)
+    gh = 22 * 2.0 * 32 * 40 * 40 * 1024 * 9 * (1024 // 32) / 1e9                # grouped: the group-sparse count
+    assert abs(agg["k_conv_halo"]["gflop"] - gh) < 1e-6 * gh
+    gm = 3 * 2.0 * 2.0 * 2097152 * 128 * 512 / 1e9                              # two GEMMs per fused MLP launch
+    assert abs(agg["k_mlp_tc"]["gflop"] - gm) < 1e-6 * gm
+    bm = 3 * (3.0 * 2097152 * 128 * 2 + 2.0 * 128 * 512 * 2 + 2097152 * 2 * 8) / 1e9
+    assert abs(agg["k_mlp_tc"]["gbytes"] - bm) < 1e-6 * bm
+    assert agg["k_layernorm"] == {"ms": 1.2, "count": 7, "gflop": 0.0}
