@@ -1153,7 +1153,7 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     // cross-CTA arrivals lengthen, not by the weight stream it halves.
     static const int pair_env = [] { const char* e = getenv("CSB_MLP_PAIR"); return e ? atoi(e) : 0; }();
     static const int eg = [] { const char* e = getenv("CSB_MLP_EG"); return e && atoi(e) == 4 ? 4 : 3; }();      // 12 (default) or 16 epilogue warps
-    const int cg = (pair_env && eg == 3 && q.tiles_m >= 2) ? 2 : 1;
+    const int cg = (pair_env && eg == 3 && dtype == 0 && q.tiles_m >= 2) ? 2 : 1;      // (the experimental forms are built for fp16 only)
     q.stage_bytes = (uint32_t) q.HC * (uint32_t) C * 2u;             // W1 chunk [HC x C] = W2 chunk [C x HC]: 16 or 32 KiB
     q.stages = (int) (98304u / q.stage_bytes) * cg;                    // 96 KiB of ring per CTA
     if (q.stages > kMlpMaxStages) q.stages = kMlpMaxStages;
@@ -1163,7 +1163,8 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     { const char* e = getenv("CSB_MLP_SUB16"); q.sub16 = e ? atoi(e) : 0; }     // measured (gpurun r2c28): 32-column tasks 1237 / 781 us, 16-column 1261 / 878 us
     // CSB_MLP_EG=4: 16 epilogue warps (640 threads, 104 registers each) on 16-column tasks: 8 / 4 tasks per TMEM lane quarter split evenly over 4 warps.
     // Measured (gpurun r2c36): 1252 / 857 us against 1238 / 836 us with 12 warps -- neither more warps nor the even split moves the GELU epilogue.
-    if (eg == 4) q.sub16 = 1;
+    const int eg_run = (eg == 4 && dtype == 0) ? 4 : 3;
+    if (eg_run == 4) q.sub16 = 1;
     { const char* e = getenv("CSB_MLP_DIAG"); q.diag = e ? atoi(e) : 0; }
     ConvKernelParams p{};
     p.N = 1; p.H = 1; p.W = (int) pixels; p.Cin = hidden; p.Cout = C; p.R = p.S = 1; p.stride = 1; p.bh = 1; p.bw = kBlockM;
@@ -1175,7 +1176,7 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
     // [X | ring | Hs | barriers | pad | epilogue staging (2 KiB per epilogue warp) | colsum, b1 copies]
     static const int vec_env = [] { const char* e = getenv("CSB_MLP_VEC_SMEM"); return e ? atoi(e) : 1; }();
     { const char* e = getenv("CSB_MLP_RES_PF"); q.res_pf = e ? atoi(e) : 1; }
-    const uint32_t staging = (uint32_t) (4 * eg) * 2048u, vec_bytes = 2u * (uint32_t) hidden * 4u;
+    const uint32_t staging = (uint32_t) (4 * eg_run) * 2048u, vec_bytes = 2u * (uint32_t) hidden * 4u;
     q.vec_off = (vec_env && (size_t) p.stage_off + staging + vec_bytes + 1024 <= 227 * 1024) ? p.stage_off + staging : 0u;
     const size_t smem = (size_t) p.stage_off + staging + (q.vec_off ? vec_bytes : 0u) + 1024;
     CSB_REQUIRE(smem <= 227 * 1024, "fused MLP: shared-memory budget exceeded");
@@ -1216,12 +1217,10 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
         cudaFuncSetAttribute(k_mlp_tc<__half, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(k_mlp_tc<__half, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(k_mlp_tc<__half, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_mlp_tc<__nv_bfloat16, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     const int sms = csb::num_sms();
-    if (cg == 2 && eg == 3) {
+    if (cg == 2) {
         const int pairs = (q.tiles_m + 1) / 2;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned) (2 * (pairs < sms / 2 ? pairs : sms / 2))); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t) stream;
@@ -1229,17 +1228,12 @@ extern "C" int csb_convnext_mlp_nhwc(const void* x, int x_ld, int x_coff, long l
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (dtype == 1) cudaLaunchKernelEx(&cfg, k_mlp_tc<__nv_bfloat16, 3, 2>, tmX, tmW1, tmW2, tmC, p, q);
-        else cudaLaunchKernelEx(&cfg, k_mlp_tc<__half, 3, 2>, tmX, tmW1, tmW2, tmC, p, q);
+        cudaLaunchKernelEx(&cfg, k_mlp_tc<__half, 3, 2>, tmX, tmW1, tmW2, tmC, p, q);
     } else {
         const int grid = q.tiles_m < sms ? q.tiles_m : sms;
-        if (eg == 4) {
-            if (dtype == 1) k_mlp_tc<__nv_bfloat16, 4, 1><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
-            else k_mlp_tc<__half, 4, 1><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
-        } else {
-            if (dtype == 1) k_mlp_tc<__nv_bfloat16, 3, 1><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
-            else k_mlp_tc<__half, 3, 1><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
-        }
+        if (eg_run == 4) k_mlp_tc<__half, 4, 1><<<grid, 640, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+        else if (dtype == 1) k_mlp_tc<__nv_bfloat16, 3, 1><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
+        else k_mlp_tc<__half, 3, 1><<<grid, 512, smem, (cudaStream_t) stream>>>(tmX, tmW1, tmW2, tmC, p, q);
     }
     if (csb::g_profiling.load(std::memory_order_relaxed) == 2) {
         char label[160];
